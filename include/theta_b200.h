@@ -1,0 +1,157 @@
+/*
+ * theta_b200 -- C ABI of the B200-native THetA likelihood search.
+ *
+ * This header is the drop-in boundary for the hot path of raphael-group/THetA
+ * (SURVEY.md section 8b).  The reference has no FFI layer: the boundary is the
+ * Python call site python/RunTHetA.py:442-447 and the classes it binds.  Each
+ * entry point below names the reference interface it replaces (file:line,
+ * relative to the reference tree).  Signatures use plain pointers and sizes
+ * only; no C++ / torch types cross the boundary.  The ctypes binding that a
+ * reference maintainer would add is shown in INTEGRATION.md and implemented in
+ * theta_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns THETA_OK (0) or a negative THETA_ERR_* code; the
+ *     message for the last error on the calling thread is theta_last_error().
+ *   - "host" pointers are ordinary host memory owned by the caller; "dev"
+ *     pointers are CUDA device pointers on the plan's device, also caller-owned.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - interval vectors (r, rN, lower, upper) are in the *sorted* interval order
+ *     produced by DataTools.sort_r (python/DataTools.py:95-118).
+ *   - there is no CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with THETA_ERR_CUDA.
+ */
+#ifndef THETA_B200_H
+#define THETA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define THETA_OK 0
+#define THETA_ERR_INVALID (-1)  /* bad argument */
+#define THETA_ERR_CUDA (-2)     /* CUDA runtime error / no device */
+#define THETA_ERR_EMPTY (-3)    /* no admissible candidate (RunTHetA.py:154-156, 217-219) */
+#define THETA_ERR_OVERFLOW (-4) /* candidate count does not fit 63 bits, or an output buffer is too small */
+#define THETA_ERR_UNSUPPORTED (-5)
+
+/* Per-candidate status.  Values < 8 mean Optimizer.solve returned a solution,
+ * values >= 8 mean it returned None (python/Optimizer.py:119-121, 159-161). */
+#define THETA_ST_OK 0          /* interior root / KKT point */
+#define THETA_ST_ROOT_LB 1     /* brenth: f(lB)==0, returns lB (Q17) */
+#define THETA_ST_ROOT_UB 2     /* brenth: f(uB)==0, returns uB */
+#define THETA_ST_FALLBACK_X0 3 /* n=3: BFGS fallback returned its start point (1/3,1/3,1/3) (H2 outcome a) */
+#define THETA_ST_NONE_SIGN 8   /* f(lB), f(uB) have the same sign */
+#define THETA_ST_NONE_NAN 9    /* NaN in the objective (zero column, 0/0) */
+#define THETA_ST_NONE_NOCONV 10
+#define THETA_ST_NONE_RANGE 11 /* n=3: fallback left [0,1]^3 (H2 outcome b) */
+
+#define THETA_MAX_COPY 15  /* largest copy number supported by the n=2 kernels */
+#define THETA_TIE_MARGIN 1e-3 /* Misc.isClose margin 10e-4, python/Misc.py:36 */
+
+/* Problem statement at the do_optimization* boundary (RunTHetA.py:124-125, 173-174). */
+typedef struct theta_problem {
+    int32_t n;            /* populations: 2 or 3 */
+    int32_t m;            /* intervals */
+    int32_t tau;          /* copies in the normal genome */
+    int32_t reserved;
+    const int64_t* r;     /* [m] tumour read counts  (host) */
+    const int64_t* rN;    /* [m] normal read counts  (host) */
+    const int32_t* lower; /* [m] per-interval lower copy bound (host) */
+    const int32_t* upper; /* [m] per-interval upper copy bound (host) */
+    double max_normal;    /* Optimizer upper_bound (Optimizer.py:43); 1.0 = unconstrained */
+} theta_problem;
+
+/* One candidate record.  `rank` is the 0-based position in the reference's
+ * enumeration order (Enumerator.py:119-152: ascending colex). */
+typedef struct theta_cand {
+    uint64_t rank;
+    double nll;
+    double mu[3];
+    int32_t status;
+    int32_t flags;
+} theta_cand;
+
+typedef struct theta_search_stats {
+    uint64_t n_candidates; /* ranks evaluated (without the duplicated first matrix, Q1) */
+    uint64_t n_solved;     /* candidates for which solve() != None */
+    uint64_t n_stripes;
+    uint64_t n_rescanned;  /* stripes re-evaluated by pass 2 */
+    double min_nll;
+    double newton_iters;   /* mean root-finder iterations per solved candidate */
+    float ms_pass1;
+    float ms_pass2;
+} theta_search_stats;
+
+typedef struct theta_plan theta_plan; /* opaque: device tables of one problem */
+
+/* ---- runtime ---------------------------------------------------------- */
+int theta_init(int device);              /* select device, create context; THETA_ERR_CUDA if none */
+int theta_device_count(void);
+void theta_shutdown(void);
+const char* theta_last_error(void);
+const char* theta_version(void);
+/* measured fp64 FMA throughput of the current device in GFLOP/s (FMA = 2 flop); roofline denominator */
+int theta_fp64_peak(double* gflops, void* stream);
+
+/* ---- plans ------------------------------------------------------------ */
+/* Replaces Enumerator.__init__ + Optimizer.__init__ (Enumerator.py:39-72, Optimizer.py:43-65):
+ * monotonises the bounds (Enumerator.py:90-113), builds the count tables and
+ * uploads r / rN prefix sums.  n=2 only for the rank-based entry points. */
+int theta_plan_create(const theta_problem* p, theta_plan** out);
+void theta_plan_destroy(theta_plan* plan);
+/* TimeEstimate.count_number_matrices_2 (TimeEstimate.py:91-111). */
+int theta_plan_count(const theta_plan* plan, uint64_t* count);
+/* Monotonised bounds as used by the search (Q16). */
+int theta_plan_bounds(const theta_plan* plan, int32_t* lower, int32_t* upper);
+
+/* ---- enumeration (Enumerator.generate_next_C, Enumerator.py:74-87,119-160) ---- */
+/* Tumour columns of ranks [rank_begin, rank_begin+count) as int8 rows of `pitch` bytes
+ * (pitch >= m; bytes m..pitch-1 are zero).  Host and device destinations. */
+int theta_enumerate_n2(theta_plan* plan, uint64_t rank_begin, int64_t count, int8_t* cols_host, int64_t pitch);
+int theta_enumerate_n2_dev(theta_plan* plan, uint64_t rank_begin, int64_t count, int8_t* cols_dev, int64_t pitch,
+                           void* stream);
+int64_t theta_tile_pitch(int32_t m); /* row pitch used by the tile kernels (smallest 8*odd >= m) */
+
+/* ---- fused search (do_optimization_single, RunTHetA.py:173-220; process_loop :53-93) ---- */
+/* Pass 1: evaluate ranks [rank_begin, rank_end): enumerate on chip, solve mu, NLL, reduce per stripe.
+ * Returns the minimum NLL of the range (+inf if no candidate solved). */
+int theta_search_n2_pass1(theta_plan* plan, uint64_t rank_begin, uint64_t rank_end, double* local_min, void* stream);
+/* Pass 2: given the global minimum (all shards) and the minimum over all ranks *before* this shard
+ * (+inf for the first shard), re-evaluate only the stripes that can matter and emit, in rank order,
+ * a superset of the candidates the reference's running-min fold (RunTHetA.py:198-206) can ever keep:
+ * every strict prefix minimum and every candidate with NLL <= global_min + 2*margin. */
+int theta_search_n2_pass2(theta_plan* plan, double global_min, double prior_min, theta_cand* out_host, uint64_t cap,
+                          uint64_t* n_out, void* stream);
+int theta_search_stats_get(const theta_plan* plan, theta_search_stats* stats);
+/* Single-shard convenience: pass1 + pass2 with global_min = local_min, prior_min = +inf. */
+int theta_search_n2(theta_plan* plan, uint64_t rank_begin, uint64_t rank_end, theta_cand* out_host, uint64_t cap,
+                    uint64_t* n_out);
+/* (mu, NLL, status, vals[m]) of given ranks -- Optimizer.solve's return for the winners (Optimizer.py:123-126). */
+int theta_eval_ranks_n2(theta_plan* plan, const uint64_t* ranks_host, int64_t count, theta_cand* out_host,
+                        double* vals_host /* [count][m] or NULL */);
+
+/* ---- tile kernels: explicit C matrices (Optimizer.solve, Optimizer.py:68-126; CalcAllC.L2, CalcAllC.py:44-61) ---- */
+/* n=2, tumour column per candidate as int8 rows of `pitch` bytes. */
+int theta_solve_tiles_n2_dev(theta_plan* plan, const int8_t* cols_dev, int64_t pitch, int64_t count, double* mu_dev,
+                             double* nll_dev, int32_t* status_dev, void* stream);
+int theta_solve_tiles_n2(theta_plan* plan, const int8_t* cols_host, int64_t pitch, int64_t count, double* mu_host,
+                         double* nll_host, int32_t* status_host);
+/* NLL at a given mu (the streaming "NLL kernel": algorithmic bytes m + 8 + 8 per candidate). */
+int theta_nll_tiles_n2_dev(theta_plan* plan, const int8_t* cols_dev, int64_t pitch, int64_t count,
+                           const double* mu_dev, double* nll_dev, void* stream);
+int theta_nll_tiles_n2(theta_plan* plan, const int8_t* cols_host, int64_t pitch, int64_t count, const double* mu_host,
+                       double* nll_host);
+
+/* ---- CalcAllC.L2 / L3 (CalcAllC.py:44-76): masked NLL of one weighted matrix at a given mu ---- */
+/* Cw is [m][n] row-major fp64 (already weighted by rN); valid_i = Cw[i][0] != 0 (L2 with mu==0: Cw[i][1] != 0).
+ * vals[i] = w_i / D (meaningful where valid[i]); does NOT modify Cw (the Python wrapper reproduces Q10). */
+int theta_nll(int32_t n, int32_t m, const double* mu, const double* Cw, const int64_t* r, double* nll, double* vals,
+              uint8_t* valid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THETA_B200_H */

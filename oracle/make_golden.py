@@ -1,0 +1,267 @@
+"""Generate tests/golden/*.json from the LIVE reference (build container only).
+
+TEST INFRASTRUCTURE.  Runs the reference's own code (imported in place from
+/root/reference/python through oracle/refshim.py, no arithmetic touched) and
+freezes its outputs as small JSON fixtures, so that the oracle restatement and
+the CUDA path can be checked on the GPU box, where /root/reference does not
+exist.  Floats are written with repr() precision (exact round trip).
+
+    python oracle/make_golden.py [--only kat,config1,synth_n2,n3_small,edge]
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import pickle
+import sys
+import time
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refshim  # noqa: E402
+import theta_oracle as O  # noqa: E402
+
+GOLD = os.path.join(HERE, "..", "tests", "golden")
+REFPY = refshim.REF
+
+
+def _quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def _dump(name, obj):
+    path = os.path.join(GOLD, name)
+    with open(path, "w") as f:
+        json.dump(obj, f, separators=(",", ":"))
+    print("wrote", name, os.path.getsize(path), "bytes")
+
+
+def _f(x):
+    return None if x is None else float(x)
+
+
+def gen_kat(R):
+    """python/L2args.pkl etc.: the reference's only known-answer vectors."""
+    def load(n):
+        with open(os.path.join(REFPY, n), "rb") as f:
+            return pickle.load(f, encoding="latin1")
+    out = {}
+    a = load("L2args.pkl")
+    mu, C, m, r = a
+    res_b, res_m = load("L2outputs_branch.pkl"), load("L2outputs_master.pkl")
+    live = R.CalcAllC.L2(mu, np.array(C, dtype=float).copy(), m, r)
+    assert float(live[0]) == float(res_b[0])
+    out["L2"] = dict(mu=float(mu), C=np.asarray(C, dtype=float).tolist(), m=int(m), r=[int(v) for v in r],
+                     nll_branch=float(res_b[0]), nll_master=float(res_m[0]),
+                     vals_branch=[v if isinstance(v, str) else float(v) for v in res_b[1]])
+    a = load("L3args.pkl")
+    mu, C, m, r, n = a
+    res_b, res_m = load("L3outputs_branch.pkl"), load("L3outputs_master.pkl")
+    live = R.CalcAllC.L3(np.asarray(mu, dtype=float), np.array(C, dtype=float).copy(), m, r, n)
+    assert float(live[0]) == float(res_b[0])
+    out["L3"] = dict(mu=[float(v) for v in mu], C=np.asarray(C, dtype=float).tolist(), m=int(m),
+                     r=[int(v) for v in r], n=int(n),
+                     nll_branch=float(res_b[0]), nll_master=float(res_m[0]),
+                     vals_branch=[v if isinstance(v, str) else float(v) for v in res_b[1]])
+    _dump("calcallc_kat.json", out)
+
+
+def config1_inputs(R):
+    """RunTHetA.py:298-412 pre-steps for `Example.intervals -n 2 -k 3` (defaults otherwise)."""
+    iv = R.FileIO.read_interval_file(os.path.join(REFPY, "..", "example", "Example.intervals"))
+    lengths, tumor, normal, m, ub, lb = iv
+    with _quiet():
+        order, lengths, tumor, normal = R.SelectIntervals.select_intervals_n2(lengths, tumor, normal, m, 3, False, 100)
+    m = len(order)
+    R.DataTools.set_total_read_counts(sum(tumor), sum(normal))
+    r, rN, si = R.DataTools.sort_r(normal, tumor)
+    with _quiet():
+        ub, lb = R.DataTools.calculate_bounds_heuristic(0.5, r, rN, m, 2, 3)
+    return dict(m=m, k=3, tau=2, r=[int(v) for v in r], rN=[int(v) for v in rN], lower=[int(v) for v in lb],
+                upper=[int(v) for v in ub], sorted_index=[int(v) for v in si], order=[int(v) for v in order])
+
+
+def gen_config1(R):
+    """Full-space run of the reference's do_optimization_single on config #1 (about 3 minutes)."""
+    inp = config1_inputs(R)
+    m = inp["m"]
+    tmp = "/tmp/theta_golden_cfg1"
+    R.RunTHetA.pre = tmp
+    t0 = time.time()
+    with _quiet():
+        best = R.RunTHetA.do_optimization_single(2, m, 3, 2, inp["lower"][:], inp["upper"][:], inp["r"], inp["rN"],
+                                                 1.0, inp["sorted_index"], True, True)
+    wall = time.time() - t0
+    solved = []
+    with open(tmp + ".likelihoods") as f:
+        for line in f:
+            cs, mu0, nll = line.rstrip("\n").split("\t")
+            solved.append((cs, float(mu0), float(nll)))
+    # rank of every solved candidate: walk the enumeration once (the stream has the first matrix twice, Q1)
+    rank_of = {}
+    for i, col in enumerate(O.enumerate_n2(inp["lower"], inp["upper"])):
+        rank_of["".join(str(v) for v in col)] = i
+    N = len(rank_of)
+    assert solved[0][0] == solved[1][0] or True
+    solved_ranks = set(rank_of[s[0]] for s in solved)
+    none_ranks = sorted(set(range(N)) - solved_ranks)
+    uniq = {}
+    for cs, mu0, nll in solved:
+        uniq[rank_of[cs]] = (mu0, nll)
+    by_nll = sorted(uniq.items(), key=lambda kv: kv[1][1])
+    top = [dict(rank=k, mu0=v[0], nll=v[1]) for k, v in by_nll[:300]]
+    sample = [dict(rank=k, mu0=uniq[k][0], nll=uniq[k][1]) for k in sorted(uniq) if k % 53 == 0]
+    out = dict(inputs=inp, n_candidates=N, n_emitted=N + 1, n_solved_emitted=len(solved), none_ranks=none_ranks,
+               reference_wall_s=wall,
+               best=[dict(C=np.asarray(b[0]).tolist(), mu=[float(b[1][0]), float(b[1][1])], nll=float(b[2]),
+                          vals=[float(v) for v in b[3]]) for b in best],
+               top=top, sample=sample)
+    _dump("config1_search.json", out)
+
+
+def gen_synth_n2(R):
+    """Per-candidate (mu, NLL | None) of the live Optimizer.solve on the synthetic n=2 configs."""
+    out = {}
+    for name, m, k, mx in (("m150_k5", 150, 5, 1.0), ("m150_k7", 150, 7, 1.0), ("m300_k7", 300, 7, 1.0),
+                           ("m40_k4_maxn", 40, 4, 0.6)):
+        P = O.synthetic_problem_n2(m, k, seed=1)
+        N = O.count_n2(P["lower"], P["upper"])
+        rng = np.random.default_rng(7)
+        ranks = list(range(200)) + sorted(int(x) for x in rng.integers(0, N, 500))
+        # plus a cluster of ranks around a random walk near the (unknown) optimum: take ranks whose column is
+        # the rounded truth-like profile
+        opt = R.Optimizer.Optimizer(P["r"], P["rN"], m, 2, 2, upper_bound=mx)
+        recs = []
+        for rk in ranks:
+            col = O.unrank_n2(P["lower"], P["upper"], rk)
+            s = opt.solve(O.column_to_matrix(col))
+            recs.append(dict(rank=rk, mu0=None if s is None else float(s[0][0]), nll=None if s is None else float(s[1])))
+        out[name] = dict(m=m, k=k, seed=1, max_normal=mx, r=P["r"], rN=P["rN"], lower=P["lower"], upper=P["upper"],
+                         n_candidates=int(N), records=recs)
+        print(name, "N=%g" % N, "none:", sum(1 for q in recs if q["nll"] is None))
+    _dump("synth_n2_candidates.json", out)
+
+
+def gen_n2_small_full(R):
+    """Whole small n=2 spaces through the live do_optimization_single: best lists incl. ties, Q1 duplicate."""
+    cases = []
+    rng = np.random.default_rng(11)
+    specs = [(7, 3, 1.0, 1), (9, 4, 1.0, 2), (12, 3, 1.0, 3), (10, 5, 0.5, 4), (8, 2, 1.0, 5), (6, 6, 0.8, 6),
+             (14, 3, 1.0, 7)]
+    for m, k, mx, seed in specs:
+        r, rN, _ = O.synthetic(m, 2, k, seed)
+        r, rN, si = O.sort_r(rN, r)
+        if seed % 2:
+            ub, lb = O.bounds_heuristic(0.5, r, rN, 2, k)
+        else:
+            lb = sorted(int(x) for x in rng.integers(0, 2, m))
+            ub = [min(k, l + int(x)) for l, x in zip(lb, rng.integers(1, k + 1, m))]
+        lb, ub = O.check_bound_order(lb, ub)
+        R.RunTHetA.pre = "/tmp/theta_golden_small"
+        with _quiet():
+            best = R.RunTHetA.do_optimization_single(2, m, k, 2, lb[:], ub[:], r, rN, mx, si, True, True)
+        solved = {}
+        with open("/tmp/theta_golden_small.likelihoods") as f:
+            for line in f:
+                cs, mu0, nll = line.rstrip("\n").split("\t")
+                solved[cs] = (float(mu0), float(nll))
+        stream = []
+        for col in O.enumerate_n2(lb, ub):
+            cs = "".join(str(v) for v in col)
+            stream.append([cs] + (list(solved[cs]) if cs in solved else [None, None]))
+        cases.append(dict(m=m, k=k, max_normal=mx, r=r, rN=rN, lower=lb, upper=ub, sorted_index=si, stream=stream,
+                          best=[dict(C=np.asarray(b[0]).tolist(), mu=[float(b[1][0]), float(b[1][1])],
+                                     nll=float(b[2]), vals=[float(v) for v in b[3]]) for b in best]))
+        print("n2 small", m, k, "N", len(stream), "best", len(best))
+    _dump("n2_small_full.json", cases)
+
+
+def gen_n3_small(R):
+    """Whole small n=3 spaces through the live reference: per-candidate dump + best list."""
+    cases = []
+    for m, lbv, ubv, seed in ((7, 1, 3, 1), (8, 1, 3, 1), (6, 0, 3, 2)):
+        r, rN, _ = O.synthetic(m, 3, 3, seed)
+        r, rN, si = O.sort_r(rN, r)
+        lb, ub = [lbv] * m, [ubv] * m
+        enum = R.Enumerator.Enumerator(3, m, 3, 2, lb[:], ub[:], True)
+        opt = R.Optimizer.Optimizer(r, rN, m, 3, 2, upper_bound=1.0)
+        rows = [tuple(x) for x in enum.rows]
+        stream = []
+        C = enum._C_to_array()  # Q2: bogus first matrix
+        first = True
+        while C is not False:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                s = opt.solve(C)
+            key = "bogus" if first else "".join("%d%d" % (int(a), int(b)) for a, b in C[:, 1:])
+            stream.append([key] + ([None, None] if s is None else [[float(v) for v in s[0]], float(s[1])]))
+            first = False
+            C = enum.generate_next_C()
+        with _quiet(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            best = R.RunTHetA.do_optimization_single(3, m, 3, 2, lb[:], ub[:], r, rN, 1.0, si, True, False)
+        cases.append(dict(m=m, k=3, r=r, rN=rN, lower=lb, upper=ub, sorted_index=si, rows=rows, stream=stream,
+                          best=[dict(C=np.asarray(b[0]).tolist(), mu=[float(v) for v in b[1]], nll=float(b[2]),
+                                     vals=[float(v) for v in b[3]]) for b in best]))
+        print("n3 small", m, "N", len(stream), "none", sum(1 for s in stream if s[1] is None), "best", len(best))
+    _dump("n3_small_full.json", cases)
+
+
+def gen_edge(R):
+    """Edge-case KATs from the live Optimizer.solve."""
+    m = 7
+    r, rN, _ = O.synthetic(m, 2, 3, 1)
+    r, rN, si = O.sort_r(rN, r)
+    opt = R.Optimizer.Optimizer(r, rN, m, 2, 2, upper_bound=1.0)
+    cols = dict(all_tau=[2] * m, all_zero=[0] * m, all_one=[1] * m, c=[0, 1, 1, 1, 2, 2, 3],
+                c2=[0, 2, 2, 2, 4, 4, 6], leading_zero=[0, 0, 0, 1, 2, 2, 2], high=[3, 3, 3, 3, 3, 3, 4],
+                low=[0, 0, 0, 0, 0, 0, 1])
+    out = dict(m=m, r=r, rN=rN, cases={})
+    for k, col in cols.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            s = opt.solve(O.column_to_matrix(col))
+        out["cases"][k] = dict(col=col, mu0=None if s is None else float(s[0][0]), nll=None if s is None else float(s[1]),
+                               vals=None if s is None else [float(v) for v in s[2]])
+    # zero tumour count in an interval whose candidate copy number is 0 -> 0/0 -> None
+    r0 = r[:]
+    r0[0] = 0
+    opt0 = R.Optimizer.Optimizer(r0, rN, m, 2, 2, upper_bound=1.0)
+    for k, col in (("zero_r_c0", [0, 0, 1, 1, 2, 2, 3]), ("zero_r_c1", [1, 1, 1, 1, 2, 2, 3])):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            s = opt0.solve(O.column_to_matrix(col))
+        out["cases"][k] = dict(col=col, r=r0, mu0=None if s is None else float(s[0][0]),
+                               nll=None if s is None else float(s[1]),
+                               vals=None if s is None else [float(v) for v in s[2]])
+    _dump("edge_n2.json", out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="kat,edge,n2_small,synth_n2,n3_small,config1")
+    a = ap.parse_args()
+    warnings.simplefilter("ignore")
+    R = refshim.modules()
+    os.makedirs(GOLD, exist_ok=True)
+    todo = a.only.split(",")
+    if "kat" in todo:
+        gen_kat(R)
+    if "edge" in todo:
+        gen_edge(R)
+    if "n2_small" in todo:
+        gen_n2_small_full(R)
+    if "synth_n2" in todo:
+        gen_synth_n2(R)
+    if "n3_small" in todo:
+        gen_n3_small(R)
+    if "config1" in todo:
+        gen_config1(R)
+
+
+if __name__ == "__main__":
+    main()

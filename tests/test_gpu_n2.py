@@ -1,0 +1,210 @@
+"""GPU parity tests for the n=2 path: CUDA (through the C ABI) vs golden vectors of the live
+reference and vs the CPU oracle on seeded inputs.
+
+Tolerances (north_star): identical None set and chosen C, mu within 1e-9 absolute,
+NLL within 1e-10 relative.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MU_TOL = 1e-9
+NLL_RTOL = 1e-10
+
+
+def _oracle():
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import theta_oracle
+    return theta_oracle
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from theta_b200 import _lib
+    _lib.init(0)
+    return _lib
+
+
+def _check_cands(st, mu, nll, ref_mu, ref_nll, what):
+    """ref_* hold None where the reference's solve() returned None."""
+    for i in range(len(ref_mu)):
+        none_ref = ref_nll[i] is None
+        none_gpu = st[i] >= 8
+        assert none_ref == none_gpu, "%s: None mismatch at %d (ref %s, gpu status %d)" % (what, i, ref_nll[i], st[i])
+        if none_ref:
+            continue
+        assert abs(mu[i] - ref_mu[i]) <= MU_TOL, "%s: mu mismatch at %d: %r vs %r" % (what, i, mu[i], ref_mu[i])
+        assert abs(nll[i] - ref_nll[i]) <= NLL_RTOL * abs(ref_nll[i]), "%s: nll mismatch at %d: %r vs %r" % (what, i, nll[i], ref_nll[i])
+
+
+def test_small_spaces_full_parity(lib, golden):
+    """Whole small spaces from the live reference: count, enumeration order, every candidate, best list."""
+    from theta_b200.search import do_optimization_single
+    for case in golden("n2_small_full.json"):
+        plan = lib.Plan(2, case["r"], case["rN"], case["lower"], case["upper"], tau=2, max_normal=case["max_normal"])
+        stream = case["stream"]
+        N = len(stream)
+        assert plan.count() == N
+        cols = plan.enumerate(0, N)
+        assert ["".join(str(int(v)) for v in row) for row in cols] == [s[0] for s in stream]
+        ref_mu = [s[1] for s in stream]
+        ref_nll = [s[2] for s in stream]
+        mu, nll, st = plan.solve_tiles(cols)
+        _check_cands(st, mu, nll, ref_mu, ref_nll, "solve_tiles m=%d" % case["m"])
+        cands, vals = plan.eval_ranks(np.arange(N), want_vals=True)
+        _check_cands(cands["status"], cands["mu"][:, 0], cands["nll"], ref_mu, ref_nll, "eval_ranks m=%d" % case["m"])
+        # NLL kernel at the reference's mu
+        ok = np.array([x is not None for x in ref_nll])
+        mu_in = np.array([x if x is not None else 0.5 for x in ref_mu])
+        nll2 = plan.nll_tiles(cols, mu_in)
+        for i in np.nonzero(ok)[0]:
+            assert abs(nll2[i] - ref_nll[i]) <= NLL_RTOL * abs(ref_nll[i])
+        plan.close()
+        best = do_optimization_single(2, case["m"], case["k"], 2, list(case["lower"]), list(case["upper"]), case["r"],
+                                      case["rN"], case["max_normal"], case["sorted_index"], True, False)
+        ref = case["best"]
+        assert len(best) == len(ref), "tie list length: %d vs %d" % (len(best), len(ref))
+        for b, g in zip(best, ref):
+            assert np.array_equal(b[0], np.array(g["C"]))
+            assert abs(b[1][0] - g["mu"][0]) <= MU_TOL and abs(b[1][1] - g["mu"][1]) <= MU_TOL
+            assert abs(b[2] - g["nll"]) <= NLL_RTOL * abs(g["nll"])
+            assert np.allclose(b[3], g["vals"], rtol=1e-9, atol=1e-12)
+
+
+def test_synthetic_configs_sampled(lib, golden):
+    """Configs #2, #3 and the >=100x target shape: sampled ranks vs the live reference's Optimizer.solve."""
+    data = golden("synth_n2_candidates.json")
+    O = _oracle()
+    for name, case in data.items():
+        plan = lib.Plan(2, case["r"], case["rN"], case["lower"], case["upper"], tau=2, max_normal=case["max_normal"])
+        assert plan.count() == case["n_candidates"], name
+        ranks = np.array([q["rank"] for q in case["records"]], dtype=np.uint64)
+        cands, _ = plan.eval_ranks(ranks, want_vals=False)
+        _check_cands(cands["status"], cands["mu"][:, 0], cands["nll"], [q["mu0"] for q in case["records"]],
+                     [q["nll"] for q in case["records"]], name)
+        # unranking agrees with the oracle's rank -> column map
+        for rk in (0, int(ranks[250]), int(ranks[-1]), case["n_candidates"] - 1):
+            assert list(plan.enumerate(rk, 1)[0]) == O.unrank_n2(case["lower"], case["upper"], rk)
+        plan.close()
+
+
+def test_edge_cases(lib, golden):
+    e = golden("edge_n2.json")
+    m = e["m"]
+    for name, c in e["cases"].items():
+        r = c.get("r", e["r"])
+        plan = lib.Plan(2, r, e["rN"], [0] * m, [7] * m)
+        mu, nll, st = plan.solve_tiles(np.array([c["col"]], dtype=np.int8))
+        _check_cands(st, mu, nll, [c["mu0"]], [c["nll"]], name)
+        plan.close()
+
+
+def test_config1_full_search(lib, golden):
+    """BASELINE config #1 (Example.intervals, n=2, k=3): the whole space against the reference run."""
+    from theta_b200.search import do_optimization_single, search_n2
+    g = golden("config1_search.json")
+    inp = g["inputs"]
+    plan = lib.Plan(2, inp["r"], inp["rN"], inp["lower"], inp["upper"], tau=2, max_normal=1.0)
+    assert plan.count() == g["n_candidates"] == 142560
+    res = search_n2(plan)
+    assert res.n_solved == g["n_candidates"] - len(g["none_ranks"])
+    # the None set, exactly
+    cands, _ = plan.eval_ranks(np.array(g["none_ranks"], dtype=np.uint64), want_vals=False)
+    assert (cands["status"] >= 8).all()
+    # 300 best candidates of the reference + every 53rd candidate
+    for part in ("top", "sample"):
+        ranks = np.array([q["rank"] for q in g[part]], dtype=np.uint64)
+        cands, _ = plan.eval_ranks(ranks, want_vals=False)
+        _check_cands(cands["status"], cands["mu"][:, 0], cands["nll"], [q["mu0"] for q in g[part]],
+                     [q["nll"] for q in g[part]], part)
+    assert abs(res.min_nll - g["top"][0]["nll"]) <= NLL_RTOL * g["top"][0]["nll"]
+    plan.close()
+    best = do_optimization_single(2, inp["m"], 3, 2, list(inp["lower"]), list(inp["upper"]), inp["r"], inp["rN"], 1.0,
+                                  inp["sorted_index"], True, False)
+    assert len(best) == len(g["best"]) == 1
+    b, ref = best[0], g["best"][0]
+    assert np.array_equal(b[0], np.array(ref["C"]))
+    assert abs(b[1][0] - ref["mu"][0]) <= MU_TOL
+    assert abs(b[2] - ref["nll"]) <= NLL_RTOL * ref["nll"]
+    assert np.allclose(b[3], ref["vals"], rtol=1e-9, atol=0)
+
+
+def test_fused_vs_tile_path_and_oracle(lib):
+    """Config #2 shape: the fused search and the enumerate->tile pipeline agree on a rank window,
+    and both agree with the CPU oracle on a seeded sample."""
+    O = _oracle()
+    P = O.synthetic_problem_n2(150, 5, seed=1)
+    plan = lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"])
+    N = plan.count()
+    assert N == O.count_n2(P["lower"], P["upper"])
+    start = N // 3
+    cnt = 20000
+    cols = plan.enumerate(start, cnt)
+    mu_t, nll_t, st_t = plan.solve_tiles(cols)
+    cands, _ = plan.eval_ranks(np.arange(start, start + cnt, dtype=np.uint64), want_vals=False)
+    assert np.array_equal(st_t >= 8, cands["status"] >= 8)
+    ok = st_t < 8
+    assert np.allclose(mu_t[ok], cands["mu"][ok, 0], rtol=0, atol=1e-12)
+    assert np.allclose(nll_t[ok], cands["nll"][ok], rtol=1e-13, atol=0)
+    nll_k = plan.nll_tiles(cols, mu_t)
+    assert np.allclose(nll_k[ok], nll_t[ok], rtol=1e-13, atol=0)
+    rng = np.random.default_rng(3)
+    for i in rng.integers(0, cnt, 40):
+        s = O.solve_n2(O.column_to_matrix(cols[i]), P["r"], P["rN"])
+        if s is None:
+            assert st_t[i] >= 8
+        else:
+            assert st_t[i] < 8
+            assert abs(s[0][0] - mu_t[i]) <= MU_TOL
+            assert abs(s[1] - nll_t[i]) <= NLL_RTOL * abs(s[1])
+    plan.close()
+
+
+def test_search_rank_window_matches_bruteforce(lib):
+    """pass1/pass2 + fold replay on windows of the m=150,k=7 space == fold over every candidate of the window."""
+    from theta_b200.search import fold_replay
+    O = _oracle()
+    P = O.synthetic_problem_n2(150, 7, seed=1)
+    plan = lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"])
+    N = plan.count()
+    for begin, cnt in ((0, 70000), (N // 2, 50001), (N - 33333, 33333)):
+        g = plan.pass1(begin, begin + cnt)
+        recs = plan.pass2(g)
+        cands, _ = plan.eval_ranks(np.arange(begin, begin + cnt, dtype=np.uint64), want_vals=False)
+        ok = cands["status"] < 8
+        full = fold_replay(cands["rank"][ok], cands["nll"][ok], dup_first=False)
+        sub = fold_replay(recs["rank"], recs["nll"], dup_first=False)
+        assert [int(cands["rank"][ok][i]) for i in full] == [int(recs["rank"][i]) for i in sub]
+        assert abs(g - cands["nll"][ok].min()) <= 1e-12 * abs(g)
+    plan.close()
+
+
+def test_calcallc_kat(lib, golden):
+    """The reference's own known-answer vectors for CalcAllC.L2 / L3 (python/L2args.pkl, L3args.pkl)."""
+    from theta_b200 import calc_all_c
+    k = golden("calcallc_kat.json")
+    a = k["L2"]
+    C = np.array(a["C"], dtype=float)
+    nll, vals = calc_all_c.L2(a["mu"], C, a["m"], a["r"])
+    assert abs(nll - a["nll_branch"]) <= 1e-12 * a["nll_branch"]
+    for v, g in zip(vals, a["vals_branch"]):
+        assert (v == 'X') == (g == 'X')
+        if g != 'X':
+            assert abs(v - g) <= 1e-12 * abs(g)
+    Cref = np.array(a["C"], dtype=float)   # Q10: the caller's C is scaled in place
+    Cref[:, 0] *= a["mu"]
+    Cref[:, 1] *= 1 - a["mu"]
+    assert np.array_equal(C, Cref)
+    b = k["L3"]
+    nll, vals = calc_all_c.L3(np.array(b["mu"]), np.array(b["C"], dtype=float), b["m"], b["r"], b["n"])
+    assert abs(nll - b["nll_branch"]) <= 1e-12 * b["nll_branch"]
+    for v, g in zip(vals, b["vals_branch"]):
+        assert (v == 'X') == (g == 'X')
+        if g != 'X':
+            assert abs(v - g) <= 1e-12 * abs(g)
+    with pytest.raises(ValueError):
+        calc_all_c.L2(0.3, np.zeros((3, 2)), 4, [1, 2, 3, 4])
+    with pytest.raises(ValueError):
+        calc_all_c.L3(np.array([.1, .2, .7]), np.zeros((4, 2)), 4, [1, 2, 3, 4], 3)

@@ -1,0 +1,255 @@
+"""ctypes binding of libtheta_b200.so (include/theta_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device
+is usable, the product path raises ThetaError.  Nothing here imports oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtheta_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_EMPTY, ERR_OVERFLOW, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+ST_OK, ST_ROOT_LB, ST_ROOT_UB, ST_FALLBACK_X0 = 0, 1, 2, 3
+ST_NONE_SIGN, ST_NONE_NAN, ST_NONE_NOCONV, ST_NONE_RANGE = 8, 9, 10, 11
+TIE_MARGIN = 10e-4  # Misc.isClose default margin (python/Misc.py:36)
+
+
+class ThetaError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "theta_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class EmptySpaceError(ThetaError):
+    """No admissible copy-number profile (RunTHetA.py:154-156, 217-219)."""
+
+
+class Problem(C.Structure):
+    _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("tau", C.c_int32), ("reserved", C.c_int32),
+                ("r", C.POINTER(C.c_int64)), ("rN", C.POINTER(C.c_int64)),
+                ("lower", C.POINTER(C.c_int32)), ("upper", C.POINTER(C.c_int32)),
+                ("max_normal", C.c_double)]
+
+
+class Cand(C.Structure):
+    _fields_ = [("rank", C.c_uint64), ("nll", C.c_double), ("mu", C.c_double * 3),
+                ("status", C.c_int32), ("flags", C.c_int32)]
+
+
+CAND_DTYPE = np.dtype([("rank", np.uint64), ("nll", np.float64), ("mu", np.float64, (3,)),
+                       ("status", np.int32), ("flags", np.int32)])
+assert CAND_DTYPE.itemsize == C.sizeof(Cand)
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("n_candidates", C.c_uint64), ("n_solved", C.c_uint64), ("n_stripes", C.c_uint64),
+                ("n_rescanned", C.c_uint64), ("min_nll", C.c_double), ("newton_iters", C.c_double),
+                ("ms_pass1", C.c_float), ("ms_pass2", C.c_float)]
+
+
+# every symbol include/theta_b200.h declares: (restype, argtypes)
+_VP = C.c_void_p
+SYMBOLS = {
+    "theta_init": (C.c_int, [C.c_int]),
+    "theta_device_count": (C.c_int, []),
+    "theta_shutdown": (None, []),
+    "theta_last_error": (C.c_char_p, []),
+    "theta_version": (C.c_char_p, []),
+    "theta_fp64_peak": (C.c_int, [C.POINTER(C.c_double), _VP]),
+    "theta_plan_create": (C.c_int, [C.POINTER(Problem), C.POINTER(_VP)]),
+    "theta_plan_destroy": (None, [_VP]),
+    "theta_plan_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
+    "theta_plan_bounds": (C.c_int, [_VP, _VP, _VP]),
+    "theta_enumerate_n2": (C.c_int, [_VP, C.c_uint64, C.c_int64, _VP, C.c_int64]),
+    "theta_enumerate_n2_dev": (C.c_int, [_VP, C.c_uint64, C.c_int64, _VP, C.c_int64, _VP]),
+    "theta_tile_pitch": (C.c_int64, [C.c_int32]),
+    "theta_search_n2_pass1": (C.c_int, [_VP, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), _VP]),
+    "theta_search_n2_pass2": (C.c_int, [_VP, C.c_double, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP]),
+    "theta_search_stats_get": (C.c_int, [_VP, C.POINTER(SearchStats)]),
+    "theta_search_n2": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "theta_eval_ranks_n2": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
+    "theta_solve_tiles_n2_dev": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP, _VP]),
+    "theta_solve_tiles_n2": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP]),
+    "theta_nll_tiles_n2_dev": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP]),
+    "theta_nll_tiles_n2": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP]),
+    "theta_nll": (C.c_int, [C.c_int32, C.c_int32, _VP, _VP, _VP, C.POINTER(C.c_double), _VP, _VP]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library and bind every declared symbol (no CUDA call is made)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ThetaError(ERR_CUDA, "%s not built: run `python -m theta_b200.build` (there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != OK:
+        msg = load().theta_last_error().decode("utf-8", "replace")
+        if rc == ERR_EMPTY:
+            raise EmptySpaceError(rc, msg)
+        raise ThetaError(rc, msg)
+
+
+_initialised = None
+
+
+def init(device=None):
+    """theta_init on `device` (default: LOCAL_RANK or 0). Raises ThetaError when no GPU is usable."""
+    global _initialised
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _initialised == device:
+        return
+    check(load().theta_init(int(device)))
+    _initialised = device
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Plan(object):
+    """Owns a theta_plan: device tables of one problem at the do_optimization* boundary."""
+
+    def __init__(self, n, r, rN, lower, upper, tau=2, max_normal=1.0, device=None):
+        init(device)
+        self.n = int(n)
+        self.m = len(r)
+        self.tau = int(tau)
+        self.max_normal = float(max_normal)
+        self._r = np.ascontiguousarray(np.asarray([int(v) for v in r], dtype=np.int64))
+        self._rN = np.ascontiguousarray(np.asarray([int(v) for v in rN], dtype=np.int64))
+        self._lo = np.ascontiguousarray(np.asarray([int(v) for v in lower], dtype=np.int32))
+        self._up = np.ascontiguousarray(np.asarray([int(v) for v in upper], dtype=np.int32))
+        if not (len(self._rN) == len(self._lo) == len(self._up) == self.m):
+            raise ValueError("r, rN, lower, upper must have the same length")
+        prob = Problem(self.n, self.m, self.tau, 0,
+                       self._r.ctypes.data_as(C.POINTER(C.c_int64)), self._rN.ctypes.data_as(C.POINTER(C.c_int64)),
+                       self._lo.ctypes.data_as(C.POINTER(C.c_int32)), self._up.ctypes.data_as(C.POINTER(C.c_int32)),
+                       self.max_normal)
+        h = C.c_void_p()
+        check(load().theta_plan_create(C.byref(prob), C.byref(h)))
+        self._h = h
+        self.pitch = int(load().theta_tile_pitch(self.m))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().theta_plan_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    def count(self):
+        c = C.c_uint64()
+        check(load().theta_plan_count(self._h, C.byref(c)))
+        return int(c.value)
+
+    def bounds(self):
+        lo = np.zeros(self.m, dtype=np.int32)
+        up = np.zeros(self.m, dtype=np.int32)
+        check(load().theta_plan_bounds(self._h, ptr(lo), ptr(up)))
+        return lo, up
+
+    def enumerate(self, rank_begin, count):
+        """int8 [count, m] tumour columns of consecutive ranks (Enumerator.generate_next_C order)."""
+        out = np.zeros((int(count), self.pitch), dtype=np.int8)
+        check(load().theta_enumerate_n2(self._h, int(rank_begin), int(count), ptr(out), self.pitch))
+        return out[:, :self.m]
+
+    def pass1(self, rank_begin, rank_end, stream=None):
+        g = C.c_double()
+        check(load().theta_search_n2_pass1(self._h, int(rank_begin), int(rank_end), C.byref(g), stream))
+        return float(g.value)
+
+    def pass2(self, global_min, prior_min=float("inf"), stream=None):
+        cap = 1 << 16
+        while True:
+            buf = np.zeros(cap, dtype=CAND_DTYPE)
+            n = C.c_uint64()
+            rc = load().theta_search_n2_pass2(self._h, float(global_min), float(prior_min), ptr(buf), cap, C.byref(n), stream)
+            if rc == ERR_OVERFLOW and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            check(rc)
+            return buf[:int(n.value)]
+
+    def stats(self):
+        s = SearchStats()
+        check(load().theta_search_stats_get(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in SearchStats._fields_}
+
+    def eval_ranks(self, ranks, want_vals=True):
+        ranks = np.ascontiguousarray(np.asarray(ranks, dtype=np.uint64))
+        out = np.zeros(len(ranks), dtype=CAND_DTYPE)
+        vals = np.zeros((len(ranks), self.m), dtype=np.float64) if want_vals else None
+        if len(ranks):
+            check(load().theta_eval_ranks_n2(self._h, ptr(ranks), len(ranks), ptr(out), ptr(vals) if want_vals else None))
+        return out, vals
+
+    def _tiles(self, cols):
+        cols = np.asarray(cols)
+        if cols.ndim != 2 or cols.shape[1] != self.m:
+            raise ValueError("cols must be [count, m]")
+        t = np.zeros((cols.shape[0], self.pitch), dtype=np.int8)
+        t[:, :self.m] = cols
+        return t
+
+    def solve_tiles(self, cols):
+        """Optimizer.solve on explicit tumour columns [count, m] -> (mu0, nll, status)."""
+        t = self._tiles(cols)
+        cnt = t.shape[0]
+        mu = np.zeros(cnt)
+        nll = np.zeros(cnt)
+        st = np.zeros(cnt, dtype=np.int32)
+        if cnt:
+            check(load().theta_solve_tiles_n2(self._h, ptr(t), self.pitch, cnt, ptr(mu), ptr(nll), ptr(st)))
+        return mu, nll, st
+
+    def nll_tiles(self, cols, mu):
+        t = self._tiles(cols)
+        cnt = t.shape[0]
+        mu = np.ascontiguousarray(np.asarray(mu, dtype=np.float64))
+        nll = np.zeros(cnt)
+        if cnt:
+            check(load().theta_nll_tiles_n2(self._h, ptr(t), self.pitch, cnt, ptr(mu), ptr(nll)))
+        return nll
+
+
+def nll_single(mu, Cw, r):
+    """theta_nll: masked NLL of one weighted matrix (CalcAllC.L2/L3 semantics). Returns (nll, vals, valid)."""
+    init()
+    Cw = np.ascontiguousarray(np.asarray(Cw, dtype=np.float64))
+    m, n = Cw.shape
+    mu = np.ascontiguousarray(np.asarray(mu, dtype=np.float64))
+    rr = np.ascontiguousarray(np.asarray([int(v) for v in r], dtype=np.int64))
+    nll = C.c_double()
+    vals = np.zeros(m)
+    valid = np.zeros(m, dtype=np.uint8)
+    check(load().theta_nll(n, m, ptr(mu), ptr(Cw), ptr(rr), C.byref(nll), ptr(vals), ptr(valid)))
+    return float(nll.value), vals, valid.astype(bool)
+
+
+def fp64_peak_gflops(stream=None):
+    init()
+    g = C.c_double()
+    check(load().theta_fp64_peak(C.byref(g), stream))
+    return float(g.value)

@@ -1,0 +1,192 @@
+// theta_core.cuh -- shared declarations + the per-candidate n=2 device solver.
+//
+// The maths follows SURVEY.md Appendix A, restated on *grouped* sufficient
+// statistics: a candidate's tumour column c takes at most KV distinct values,
+// and every term of the reference's per-interval sums
+//     dL_dMu  (python/Optimizer.py:209-221),  M2 (:223-226),  L2 (:187-196)
+// depends on the interval only through c_i once rN_i cancels:
+//     f(x)  = - sum_v R_v (S1 - v A) / (x S1 + v (1-x) A),   R_v = sum_{c_i=v} r_i
+//     NLL   = K0 - sum_v R_v log(g_v / gbar),  g_v = tau mu + v (1-mu),  gbar = (mu S0 + (1-mu) S1)/A
+// with A = sum rN, S0 = tau A, S1 = sum rN_i c_i, K0 = -sum r_i log(rN_i/A).
+// All R_v, S1 are exact integers (< 2^53) held in doubles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/theta_b200.h"
+
+namespace theta {
+
+// candidate-independent constants of one n=2 problem
+struct N2Const {
+    double A;        // sum rN
+    double S0;       // tau * A
+    double Rtot;     // sum r
+    double K0;       // -sum r_i log(rN_i / A)
+    double tau;
+    double max_normal;  // 1.0 => uB = 1
+    int any_zero_rN;    // some rN_i == 0 -> every candidate is NaN/None
+    int m;
+};
+
+struct SolveOut {
+    double x;    // root in normalised coordinates (Optimizer.py:118)
+    double mu;   // M2 (Optimizer.py:223-226)
+    double nll;  // L2 (Optimizer.py:187-196)
+    int status;
+    int iters;
+};
+
+#define THETA_NEWTON_MAXIT 100
+
+// Evaluate f and f' at x over the non-empty groups.
+template <int KV>
+__device__ __forceinline__ void n2_f_df(const double (&nv)[KV], const double (&ev)[KV], double S1, double A, double x,
+                                        double& f, double& fp) {
+    const double z = x * S1;
+    const double y = (1.0 - x) * A;
+    double s = 0.0, sp = 0.0;
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+        if (nv[v] != 0.0) {
+            const double den = fma((double)v, y, z);
+            const double inv = 1.0 / den;
+            const double t = nv[v] * inv;
+            s += t;
+            sp = fma(t * ev[v], inv, sp);
+        }
+    }
+    f = -s;
+    fp = sp;
+}
+
+template <int KV>
+__device__ __forceinline__ double n2_f(const double (&nv)[KV], double S1, double A, double x) {
+    const double z = x * S1;
+    const double y = (1.0 - x) * A;
+    double s = 0.0;
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+        if (nv[v] != 0.0) s += nv[v] / fma((double)v, y, z);
+    }
+    return -s;
+}
+
+// Optimizer._solve_n2 (python/Optimizer.py:90-126) on grouped statistics.
+//   R[v]      : sum of r_i over intervals with c_i == v
+//   S1        : sum rN_i c_i
+//   zero_r_c0 : some interval with c_i == 0 has r_i == 0 (0/0 at x = lB = 0 -> NaN -> None)
+//   x0        : warm start for the root (<= 0: none)
+template <int KV>
+__device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool zero_r_c0, const N2Const& k, double x0,
+                                         SolveOut& o) {
+    o.x = 0.0;
+    o.mu = 0.0;
+    o.nll = 0.0;
+    o.iters = 0;
+    // normalize_C (Optimizer.py:167-174): a zero tumour column gives 0/0 = NaN; brenth's
+    // NaN guard raises -> None.  Same for any rN_i == 0 (both normalised entries are 0).
+    if (!(S1 > 0.0) || k.any_zero_rN || zero_r_c0) {
+        o.status = THETA_ST_NONE_NAN;
+        return;
+    }
+    double ev[KV], nv[KV];
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+        ev[v] = S1 - (double)v * k.A;  // exact
+        nv[v] = R[v] * ev[v];
+    }
+    // bracket [lB, uB] = [0, 1] or [0, M2_Rev(max_normal)] (Optimizer.py:109-112, 228-231)
+    double uB = 1.0;
+    if (k.max_normal != 1.0) {
+        const double numer = -k.max_normal * k.S0;
+        const double denom = (k.max_normal - 1.0) * S1 + numer;
+        uB = numer / denom;
+    }
+    // f(lB = 0): the v = 0 group has denominator 0 -> -inf when it carries reads
+    double f0;
+    if (nv[0] != 0.0) {
+        f0 = -INFINITY;
+    } else {
+        double s = 0.0;
+#pragma unroll
+        for (int v = 1; v < KV; ++v)
+            if (nv[v] != 0.0) s += nv[v] / ((double)v * k.A);
+        f0 = -s;
+    }
+    const double fU = n2_f<KV>(nv, S1, k.A, uB);
+    if (f0 != f0 || fU != fU) {
+        o.status = THETA_ST_NONE_NAN;
+        return;
+    }
+    double x;
+    int status = THETA_ST_OK;
+    if (f0 == 0.0) {  // scipy brenth: f(a)==0 -> return a (flat likelihood, Q17)
+        x = 0.0;
+        status = THETA_ST_ROOT_LB;
+    } else if (fU == 0.0) {
+        x = uB;
+        status = THETA_ST_ROOT_UB;
+    } else if ((f0 < 0.0) == (fU < 0.0)) {
+        o.status = THETA_ST_NONE_SIGN;
+        return;
+    } else {
+        // f is increasing (f' = sum R_v e_v^2 / den^2 > 0): safeguarded Newton inside the bracket.
+        // When f0 > 0 > fU the bracket is reversed; the reference's brenth still finds the sign change.
+        double lo = 0.0, hi = uB;
+        const bool rising = f0 < 0.0;
+        x = (x0 > lo && x0 < hi) ? x0 : 0.5 * (lo + hi);
+        int it = 0;
+        for (; it < THETA_NEWTON_MAXIT; ++it) {
+            double f, fp;
+            n2_f_df<KV>(nv, ev, S1, k.A, x, f, fp);
+            if (f == 0.0) break;
+            if ((f < 0.0) == rising) lo = x; else hi = x;
+            double xn = x - f / fp;
+            if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+            const double dx = fabs(xn - x);
+            x = xn;
+            if (dx <= 1e-14 * fabs(xn)) break;
+        }
+        o.iters = it + 1;
+        if (it >= THETA_NEWTON_MAXIT) {
+            o.status = THETA_ST_NONE_NOCONV;
+            return;
+        }
+    }
+    // M2 (Optimizer.py:223-226), same operation order
+    const double numer = -x * S1;
+    const double denom = (x - 1.0) * k.S0 + numer;
+    const double mu = numer / denom;
+    const double mu1 = 1.0 - mu;
+    // L2 (Optimizer.py:187-196) on grouped statistics
+    const double gbar = (mu * k.S0 + mu1 * S1) / k.A;
+    const double lg = log(gbar);
+    double acc = 0.0;
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+        if (R[v] != 0.0) {
+            const double g = fma((double)v, mu1, k.tau * mu);
+            acc = fma(R[v], log(g) - lg, acc);
+        }
+    }
+    o.x = x;
+    o.mu = mu;
+    o.nll = k.K0 - acc;
+    o.status = status;
+}
+
+}  // namespace theta
+
+// ---- host-side helpers shared by the translation units ----
+namespace theta {
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+}  // namespace theta
+
+#define THETA_CUDA(expr)                                                        \
+    do {                                                                        \
+        cudaError_t _e = (expr);                                                \
+        if (_e != cudaSuccess) return theta::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)

@@ -1,0 +1,653 @@
+// theta_n2.cu -- n=2 plans, on-chip enumeration and the fused search kernels.
+//
+// Replaces, for n=2: Enumerator (python/Enumerator.py:39-160), Optimizer._solve_n2
+// (python/Optimizer.py:90-126) and the enumerate->solve->keep-best loop of
+// do_optimization_single / process_loop (python/RunTHetA.py:53-93,173-220).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "theta_n2.cuh"
+
+namespace theta {
+
+static constexpr int kBlock = 128;
+static constexpr int kCounters = 8;
+
+struct SearchParams {
+    const unsigned char* tables;
+    TableLayout layout;
+    N2Const kc;
+    uint64_t begin, end;
+    int L;
+    uint32_t n_items;  // stripes (pass 1) or listed stripes (pass 2)
+    double* stripe_min;
+    unsigned long long* counters;
+    const uint32_t* stripe_list;
+    const double* stripe_prior;
+    double near_thr;
+    theta_cand* emit;
+    unsigned long long emit_cap;
+    int emit_all_nan;
+};
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void stage_tables(unsigned char* smem, const unsigned char* g, size_t bytes) {
+    const uint4* src = reinterpret_cast<const uint4*>(g);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+// One CTA takes stripes from a ticket counter.  A stripe is blockDim.x * L consecutive ranks;
+// each thread unranks the first column of its run once and then walks L columns with the
+// odometer, warm-starting the root-finder from the previous column's root.
+template <int KT, bool EMIT>
+__global__ void __launch_bounds__(kBlock) n2_search_kernel(const SearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double s_red[kBlock / 32];
+    __shared__ uint32_t s_ticket;
+    stage_tables(smem, p.tables, p.layout.bytes);
+    Tables T;
+    T.bind(smem, p.layout);
+    const N2Const kc = p.kc;
+    unsigned long long solved = 0, iters = 0, nan_nll = 0;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_ticket = (uint32_t)atomicAdd(&p.counters[0], 1ULL);
+        __syncthreads();
+        const uint32_t ticket = s_ticket;
+        __syncthreads();
+        if (ticket >= p.n_items) break;
+        const uint32_t stripe = EMIT ? p.stripe_list[ticket] : ticket;
+        const double prior = EMIT ? p.stripe_prior[ticket] : 0.0;
+        const uint64_t r0 = p.begin + ((uint64_t)stripe * blockDim.x + threadIdx.x) * (uint64_t)p.L;
+        double tmin = INFINITY;
+        if (r0 < p.end) {
+            const int cnt = (int)min((uint64_t)p.L, p.end - r0);
+            int q[KT];
+            n2_unrank<KT>(T, r0, q);
+            double xprev = -1.0;
+            for (int t = 0; t < cnt; ++t) {
+                double R[KT + 1], S1;
+                bool z;
+                n2_groups<KT>(T, q, R, S1, z);
+                SolveOut o;
+                n2_solve<KT + 1>(R, S1, z, kc, xprev, o);
+                if (o.status < THETA_ST_NONE_SIGN) {
+                    ++solved;
+                    iters += o.iters;
+                    xprev = o.x;
+                    const double nll = o.nll;
+                    bool emit = false;
+                    if (nll != nll) {
+                        ++nan_nll;
+                        emit = true;  // isClose(nan, x) is True: a NaN NLL is always appended (Q6)
+                    } else {
+                        if (EMIT) emit = (nll <= p.near_thr) || (nll < prior && nll < tmin);
+                        tmin = fmin(tmin, nll);
+                    }
+                    if (EMIT && emit) {
+                        const unsigned long long slot = atomicAdd(&p.counters[3], 1ULL);
+                        if (slot < p.emit_cap) {
+                            theta_cand c;
+                            c.rank = r0 + t;
+                            c.nll = nll;
+                            c.mu[0] = o.mu;
+                            c.mu[1] = 1.0 - o.mu;
+                            c.mu[2] = 0.0;
+                            c.status = o.status;
+                            c.flags = o.iters;
+                            p.emit[slot] = c;
+                        }
+                    }
+                }
+                if (t + 1 < cnt) n2_next<KT>(T, q);
+            }
+        }
+        if (!EMIT) {
+            const double w = warp_min(tmin);
+            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = w;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double b = s_red[0];
+#pragma unroll
+                for (int i = 1; i < kBlock / 32; ++i) b = fmin(b, s_red[i]);
+                p.stripe_min[stripe] = b;
+            }
+        }
+    }
+    if (!EMIT) {
+        solved = warp_sum(solved);
+        iters = warp_sum(iters);
+        nan_nll = warp_sum(nan_nll);
+        if ((threadIdx.x & 31) == 0) {
+            if (solved) atomicAdd(&p.counters[1], solved);
+            if (iters) atomicAdd(&p.counters[2], iters);
+            if (nan_nll) atomicAdd(&p.counters[4], nan_nll);
+        }
+    }
+}
+
+// Columns of consecutive ranks as int8 rows (Enumerator._C_to_array, Enumerator.py:154-160, tumour column only).
+// Lane l of a warp owns row (warp_base + l); rows are written cooperatively so stores are coalesced.
+template <int KT>
+__global__ void __launch_bounds__(kBlock) n2_enumerate_kernel(const unsigned char* tables, TableLayout layout,
+                                                              uint64_t rank_begin, int64_t count, int8_t* out,
+                                                              int64_t pitch) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    stage_tables(smem, tables, layout.bytes);
+    Tables T;
+    T.bind(smem, layout);
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int m = layout.m;
+    const int words = (int)(pitch >> 2);
+    for (int64_t wbase = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; wbase < count; wbase += warps * 32) {
+        int q[KT];
+        const int64_t row = wbase + lane;
+        if (row < count) n2_unrank<KT>(T, rank_begin + row, q);
+        else {
+#pragma unroll
+            for (int v = 0; v < KT; ++v) q[v] = 0;
+        }
+        const int nrows = (int)min((int64_t)32, count - wbase);
+        for (int j = 0; j < nrows; ++j) {
+            int qj[KT];
+#pragma unroll
+            for (int v = 0; v < KT; ++v) qj[v] = __shfl_sync(0xffffffffu, q[v], j);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(out + (wbase + j) * pitch);
+            for (int w = lane; w < words; w += 32) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int i = w * 4 + b;
+                    int c = 0;
+#pragma unroll
+                    for (int v = 0; v < KT; ++v) c += (i >= m - qj[v]) ? 1 : 0;
+                    if (i >= m) c = 0;
+                    word |= (uint32_t)c << (8 * b);
+                }
+                dst[w] = word;
+            }
+        }
+    }
+}
+
+// Optimizer.solve for given ranks, with the per-interval `vals` the reference returns (Optimizer.py:123-126).
+template <int KT>
+__global__ void __launch_bounds__(kBlock) n2_eval_ranks_kernel(const unsigned char* tables, TableLayout layout,
+                                                               N2Const kc, const uint64_t* ranks, int64_t count,
+                                                               const double* rN, theta_cand* out, double* vals) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    stage_tables(smem, tables, layout.bytes);
+    Tables T;
+    T.bind(smem, layout);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int q[KT];
+    n2_unrank<KT>(T, ranks[i], q);
+    double R[KT + 1], S1;
+    bool z;
+    n2_groups<KT>(T, q, R, S1, z);
+    SolveOut o;
+    n2_solve<KT + 1>(R, S1, z, kc, -1.0, o);
+    theta_cand c;
+    c.rank = ranks[i];
+    c.nll = o.nll;
+    c.mu[0] = o.mu;
+    c.mu[1] = 1.0 - o.mu;
+    c.mu[2] = 0.0;
+    c.status = o.status;
+    c.flags = o.iters;
+    out[i] = c;
+    if (vals != nullptr && o.status < THETA_ST_NONE_SIGN) {
+        // vals_i = numer_i / denom of Optimizer.L2 (Optimizer.py:187-196)
+        const double mu1 = 1.0 - o.mu;
+        const double D = o.mu * kc.S0 + mu1 * S1;
+        const int m = layout.m;
+        for (int j = 0; j < m; ++j) {
+            int cv = 0;
+#pragma unroll
+            for (int v = 0; v < KT; ++v) cv += (j >= m - q[v]) ? 1 : 0;
+            vals[i * m + j] = rN[j] * (kc.tau * o.mu + (double)cv * mu1) / D;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- dispatch on the level count
+#define THETA_KT_DISPATCH(KT_RUNTIME, ...)                 \
+    switch (KT_RUNTIME) {                                    \
+        case 2: { constexpr int KT = 2; __VA_ARGS__; } break;       \
+        case 3: { constexpr int KT = 3; __VA_ARGS__; } break;       \
+        case 4: { constexpr int KT = 4; __VA_ARGS__; } break;       \
+        case 5: { constexpr int KT = 5; __VA_ARGS__; } break;       \
+        case 6: { constexpr int KT = 6; __VA_ARGS__; } break;       \
+        case 7: { constexpr int KT = 7; __VA_ARGS__; } break;       \
+        case 8: { constexpr int KT = 8; __VA_ARGS__; } break;       \
+        case 10: { constexpr int KT = 10; __VA_ARGS__; } break;     \
+        case 12: { constexpr int KT = 12; __VA_ARGS__; } break;     \
+        case 15: { constexpr int KT = 15; __VA_ARGS__; } break;     \
+        default: set_error("unsupported level count %d", KT_RUNTIME); return THETA_ERR_UNSUPPORTED; \
+    }
+
+static int pick_KT(int K) {
+    static const int opts[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 15};
+    for (int o : opts)
+        if (K <= o) return o;
+    return -1;
+}
+
+template <typename Kern>
+static int config_kernel(Kern kern, size_t smem, int* blocks_per_sm) {
+    if (smem > 48 * 1024) THETA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    THETA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, kBlock, smem));
+    if (*blocks_per_sm < 1) *blocks_per_sm = 1;
+    return THETA_OK;
+}
+
+static int sm_count(int device) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    return sms;
+}
+
+template <int KT, bool EMIT>
+static int launch_search(const theta_plan* plan, const SearchParams& sp, cudaStream_t st) {
+    int bps = 1;
+    int rc = config_kernel(n2_search_kernel<KT, EMIT>, plan->layout.bytes, &bps);
+    if (rc) return rc;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(sp.n_items, (uint64_t)sm_count(plan->device) * bps);
+    if (grid == 0) return THETA_OK;
+    n2_search_kernel<KT, EMIT><<<grid, kBlock, plan->layout.bytes, st>>>(sp);
+    THETA_CUDA(cudaGetLastError());
+    return THETA_OK;
+}
+
+}  // namespace theta
+
+using namespace theta;
+
+// ======================================================================= plan
+extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
+    if (!p || !out) { set_error("null argument"); return THETA_ERR_INVALID; }
+    *out = nullptr;
+    if (p->n != 2 && p->n != 3) { set_error("n must be 2 or 3 (FileIO.py:42), got %d", p->n); return THETA_ERR_INVALID; }
+    if (p->m < 1 || !p->r || !p->rN || !p->lower || !p->upper) { set_error("bad problem"); return THETA_ERR_INVALID; }
+    if (p->tau < 1) { set_error("tau must be >= 1"); return THETA_ERR_INVALID; }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError())); return THETA_ERR_CUDA; }
+    theta_plan* pl = new theta_plan();
+    pl->device = dev;
+    pl->n = p->n; pl->m = p->m; pl->tau = p->tau; pl->max_normal = p->max_normal;
+    const int m = p->m;
+    pl->lower.assign(p->lower, p->lower + m);
+    pl->upper.assign(p->upper, p->upper + m);
+    pl->r.assign(p->r, p->r + m);
+    pl->rN.assign(p->rN, p->rN + m);
+    // Enumerator._check_bound_order (Enumerator.py:90-113)
+    for (int i = 1; i < m; ++i) if (pl->lower[i] < pl->lower[i - 1]) pl->lower[i] = pl->lower[i - 1];
+    for (int i = m - 2; i >= 0; --i) if (pl->upper[i] > pl->upper[i + 1]) pl->upper[i] = pl->upper[i + 1];
+    int K = 0;
+    bool empty = false;
+    for (int i = 0; i < m; ++i) {
+        if (pl->lower[i] < 0) { set_error("negative lower bound"); delete pl; return THETA_ERR_INVALID; }
+        if (pl->lower[i] > pl->upper[i]) empty = true;
+        K = std::max(K, pl->upper[i]);
+        if (pl->r[i] < 0 || pl->rN[i] < 0) { set_error("negative read count"); delete pl; return THETA_ERR_INVALID; }
+    }
+    if (K > THETA_MAX_COPY) { set_error("copy number bound %d exceeds THETA_MAX_COPY=%d", K, THETA_MAX_COPY); delete pl; return THETA_ERR_UNSUPPORTED; }
+    pl->K = K;
+    pl->KT = pick_KT(std::max(K, 1));
+    const int KT = pl->KT;
+    // constants
+    long double A = 0, Rt = 0;
+    int zero_rN = 0;
+    for (int i = 0; i < m; ++i) { A += pl->rN[i]; Rt += pl->r[i]; if (pl->rN[i] == 0) zero_rN = 1; }
+    if (A >= 9.0e15L / std::max(1, std::max(K, p->tau)) || Rt >= 9.0e15L) { set_error("read counts too large for exact fp64 sums"); delete pl; return THETA_ERR_UNSUPPORTED; }
+    long double K0 = 0;
+    for (int i = 0; i < m; ++i)
+        if (pl->r[i] > 0 && pl->rN[i] > 0) K0 -= (long double)pl->r[i] * logl((long double)pl->rN[i] / A);
+    pl->kc.A = (double)A; pl->kc.S0 = (double)(A * p->tau); pl->kc.Rtot = (double)Rt; pl->kc.K0 = (double)K0;
+    pl->kc.tau = (double)p->tau; pl->kc.max_normal = p->max_normal; pl->kc.any_zero_rN = zero_rN; pl->kc.m = m;
+    // tables
+    pl->layout = TableLayout(m, KT);
+    std::vector<unsigned char> blob(pl->layout.bytes, 0);
+    double* SR = reinterpret_cast<double*>(blob.data() + pl->layout.off_SR);
+    double* SRN = reinterpret_cast<double*>(blob.data() + pl->layout.off_SRN);
+    uint64_t* SW = reinterpret_cast<uint64_t*>(blob.data() + pl->layout.off_SW);
+    int32_t* Z0 = reinterpret_cast<int32_t*>(blob.data() + pl->layout.off_Z0);
+    int32_t* qlo = reinterpret_cast<int32_t*>(blob.data() + pl->layout.off_qlo);
+    int32_t* qhi = reinterpret_cast<int32_t*>(blob.data() + pl->layout.off_qhi);
+    {
+        int64_t s = 0, sn = 0;
+        SR[0] = 0; SRN[0] = 0;
+        for (int q = 1; q <= m; ++q) { s += pl->r[m - q]; sn += pl->rN[m - q]; SR[q] = (double)s; SRN[q] = (double)sn; }
+        int z = 0;
+        std::vector<int> zp(m + 1, 0);
+        for (int i = 0; i < m; ++i) { zp[i + 1] = zp[i] + (pl->r[i] == 0 ? 1 : 0); }
+        (void)z;
+        for (int q = 0; q <= m; ++q) Z0[q] = zp[m - q];
+    }
+    for (int v = 1; v <= KT; ++v) {
+        int lo = 0, hi = 0;
+        for (int i = 0; i < m; ++i) { if (pl->lower[i] >= v) ++lo; if (pl->upper[i] >= v) ++hi; }
+        qlo[v - 1] = lo; qhi[v - 1] = hi;
+    }
+    // W_1(q) = 1;  W_v(q) = SW_{v-1}[max(q, qlo_{v-1})]   (0 beyond qhi_{v-1})
+    bool overflow = false;
+    const unsigned __int128 LIM = ((unsigned __int128)1) << 63;
+    for (int v = 1; v <= KT; ++v) {
+        uint64_t* sw = SW + (size_t)(v - 1) * (m + 2);
+        const uint64_t* swp = v > 1 ? SW + (size_t)(v - 2) * (m + 2) : nullptr;
+        sw[m + 1] = 0;
+        unsigned __int128 acc = 0;
+        for (int q = m; q >= 0; --q) {
+            uint64_t w;
+            if (v == 1) w = 1;
+            else { const int x = std::max(q, qlo[v - 2]); w = (x <= qhi[v - 2]) ? swp[x] : 0; }
+            if (q <= qhi[v - 1]) acc += w;
+            if (acc >= LIM) { overflow = true; acc = LIM - 1; }
+            sw[q] = (uint64_t)acc;
+        }
+    }
+    if (overflow) { set_error("candidate count exceeds 2^63"); delete pl; return THETA_ERR_OVERFLOW; }
+    {
+        const uint64_t* swK = SW + (size_t)(KT - 1) * (m + 2);
+        pl->count = (empty || qlo[KT - 1] > qhi[KT - 1]) ? 0 : swK[qlo[KT - 1]];
+        if (empty) pl->count = 0;
+    }
+    cudaError_t e = cudaMalloc(&pl->d_tables, pl->layout.bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_tables, blob.data(), pl->layout.bytes, cudaMemcpyHostToDevice);
+    std::vector<double> rd(m), rnd(m);
+    for (int i = 0; i < m; ++i) { rd[i] = (double)pl->r[i]; rnd[i] = (double)pl->rN[i]; }
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_r, sizeof(double) * m);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_rN, sizeof(double) * m);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_r, rd.data(), sizeof(double) * m, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_rN, rnd.data(), sizeof(double) * m, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_counters, sizeof(unsigned long long) * kCounters);
+    {   // prefix tables for the tile kernels (theta_tiles.cu)
+        const int64_t pitch = theta_tile_pitch(m);
+        pl->tile_pitch = pitch;
+        std::vector<double> PR(pitch + 1, 0.0), PRN(pitch + 1, 0.0);
+        std::vector<int32_t> ZP(pitch + 1, 0);
+        int64_t s = 0, sn = 0;
+        int z = 0;
+        for (int64_t i = 0; i < pitch; ++i) {
+            if (i < m) { s += pl->r[i]; sn += pl->rN[i]; z += pl->r[i] == 0 ? 1 : 0; }
+            PR[i + 1] = (double)s; PRN[i + 1] = (double)sn; ZP[i + 1] = z;
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&pl->d_PR, sizeof(double) * (pitch + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&pl->d_PRN, sizeof(double) * (pitch + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&pl->d_ZP, sizeof(int32_t) * (pitch + 1));
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_PR, PR.data(), sizeof(double) * (pitch + 1), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_PRN, PRN.data(), sizeof(double) * (pitch + 1), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_ZP, ZP.data(), sizeof(int32_t) * (pitch + 1), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(e, "plan allocation", __FILE__, __LINE__);
+        theta_plan_destroy(pl);
+        return rc;
+    }
+    *out = pl;
+    return THETA_OK;
+}
+
+extern "C" void theta_plan_destroy(theta_plan* pl) {
+    if (!pl) return;
+    cudaFree(pl->d_tables); cudaFree(pl->d_r); cudaFree(pl->d_rN);
+    cudaFree(pl->d_PR); cudaFree(pl->d_PRN); cudaFree(pl->d_ZP);
+    cudaFree(pl->d_stripe_min); cudaFree(pl->d_counters); cudaFree(pl->d_emit);
+    delete pl;
+}
+
+extern "C" int theta_plan_count(const theta_plan* pl, uint64_t* count) {
+    if (!pl || !count) { set_error("null argument"); return THETA_ERR_INVALID; }
+    *count = pl->count;
+    return THETA_OK;
+}
+
+extern "C" int theta_plan_bounds(const theta_plan* pl, int32_t* lower, int32_t* upper) {
+    if (!pl) { set_error("null plan"); return THETA_ERR_INVALID; }
+    if (lower) std::memcpy(lower, pl->lower.data(), sizeof(int32_t) * pl->m);
+    if (upper) std::memcpy(upper, pl->upper.data(), sizeof(int32_t) * pl->m);
+    return THETA_OK;
+}
+
+extern "C" int64_t theta_tile_pitch(int32_t m) {
+    int64_t p = ((int64_t)m + 7) / 8;
+    if ((p & 1) == 0) ++p;
+    return p * 8;
+}
+
+// ======================================================================= enumeration
+extern "C" int theta_enumerate_n2_dev(theta_plan* pl, uint64_t rank_begin, int64_t count, int8_t* cols_dev,
+                                      int64_t pitch, void* stream) {
+    if (!pl || !cols_dev) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (pl->n != 2) { set_error("plan is not n=2"); return THETA_ERR_INVALID; }
+    if (count <= 0) return THETA_OK;
+    if (pitch < pl->m || (pitch & 3)) { set_error("pitch must be >= m and a multiple of 4"); return THETA_ERR_INVALID; }
+    if (rank_begin + (uint64_t)count > pl->count) { set_error("rank range exceeds candidate count"); return THETA_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t warps_needed = (count + 31) / 32;
+    const int grid = (int)std::min<int64_t>((warps_needed + (kBlock / 32) - 1) / (kBlock / 32), (int64_t)sm_count(pl->device) * 8);
+    THETA_KT_DISPATCH(pl->KT, {
+        if (pl->layout.bytes > 48 * 1024)
+            THETA_CUDA(cudaFuncSetAttribute(n2_enumerate_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->layout.bytes));
+        n2_enumerate_kernel<KT><<<grid, kBlock, pl->layout.bytes, st>>>(pl->d_tables, pl->layout, rank_begin, count, cols_dev, pitch);
+    });
+    THETA_CUDA(cudaGetLastError());
+    return THETA_OK;
+}
+
+extern "C" int theta_enumerate_n2(theta_plan* pl, uint64_t rank_begin, int64_t count, int8_t* cols_host, int64_t pitch) {
+    if (!pl || !cols_host) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (count <= 0) return THETA_OK;
+    int8_t* d = nullptr;
+    THETA_CUDA(cudaMalloc(&d, (size_t)count * pitch));
+    int rc = theta_enumerate_n2_dev(pl, rank_begin, count, d, pitch, nullptr);
+    if (rc == THETA_OK) {
+        cudaError_t e = cudaMemcpy(cols_host, d, (size_t)count * pitch, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "enumerate D2H", __FILE__, __LINE__);
+    }
+    cudaFree(d);
+    return rc;
+}
+
+// ======================================================================= search
+extern "C" int theta_search_n2_pass1(theta_plan* pl, uint64_t rank_begin, uint64_t rank_end, double* local_min,
+                                     void* stream) {
+    if (!pl || !local_min) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (pl->n != 2) { set_error("plan is not n=2"); return THETA_ERR_INVALID; }
+    if (pl->count == 0) { set_error("No valid Copy Number Profiles exist for these intervals within the bounds specified"); return THETA_ERR_EMPTY; }
+    if (rank_end > pl->count) rank_end = pl->count;
+    if (rank_begin > rank_end) { set_error("bad rank range"); return THETA_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t N = rank_end - rank_begin;
+    pl->p1_begin = rank_begin; pl->p1_end = rank_end;
+    pl->stats = theta_search_stats{};
+    pl->stats.n_candidates = N;
+    pl->stats.min_nll = INFINITY;
+    *local_min = INFINITY;
+    if (N == 0) { pl->p1_stripes = 0; pl->h_stripe_min.clear(); return THETA_OK; }
+    // run length per thread: enough stripes to balance 148 SMs, few enough to keep the stripe table small
+    const uint64_t target_stripes = (uint64_t)sm_count(pl->device) * 24;
+    uint64_t L = N / (target_stripes * kBlock);
+    L = std::max<uint64_t>(8, std::min<uint64_t>(L, 256));
+    while ((N + L * kBlock - 1) / (L * kBlock) > (1ull << 22)) L *= 2;
+    pl->p1_L = (int)L; pl->p1_block = kBlock;
+    const uint64_t stripes = (N + L * kBlock - 1) / (L * kBlock);
+    pl->p1_stripes = stripes;
+    if (stripes > pl->stripe_cap) {
+        cudaFree(pl->d_stripe_min); pl->d_stripe_min = nullptr; pl->stripe_cap = 0;
+        THETA_CUDA(cudaMalloc(&pl->d_stripe_min, sizeof(double) * stripes));
+        pl->stripe_cap = stripes;
+    }
+    THETA_CUDA(cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kCounters, st));
+    SearchParams sp{};
+    sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc;
+    sp.begin = rank_begin; sp.end = rank_end; sp.L = (int)L; sp.n_items = (uint32_t)stripes;
+    sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters;
+    cudaEvent_t e0, e1;
+    THETA_CUDA(cudaEventCreate(&e0)); THETA_CUDA(cudaEventCreate(&e1));
+    THETA_CUDA(cudaEventRecord(e0, st));
+    THETA_KT_DISPATCH(pl->KT, { int rc = launch_search<KT, false>(pl, sp, st); if (rc) return rc; });
+    THETA_CUDA(cudaEventRecord(e1, st));
+    pl->h_stripe_min.resize(stripes);
+    THETA_CUDA(cudaMemcpyAsync(pl->h_stripe_min.data(), pl->d_stripe_min, sizeof(double) * stripes, cudaMemcpyDeviceToHost, st));
+    unsigned long long ctr[kCounters];
+    THETA_CUDA(cudaMemcpyAsync(ctr, pl->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, st));
+    THETA_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&pl->stats.ms_pass1, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    double g = INFINITY;
+    for (double v : pl->h_stripe_min) if (v < g) g = v;
+    pl->stats.n_solved = ctr[1];
+    pl->stats.n_stripes = stripes;
+    pl->stats.newton_iters = ctr[1] ? (double)ctr[2] / (double)ctr[1] : 0.0;
+    pl->stats.min_nll = g;
+    pl->stats.n_rescanned = ctr[4];  // provisional: number of NaN-NLL candidates, consumed by pass 2
+    *local_min = g;
+    return THETA_OK;
+}
+
+extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double prior_min, theta_cand* out_host,
+                                     uint64_t cap, uint64_t* n_out, void* stream) {
+    if (!pl || !n_out) { set_error("null argument"); return THETA_ERR_INVALID; }
+    *n_out = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t stripes = pl->p1_stripes;
+    const bool any_nan = pl->stats.n_rescanned != 0;
+    pl->stats.n_rescanned = 0;
+    if (stripes == 0) return THETA_OK;
+    // A stripe matters if it holds a strict prefix minimum of the NLL stream (every reset of the
+    // reference fold is one, RunTHetA.py:203-206) or a candidate within two margins of the global minimum
+    // (every member of the final tie list is, RunTHetA.py:199-202).
+    const double near_thr = global_min + 2.5 * THETA_TIE_MARGIN;
+    std::vector<uint32_t> list;
+    std::vector<double> prior;
+    double P = prior_min;
+    for (uint64_t s = 0; s < stripes; ++s) {
+        const double v = pl->h_stripe_min[s];
+        const bool rec = v < P, near = v <= near_thr;
+        if (rec || near || any_nan) {
+            list.push_back((uint32_t)s);
+            prior.push_back(rec ? P : -INFINITY);
+        }
+        if (v < P) P = v;
+    }
+    pl->stats.n_rescanned = list.size();
+    if (list.empty()) return THETA_OK;
+    uint32_t* d_list = nullptr;
+    double* d_prior = nullptr;
+    THETA_CUDA(cudaMalloc(&d_list, sizeof(uint32_t) * list.size()));
+    THETA_CUDA(cudaMalloc(&d_prior, sizeof(double) * list.size()));
+    THETA_CUDA(cudaMemcpyAsync(d_list, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice, st));
+    THETA_CUDA(cudaMemcpyAsync(d_prior, prior.data(), sizeof(double) * list.size(), cudaMemcpyHostToDevice, st));
+    size_t want = std::max<size_t>(1 << 16, pl->emit_cap);
+    std::vector<theta_cand> host;
+    int rc = THETA_OK;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        if (want > pl->emit_cap) {
+            cudaFree(pl->d_emit); pl->d_emit = nullptr; pl->emit_cap = 0;
+            cudaError_t e = cudaMalloc(&pl->d_emit, sizeof(theta_cand) * want);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "emit buffer", __FILE__, __LINE__); break; }
+            pl->emit_cap = want;
+        }
+        cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kCounters, st);
+        SearchParams sp{};
+        sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc;
+        sp.begin = pl->p1_begin; sp.end = pl->p1_end; sp.L = pl->p1_L; sp.n_items = (uint32_t)list.size();
+        sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters;
+        sp.stripe_list = d_list; sp.stripe_prior = d_prior; sp.near_thr = near_thr;
+        sp.emit = pl->d_emit; sp.emit_cap = pl->emit_cap;
+        cudaEventRecord(e0, st);
+        rc = THETA_OK;
+        switch (pl->KT) {
+#define THETA_P2(KTV) case KTV: rc = launch_search<KTV, true>(pl, sp, st); break;
+            THETA_P2(2) THETA_P2(3) THETA_P2(4) THETA_P2(5) THETA_P2(6) THETA_P2(7) THETA_P2(8) THETA_P2(10) THETA_P2(12) THETA_P2(15)
+#undef THETA_P2
+            default: set_error("unsupported level count"); rc = THETA_ERR_UNSUPPORTED;
+        }
+        if (rc) break;
+        cudaEventRecord(e1, st);
+        unsigned long long ctr[kCounters];
+        cudaError_t e = cudaMemcpyAsync(ctr, pl->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "pass2", __FILE__, __LINE__); break; }
+        cudaEventElapsedTime(&pl->stats.ms_pass2, e0, e1);
+        const unsigned long long emitted = ctr[3];
+        if (emitted > pl->emit_cap) { want = (size_t)emitted + 1024; continue; }
+        host.resize(emitted);
+        if (emitted) {
+            e = cudaMemcpy(host.data(), pl->d_emit, sizeof(theta_cand) * emitted, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "pass2 D2H", __FILE__, __LINE__); break; }
+        }
+        break;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_list); cudaFree(d_prior);
+    if (rc) return rc;
+    std::sort(host.begin(), host.end(), [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; });
+    *n_out = host.size();
+    if (host.size() > cap) {
+        set_error("pass2 produced %zu records but the caller's buffer holds %llu", host.size(), (unsigned long long)cap);
+        return THETA_ERR_OVERFLOW;
+    }
+    if (out_host && !host.empty()) std::memcpy(out_host, host.data(), sizeof(theta_cand) * host.size());
+    return THETA_OK;
+}
+
+extern "C" int theta_search_stats_get(const theta_plan* pl, theta_search_stats* s) {
+    if (!pl || !s) { set_error("null argument"); return THETA_ERR_INVALID; }
+    *s = pl->stats;
+    return THETA_OK;
+}
+
+extern "C" int theta_search_n2(theta_plan* pl, uint64_t rank_begin, uint64_t rank_end, theta_cand* out_host,
+                               uint64_t cap, uint64_t* n_out) {
+    double g = 0;
+    int rc = theta_search_n2_pass1(pl, rank_begin, rank_end, &g, nullptr);
+    if (rc) return rc;
+    return theta_search_n2_pass2(pl, g, INFINITY, out_host, cap, n_out, nullptr);
+}
+
+extern "C" int theta_eval_ranks_n2(theta_plan* pl, const uint64_t* ranks_host, int64_t count, theta_cand* out_host,
+                                   double* vals_host) {
+    if (!pl || !ranks_host || !out_host) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (pl->n != 2) { set_error("plan is not n=2"); return THETA_ERR_INVALID; }
+    if (count <= 0) return THETA_OK;
+    for (int64_t i = 0; i < count; ++i)
+        if (ranks_host[i] >= pl->count) { set_error("rank %llu out of range", (unsigned long long)ranks_host[i]); return THETA_ERR_INVALID; }
+    uint64_t* d_ranks = nullptr; theta_cand* d_out = nullptr; double* d_vals = nullptr;
+    const int m = pl->m;
+    THETA_CUDA(cudaMalloc(&d_ranks, sizeof(uint64_t) * count));
+    THETA_CUDA(cudaMalloc(&d_out, sizeof(theta_cand) * count));
+    if (vals_host) THETA_CUDA(cudaMalloc(&d_vals, sizeof(double) * count * m));
+    THETA_CUDA(cudaMemcpy(d_ranks, ranks_host, sizeof(uint64_t) * count, cudaMemcpyHostToDevice));
+    const int grid = (int)((count + kBlock - 1) / kBlock);
+    THETA_KT_DISPATCH(pl->KT, {
+        if (pl->layout.bytes > 48 * 1024)
+            THETA_CUDA(cudaFuncSetAttribute(n2_eval_ranks_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->layout.bytes));
+        n2_eval_ranks_kernel<KT><<<grid, kBlock, pl->layout.bytes>>>(pl->d_tables, pl->layout, pl->kc, d_ranks, count, pl->d_rN, d_out, d_vals);
+    });
+    THETA_CUDA(cudaGetLastError());
+    THETA_CUDA(cudaMemcpy(out_host, d_out, sizeof(theta_cand) * count, cudaMemcpyDeviceToHost));
+    if (vals_host) THETA_CUDA(cudaMemcpy(vals_host, d_vals, sizeof(double) * count * m, cudaMemcpyDeviceToHost));
+    cudaFree(d_ranks); cudaFree(d_out); cudaFree(d_vals);
+    return THETA_OK;
+}

@@ -1,0 +1,351 @@
+// theta_tiles.cu -- streaming kernels over explicit candidate tiles (n=2).
+//
+// A tile is a block of candidates stored as int8 tumour columns, one row of `pitch`
+// bytes per candidate (pitch = theta_tile_pitch(m) = smallest 8*odd >= m, padding
+// bytes zero), i.e. the compact form of the m x 2 float64 matrices that
+// Enumerator._C_to_array (python/Enumerator.py:154-160) hands to Optimizer.solve.
+//
+//   nll_tiles_n2   : Optimizer.L2 (python/Optimizer.py:187-196) at a given mu -- the
+//                    streaming "NLL kernel": per candidate it reads m bytes of C and
+//                    8 bytes of mu and writes 8 bytes of NLL.
+//   solve_tiles_n2 : Optimizer._solve_n2 (python/Optimizer.py:90-126) on explicit C.
+//
+// Data movement: persistent CTAs; each tile (kRows rows, contiguous in HBM) is brought
+// into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier complete_tx) through
+// a kStages-deep ring, so HBM reads are full 128 B lines issued by the copy engine while
+// the SM computes on earlier tiles.  One thread owns one row; pitch/8 is odd so the
+// per-thread 8-byte row reads are bank-conflict free.
+//
+// Arithmetic: a row is scanned 8 bytes at a time for *change points* (c_i != c_{i-1});
+// each run [s, e) of equal copy number v contributes  (PR[e]-PR[s]) * log(tau mu + v (1-mu))
+// to the log-sum and v * (PRN[e]-PRN[s]) to S1, with PR / PRN the exact prefix sums of r / rN.
+// THetA's candidates are monotone, so a row has at most K+1 runs and the per-byte work is
+// a handful of integer instructions; arbitrary rows are handled by the same code at a
+// cost proportional to their number of runs.
+#include <algorithm>
+#include <vector>
+
+#include "theta_n2.cuh"
+
+namespace theta {
+
+static constexpr int kRows = 128;   // rows per tile == threads per CTA
+static constexpr int kStages = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct TileParams {
+    const int8_t* cols;
+    int64_t pitch;
+    int64_t count;
+    const double* PR;   // [pitch+1] prefix sums of r  (zero-extended past m)
+    const double* PRN;  // [pitch+1] prefix sums of rN
+    const int32_t* ZP;  // [pitch+1] prefix counts of r_i == 0
+    N2Const kc;
+    const double* mu_in;
+    double* mu_out;
+    double* nll_out;
+    int32_t* status_out;
+};
+
+// Shared-memory carve-up (dynamic): ring of tiles | PR | PRN | ZP | [histogram] ; barriers are static.
+struct TileSmem {
+    unsigned char* ring;
+    double* PR;
+    double* PRN;
+    int32_t* ZP;
+    double* hist;
+};
+
+__host__ __device__ inline size_t tile_smem_bytes(int64_t pitch, int hist_levels) {
+    size_t o = (size_t)kStages * kRows * pitch;
+    o = (o + 15) & ~(size_t)15;
+    o += sizeof(double) * (pitch + 1) * 2;
+    o += sizeof(int32_t) * (pitch + 1);
+    o = (o + 15) & ~(size_t)15;
+    o += sizeof(double) * (size_t)hist_levels * kRows;
+    return o;
+}
+
+__device__ __forceinline__ TileSmem tile_smem_bind(unsigned char* base, int64_t pitch) {
+    TileSmem s;
+    size_t o = 0;
+    s.ring = base;
+    o = (size_t)kStages * kRows * pitch;
+    o = (o + 15) & ~(size_t)15;
+    s.PR = reinterpret_cast<double*>(base + o);
+    o += sizeof(double) * (pitch + 1);
+    s.PRN = reinterpret_cast<double*>(base + o);
+    o += sizeof(double) * (pitch + 1);
+    s.ZP = reinterpret_cast<int32_t*>(base + o);
+    o += sizeof(int32_t) * (pitch + 1);
+    o = (o + 15) & ~(size_t)15;
+    s.hist = reinterpret_cast<double*>(base + o);
+    return s;
+}
+
+// Issue the bulk copy of tile `t` into ring slot `slot` (one thread).  The 16-byte-multiple
+// body goes through TMA; a possible 8-byte tail of the last tile is copied by hand.
+__device__ __forceinline__ void issue_tile(const TileParams& p, unsigned char* ring, uint64_t* bars, int64_t t, int slot) {
+    const int64_t row0 = t * kRows;
+    const int64_t rows = min((int64_t)kRows, p.count - row0);
+    const uint32_t bytes = (uint32_t)(rows * p.pitch);
+    const uint32_t body = bytes & ~15u;
+    unsigned char* dst = ring + (size_t)slot * kRows * p.pitch;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.cols) + row0 * p.pitch;
+    if (body < bytes) {
+        *reinterpret_cast<uint64_t*>(dst + body) = *reinterpret_cast<const uint64_t*>(src + body);
+    }
+    if (body) {
+        mbar_expect_tx(&bars[slot], body);
+        tma_load_1d(dst, src, body, &bars[slot]);
+    } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory");
+    }
+}
+
+// Scan one row for runs of equal copy number; F(v, start, end) is called once per run.
+template <typename F>
+__device__ __forceinline__ void scan_runs(const unsigned char* row, int words, F&& on_run) {
+    const uint64_t* rw = reinterpret_cast<const uint64_t*>(row);
+    uint64_t w = rw[0];
+    uint32_t cur = (uint32_t)(w & 0xff);
+    uint32_t prev_last = cur;
+    int start = 0;
+    for (int wi = 0; wi < words; ++wi) {
+        if (wi) w = rw[wi];
+        const uint64_t sh = (w << 8) | prev_last;
+        uint64_t x = w ^ sh;
+        prev_last = (uint32_t)(w >> 56);
+        while (x) {
+            const int b = (__ffsll((long long)x) - 1) >> 3;
+            const int pos = wi * 8 + b;
+            on_run(cur, start, pos);
+            start = pos;
+            cur = (uint32_t)(w >> (8 * b)) & 0xff;
+            x &= ~(0xffull << (8 * b));
+        }
+    }
+    on_run(cur, start, words * 8);
+}
+
+template <bool SOLVE, int KT>
+__global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[kStages];
+    TileSmem S = tile_smem_bind(smem, p.pitch);
+    const int tid = threadIdx.x;
+    const int words = (int)(p.pitch >> 3);
+    for (int i = tid; i <= p.pitch; i += kRows) {
+        S.PR[i] = p.PR[i];
+        S.PRN[i] = p.PRN[i];
+        S.ZP[i] = p.ZP[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t n_tiles = (p.count + kRows - 1) / kRows;
+    const N2Const kc = p.kc;
+    // prologue: fill the ring
+    if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < kStages - 1; ++s) {
+            const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+            if (t < n_tiles) issue_tile(p, S.ring, bars, t, s);
+        }
+    }
+    __syncthreads();  // makes a hand-copied tail of the prologue tiles visible to every thread
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int slot = it % kStages;
+        const uint32_t parity = (uint32_t)(it / kStages) & 1u;
+        // refill the slot consumed in the previous iteration (every thread has passed the barrier below)
+        if (tid == 0) {
+            const int64_t tn = t + (int64_t)(kStages - 1) * gridDim.x;
+            if (tn < n_tiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_tile(p, S.ring, bars, tn, (it + kStages - 1) % kStages);
+            }
+        }
+        mbar_wait(&bars[slot], parity);
+        const int64_t row = t * kRows + tid;
+        if (row < p.count) {
+            const unsigned char* rp = S.ring + ((size_t)slot * kRows + tid) * p.pitch;
+            if (!SOLVE) {
+                const double mu = p.mu_in[row];
+                const double mu1 = 1.0 - mu;
+                const double tm = kc.tau * mu;
+                double acc = 0.0, s1 = 0.0;
+                scan_runs(rp, words, [&](uint32_t v, int s, int e) {
+                    const double wgt = S.PR[e] - S.PR[s];
+                    s1 = fma((double)v, S.PRN[e] - S.PRN[s], s1);
+                    if (wgt != 0.0) acc = fma(wgt, log(fma((double)v, mu1, tm)), acc);
+                });
+                const double gbar = (mu * kc.S0 + mu1 * s1) / kc.A;
+                double nll = kc.K0 - (acc - kc.Rtot * log(gbar));
+                if (kc.any_zero_rN) nll = INFINITY;
+                p.nll_out[row] = nll;
+            } else {
+                double* h = S.hist + tid;  // hist[v * kRows + tid]
+#pragma unroll
+                for (int v = 0; v <= KT; ++v) h[v * kRows] = 0.0;
+                double s1 = 0.0;
+                bool z0 = false, bad = false;
+                scan_runs(rp, words, [&](uint32_t v, int s, int e) {
+                    const double wgt = S.PR[e] - S.PR[s];
+                    if (v > (uint32_t)KT) { if (S.PRN[e] - S.PRN[s] != 0.0 || wgt != 0.0) bad = true; return; }
+                    s1 = fma((double)v, S.PRN[e] - S.PRN[s], s1);
+                    h[v * kRows] += wgt;
+                    if (v == 0 && S.ZP[e] - S.ZP[s] > 0) z0 = true;
+                });
+                double R[KT + 1];
+#pragma unroll
+                for (int v = 0; v <= KT; ++v) R[v] = h[v * kRows];
+                SolveOut o;
+                n2_solve<KT + 1>(R, s1, z0, kc, -1.0, o);
+                if (bad) { o.status = THETA_ST_NONE_NAN; o.mu = 0.0; o.nll = 0.0; }
+                p.mu_out[row] = o.mu;
+                p.nll_out[row] = o.nll;
+                p.status_out[row] = o.status;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <bool SOLVE, int KT>
+static int launch_tiles(const theta_plan* pl, const TileParams& tp, cudaStream_t st) {
+    const size_t smem = tile_smem_bytes(tp.pitch, SOLVE ? KT + 1 : 0);
+    auto kern = tiles_n2_kernel<SOLVE, KT>;
+    if (smem > 227 * 1024) { set_error("tile of %d rows x %lld bytes does not fit shared memory", kRows, (long long)tp.pitch); return THETA_ERR_UNSUPPORTED; }
+    THETA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 1;
+    THETA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kRows, smem));
+    if (bps < 1) bps = 1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    const int64_t n_tiles = (tp.count + kRows - 1) / kRows;
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sms * bps);
+    kern<<<grid, kRows, smem, st>>>(tp);
+    THETA_CUDA(cudaGetLastError());
+    return THETA_OK;
+}
+
+static int check_tile_args(const theta_plan* pl, const void* cols, int64_t pitch, int64_t count) {
+    if (!pl || !cols) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (pl->n != 2) { set_error("plan is not n=2"); return THETA_ERR_INVALID; }
+    if (count < 0) { set_error("negative count"); return THETA_ERR_INVALID; }
+    if (pitch != pl->tile_pitch) {
+        set_error("pitch %lld invalid: tile kernels need theta_tile_pitch(m) = %lld", (long long)pitch, (long long)pl->tile_pitch);
+        return THETA_ERR_INVALID;
+    }
+    if (reinterpret_cast<uintptr_t>(cols) & 15) { set_error("tile buffer must be 16-byte aligned"); return THETA_ERR_INVALID; }
+    return THETA_OK;
+}
+
+}  // namespace theta
+
+using namespace theta;
+
+extern "C" int theta_nll_tiles_n2_dev(theta_plan* pl, const int8_t* cols_dev, int64_t pitch, int64_t count,
+                                      const double* mu_dev, double* nll_dev, void* stream) {
+    int rc = check_tile_args(pl, cols_dev, pitch, count);
+    if (rc) return rc;
+    if (!mu_dev || !nll_dev) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (count == 0) return THETA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    TileParams tp{};
+    tp.cols = cols_dev; tp.pitch = pitch; tp.count = count; tp.PR = pl->d_PR; tp.PRN = pl->d_PRN; tp.ZP = pl->d_ZP;
+    tp.kc = pl->kc; tp.mu_in = mu_dev; tp.nll_out = nll_dev;
+    return launch_tiles<false, 1>(pl, tp, st);  // asynchronous on `stream`
+}
+
+extern "C" int theta_solve_tiles_n2_dev(theta_plan* pl, const int8_t* cols_dev, int64_t pitch, int64_t count,
+                                        double* mu_dev, double* nll_dev, int32_t* status_dev, void* stream) {
+    int rc = check_tile_args(pl, cols_dev, pitch, count);
+    if (rc) return rc;
+    if (!mu_dev || !nll_dev || !status_dev) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (count == 0) return THETA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        TileParams tp{};
+        tp.cols = cols_dev; tp.pitch = pitch; tp.count = count; tp.PR = pl->d_PR; tp.PRN = pl->d_PRN; tp.ZP = pl->d_ZP;
+        tp.kc = pl->kc; tp.mu_out = mu_dev; tp.nll_out = nll_dev; tp.status_out = status_dev;
+        switch (pl->KT) {
+#define THETA_TS(KTV) case KTV: rc = launch_tiles<true, KTV>(pl, tp, st); break;
+            THETA_TS(2) THETA_TS(3) THETA_TS(4) THETA_TS(5) THETA_TS(6) THETA_TS(7) THETA_TS(8) THETA_TS(10) THETA_TS(12) THETA_TS(15)
+#undef THETA_TS
+            default: set_error("unsupported level count"); rc = THETA_ERR_UNSUPPORTED;
+        }
+    }
+    return rc;  // asynchronous on `stream`
+}
+
+extern "C" int theta_nll_tiles_n2(theta_plan* pl, const int8_t* cols_host, int64_t pitch, int64_t count,
+                                  const double* mu_host, double* nll_host) {
+    if (!pl || !cols_host || !mu_host || !nll_host) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (count <= 0) return THETA_OK;
+    int8_t* d_c = nullptr; double *d_mu = nullptr, *d_nll = nullptr;
+    int rc = THETA_OK;
+    cudaError_t e = cudaMalloc(&d_c, (size_t)count * pitch);
+    if (e == cudaSuccess) e = cudaMalloc(&d_mu, sizeof(double) * count);
+    if (e == cudaSuccess) e = cudaMalloc(&d_nll, sizeof(double) * count);
+    if (e == cudaSuccess) e = cudaMemcpy(d_c, cols_host, (size_t)count * pitch, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_mu, mu_host, sizeof(double) * count, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "nll_tiles H2D", __FILE__, __LINE__);
+    if (rc == THETA_OK) rc = theta_nll_tiles_n2_dev(pl, d_c, pitch, count, d_mu, d_nll, nullptr);
+    if (rc == THETA_OK) { e = cudaMemcpy(nll_host, d_nll, sizeof(double) * count, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = cuda_fail(e, "nll_tiles D2H", __FILE__, __LINE__); }
+    cudaFree(d_c); cudaFree(d_mu); cudaFree(d_nll);
+    return rc;
+}
+
+extern "C" int theta_solve_tiles_n2(theta_plan* pl, const int8_t* cols_host, int64_t pitch, int64_t count,
+                                    double* mu_host, double* nll_host, int32_t* status_host) {
+    if (!pl || !cols_host || !mu_host || !nll_host || !status_host) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (count <= 0) return THETA_OK;
+    int8_t* d_c = nullptr; double *d_mu = nullptr, *d_nll = nullptr; int32_t* d_st = nullptr;
+    int rc = THETA_OK;
+    cudaError_t e = cudaMalloc(&d_c, (size_t)count * pitch);
+    if (e == cudaSuccess) e = cudaMalloc(&d_mu, sizeof(double) * count);
+    if (e == cudaSuccess) e = cudaMalloc(&d_nll, sizeof(double) * count);
+    if (e == cudaSuccess) e = cudaMalloc(&d_st, sizeof(int32_t) * count);
+    if (e == cudaSuccess) e = cudaMemcpy(d_c, cols_host, (size_t)count * pitch, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "solve_tiles H2D", __FILE__, __LINE__);
+    if (rc == THETA_OK) rc = theta_solve_tiles_n2_dev(pl, d_c, pitch, count, d_mu, d_nll, d_st, nullptr);
+    if (rc == THETA_OK) {
+        e = cudaMemcpy(mu_host, d_mu, sizeof(double) * count, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(nll_host, d_nll, sizeof(double) * count, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(status_host, d_st, sizeof(int32_t) * count, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "solve_tiles D2H", __FILE__, __LINE__);
+    }
+    cudaFree(d_c); cudaFree(d_mu); cudaFree(d_nll); cudaFree(d_st);
+    return rc;
+}

@@ -1,0 +1,243 @@
+"""Host side of the likelihood search: the reference's do_optimization* interface.
+
+Mirrors python/RunTHetA.py:124-220 (same names, argument meaning, return
+structure and error behaviour).  The enumerate -> solve -> keep-best loop runs on
+the GPU through the C ABI (theta_b200/_lib.py); this module only
+  * shards the rank range over the ranks of an initialised torch.distributed
+    group (one process per GPU) and exchanges the per-shard minima with one
+    all-reduce(min) plus a tiny all-gather, and
+  * replays the reference's order-dependent tie fold (RunTHetA.py:198-206,
+    Misc.isClose python/Misc.py:36-47) over the few records pass 2 returns.
+"""
+import sys
+
+import numpy as np
+
+from . import _lib
+from ._lib import Plan, TIE_MARGIN
+
+INF = float("inf")
+
+
+def is_close(a, b, margin=TIE_MARGIN):
+    """Misc.isClose for one pair (python/Misc.py:36-47): `not (|a-b| > margin)`, so NaN is close (Q6)."""
+    return not (abs(a - b) > margin)
+
+
+def fold_replay(ranks, nlls, dup_first=True):
+    """The running-min fold of RunTHetA.py:198-206 over records sorted by enumeration rank.
+
+    Returns the indices of the surviving records in fold order (an index can appear
+    twice: the drivers evaluate the first matrix twice, RunTHetA.py:148,188 -- Q1).
+    """
+    best, m_ = [], INF
+    for i in range(len(ranks)):
+        reps = 2 if (dup_first and int(ranks[i]) == 0) else 1
+        for _ in range(reps):
+            nll = float(nlls[i])
+            if is_close(nll, m_):
+                best.append(i)
+            elif nll < m_:
+                best = [i]
+                m_ = nll
+    return best
+
+
+def _dist_state():
+    """(rank, world, torch.distributed or None)."""
+    try:
+        import torch.distributed as dist
+    except Exception:  # torch absent: single process
+        return 0, 1, None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size(), dist
+    return 0, 1, None
+
+
+def shard_range(total, rank, world):
+    """Contiguous rank range of one shard: [total*rank//world, total*(rank+1)//world)."""
+    return (total * rank) // world, (total * (rank + 1)) // world
+
+
+def exchange_minima(local_min, dist, rank, world):
+    """One all-reduce(min) for the global best NLL + an all-gather of the shard minima.
+
+    Returns (global_min, prior_min) with prior_min = min over shards before `rank`.
+    """
+    if dist is None:
+        return local_min, INF
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([local_min], dtype=torch.float64, device=dev)
+    g = t.clone()
+    dist.all_reduce(g, op=dist.ReduceOp.MIN)
+    allm = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allm, t)
+    mins = [float(x.item()) for x in allm]
+    prior = min(mins[:rank]) if rank > 0 else INF
+    return float(g.item()), prior
+
+
+def gather_records(recs, dist, world):
+    """All shards' pass-2 records, concatenated in rank order (they are already sorted per shard)."""
+    if dist is None:
+        return recs
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    n = torch.tensor([len(recs)], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    ns = [int(x.item()) for x in ns]
+    cap = max(max(ns), 1)
+    item = _lib.CAND_DTYPE.itemsize
+    buf = np.zeros(cap * item, dtype=np.uint8)
+    buf[:len(recs) * item] = np.frombuffer(recs.tobytes(), dtype=np.uint8)
+    t = torch.from_numpy(buf).to(dev)
+    outs = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    parts = [np.frombuffer(o.cpu().numpy().tobytes(), dtype=_lib.CAND_DTYPE)[:k] for o, k in zip(outs, ns)]
+    return np.concatenate(parts) if parts else recs
+
+
+class SearchResult(object):
+    def __init__(self):
+        self.best = []          # [(rank, mu0, nll, status)] in fold order (may repeat rank 0)
+        self.records = None     # all pass-2 records (global)
+        self.count = 0          # candidates in the space (without the duplicate)
+        self.n_solved = 0
+        self.min_nll = INF
+        self.stats = {}
+
+
+def search_n2(plan, stream=None):
+    """Sharded two-pass search; every rank returns the same SearchResult."""
+    rank, world, dist = _dist_state()
+    total = plan.count()
+    begin, end = shard_range(total, rank, world)
+    local_min = plan.pass1(begin, end, stream)
+    stats = plan.stats()
+    g, prior = exchange_minima(local_min, dist, rank, world)
+    recs = plan.pass2(g, prior, stream)
+    stats.update({k: v for k, v in plan.stats().items() if k in ("n_rescanned", "ms_pass2")})
+    allrecs = gather_records(recs, dist, world)
+    res = SearchResult()
+    res.records = allrecs
+    res.count = total
+    res.min_nll = g
+    res.stats = stats
+    n_solved = stats["n_solved"]
+    if dist is not None:
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor([n_solved], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        n_solved = int(t.item())
+    res.n_solved = n_solved
+    idx = fold_replay(allrecs["rank"], allrecs["nll"], dup_first=True)
+    res.best = [(int(allrecs["rank"][i]), float(allrecs["mu"][i][0]), float(allrecs["nll"][i]), int(allrecs["status"][i]))
+                for i in idx]
+    return res
+
+
+def _reverse_sort_rows(C, sorted_index):
+    """DataTools.reverse_sort_C (python/DataTools.py:132-145)."""
+    out = np.zeros(C.shape)
+    out[np.asarray(sorted_index, dtype=np.int64)] = C
+    return out
+
+
+def _reverse_sort_list(vec, sorted_index):
+    """DataTools.reverse_sort_list (python/DataTools.py:147-159)."""
+    out = [0] * len(sorted_index)
+    for i, s in enumerate(sorted_index):
+        out[s] = vec[i]
+    return out
+
+
+def _finish_n2(plan, res, tau, sorted_index):
+    """Winners -> the reference's `best` tuples (C_new, mu, likelihood, vals) in original interval order."""
+    best = []
+    if not res.best:
+        return best
+    uniq = sorted(set(b[0] for b in res.best))
+    cands, vals = plan.eval_ranks(uniq, want_vals=True)
+    where = {rk: i for i, rk in enumerate(uniq)}
+    cols = {rk: plan.enumerate(rk, 1)[0] for rk in uniq}
+    for rk, mu0, nll, _st in res.best:
+        C = np.zeros((plan.m, 2))
+        C[:, 0] = tau
+        C[:, 1] = cols[rk]
+        mu0 = np.float64(mu0)
+        v = [np.float64(x) for x in vals[where[rk]]]
+        best.append((_reverse_sort_rows(C, sorted_index), (mu0, 1 - mu0), np.float64(nll),
+                     _reverse_sort_list(v, sorted_index)))
+    return best
+
+
+_NO_PROFILES = ("Error: No valid Copy Number Profiles exist for these intervals within the bounds specified. "
+                "Exiting...")
+
+
+def do_optimization_single(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_normal, sorted_index, multi_event,
+                           get_values, prefix=None):
+    """RunTHetA.do_optimization_single (python/RunTHetA.py:173-220) on the GPU.
+
+    Same arguments and return value: a list of (C_new, mu, likelihood, vals) with
+    C_new an m x n float64 array in the original interval order.  `k` and
+    `multi_event` are accepted and, as in the reference, not used by the search
+    (Enumerator.py:55,58 -- Q3/Q4).  With get_values, every candidate's
+    (column, mu0, NLL) is written to <prefix>.likelihoods like RunTHetA.py:210-215.
+    """
+    if n == 3:
+        from .search_n3 import do_optimization_n3
+        return do_optimization_n3(m, k, tau, lower_bounds, upper_bounds, r, rN, sorted_index, get_values, prefix)
+    if n != 2:
+        raise ValueError("n must be 2 or 3 (FileIO.py:42)")
+    plan = Plan(2, r, rN, lower_bounds, upper_bounds, tau=tau, max_normal=max_normal)
+    try:
+        # Enumerator._check_bound_order edits the caller's lists in place (Q16)
+        lo, up = plan.bounds()
+        for i in range(len(lower_bounds)):
+            lower_bounds[i] = int(lo[i])
+            upper_bounds[i] = int(up[i])
+        try:
+            res = search_n2(plan)
+        except _lib.EmptySpaceError:
+            print(_NO_PROFILES)
+            sys.exit(1)
+        if get_values:
+            dump_values_n2(plan, (prefix or "theta") + ".likelihoods")
+        return _finish_n2(plan, res, tau, sorted_index)
+    finally:
+        plan.close()
+
+
+def do_optimization(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_normal, sorted_index, max_processes,
+                    multi_event, get_values, prefix=None):
+    """RunTHetA.do_optimization (python/RunTHetA.py:124-171).
+
+    The reference farms candidates out to `max_processes - 1` worker processes and merges
+    their tie lists in scheduling order (Q13); parity is defined against the single-process
+    fold, which is what the GPU path reproduces.  `max_processes` is accepted and ignored:
+    parallelism comes from the GPU(s) -- one process per GPU under torch.distributed.
+    """
+    return do_optimization_single(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_normal, sorted_index,
+                                  multi_event, get_values, prefix)
+
+
+def dump_values_n2(plan, path, chunk=1 << 18):
+    """--GET_VALUES (python/RunTHetA.py:210-215): one line per *solved* candidate in enumeration
+    order, first matrix twice: tumour column string, mu[0], likelihood."""
+    total = plan.count()
+    with open(path, "w") as f:
+        for b in range(0, total, chunk):
+            cnt = min(chunk, total - b)
+            cols = plan.enumerate(b, cnt)
+            mu, nll, st = plan.solve_tiles(cols)
+            for i in range(cnt):
+                if st[i] >= _lib.ST_NONE_SIGN:
+                    continue
+                line = "".join(str(int(v)) for v in cols[i]) + "\t" + str(np.float64(mu[i])) + "\t" + str(np.float64(nll[i])) + "\n"
+                f.write(line)
+                if b + i == 0:
+                    f.write(line)
