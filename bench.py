@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- candidates/second of THetA's combinatorial likelihood search on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|m150k7|cfg3win]
+
+One "step" = one complete search (enumerate every admissible C, solve mu, NLL, keep the
+best with the reference's tie fold) of the workload's candidate space.  Default workload is
+BASELINE.json configs[1]: synthetic m=150, n=2, k=5 (seed 1) -> 25,251,200 candidates.
+For N>1 (torchrun, one rank per GPU) the rank range is sharded contiguously (strong scaling on
+the same space); the only communication is the min exchange + the record gather.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      the streaming NLL kernel (theta_nll_tiles_n2) on tiles larger than L2, HBM-bound
+  search_kernel the fused search kernel's own device time / fp64 utilisation
+  cpu_baseline  the oracle's Python port of the reference path on the host cores (bounded sample)
+  extra         the >=100x target shape (m=150, k=7) searched once
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg2": dict(m=150, k=5, seed=1, desc="synthetic m=150 n=2 k=5 seed=1 (BASELINE configs[1]), full space"),
+    "m150k7": dict(m=150, k=7, seed=1, desc="synthetic m=150 n=2 k=7 seed=1 (>=100x target shape), full space"),
+    "cfg3win": dict(m=300, k=7, seed=1, window=1 << 33,
+                    desc="synthetic m=300 n=2 k=7 seed=1 (BASELINE configs[2]), first 2^33 ranks"),
+}
+
+
+def problem(name):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import theta_oracle as O  # input generator only; not on the measured path
+    w = WORKLOADS[name]
+    P = O.synthetic_problem_n2(w["m"], w["k"], seed=w["seed"])
+    P["window"] = w.get("window")
+    P["desc"] = w["desc"]
+    return P
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port of the reference)
+def _cpu_worker(args):
+    name, begin, count = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import theta_oracle as O
+    P = problem(name)
+    col = O.unrank_n2(P["lower"], P["upper"], begin)
+    # continue the reference odometer (Enumerator.py:119-152) from `begin`
+    lo, up = P["lower"], P["upper"]
+    m = len(col)
+    t0 = time.perf_counter()
+    best = float("inf")
+    for _ in range(count):
+        s = O.solve_n2(O.column_to_matrix(col), P["r"], P["rN"], 1.0)
+        if s is not None and s[1] < best:
+            best = s[1]
+        for i in range(m - 1):
+            if col[i] < col[i + 1] and col[i] < up[i]:
+                col[i] += 1
+                for j in range(i):
+                    col[j] = lo[j]
+                break
+        else:
+            if col[m - 1] < up[m - 1]:
+                col[m - 1] += 1
+                for j in range(m - 1):
+                    col[j] = lo[j]
+            else:
+                break
+    return time.perf_counter() - t0, best
+
+
+def cpu_reference_rate(name, per_core, cores=None):
+    """Oracle port of do_optimization on `cores` worker processes (RunTHetA.py:124-171 farms
+    candidates to processes the same way): first per_core*cores candidates in enumeration order."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    jobs = [(name, i * per_core, per_core) for i in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_cpu_worker, [(name, 0, 8)] * cores)  # import / warm-up, untimed
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, jobs)
+        wall = time.perf_counter() - t0
+    total = per_core * cores
+    return {"value": total / wall, "unit": "candidates/s", "cores": cores, "kind": "port",
+            "sample": "first %d candidates of the workload in enumeration order, %d per worker process, "
+                      "oracle/theta_oracle.py (numpy+scipy restatement of Optimizer.solve), %.1f s wall"
+                      % (total, per_core, wall)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_core = 40000
+    vals = []
+    for _ in range(args.warmup and 1 or 0):
+        cpu_reference_rate(args.workload, 100)
+    res = None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = cpu_reference_rate(args.workload, per_core)
+        vals.append(res["value"])
+    wall = time.perf_counter() - t0
+    v = sum(vals) / len(vals)
+    res["value"] = v
+    P = problem(args.workload)
+    line = {"impl": "reference", "metric": "C-candidates/sec", "value": v, "unit": "candidates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": P["desc"], "n": 2, "m": P["m"], "k": P["k"]},
+            "cpu_baseline": res,
+            "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from theta_b200 import _lib, search
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    _lib.init(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    P = problem(args.workload)
+    plan = _lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"])
+    total = plan.count()
+    if P["window"]:
+        total = min(total, P["window"])
+    begin, end = search.shard_range(total, rank, world)
+    _, _, D = search._dist_state()
+
+    launches = [0]
+
+    def step():
+        lm = plan.pass1(begin, end, stream)
+        g, prior = search.exchange_minima(lm, D, rank, world)
+        recs = plan.pass2(g, prior, stream)
+        launches[0] += 1 + (1 if plan.stats()["n_rescanned"] else 0)
+        return search.gather_records(recs, D, world), g
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p1_ms = []
+    e0.record()
+    for _ in range(args.steps):
+        recs, g = step()
+        p1_ms.append(plan.stats()["ms_pass1"])
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    st = plan.stats()
+    value = total * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: the public call (host buffers in, Python `best` list out), every step from scratch
+    def e2e_step():
+        return search.do_optimization_single(2, P["m"], P["k"], 2, list(P["lower"]), list(P["upper"]), P["r"], P["rN"],
+                                             1.0, P["sorted_index"], True, False)
+    e2e = None
+    if not P["window"]:
+        for _ in range(2):
+            best = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            best = e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        h2d = plan.m * (8 + 8 + 4 + 4) + 2 * 8 * (plan.pitch + 1) * 2
+        d2h = 8 * st["n_stripes"] + 48 * max(1, len(recs)) + (48 + 8 * plan.m + plan.pitch) * max(1, len(best))
+        e2e = {"value": total * args.steps / float(tdt.item()), "unit": "candidates/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "best_nll": float(best[0][2]), "best_mu0": float(best[0][1][0]), "n_best": len(best)}
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the streaming NLL kernel (rank 0 only; tiles > L2 so every launch streams from HBM)
+    roof = None
+    extra = {}
+    if rank == 0:
+        lib = _lib.load()
+        cnt = min(plan.count(), 4 * 1024 * 1024)
+        pitch = plan.pitch
+        tiles = torch.empty(cnt * pitch, dtype=torch.int8, device="cuda")
+        mu = torch.empty(cnt, dtype=torch.float64, device="cuda")
+        nll = torch.empty(cnt, dtype=torch.float64, device="cuda")
+        stt = torch.empty(cnt, dtype=torch.int32, device="cuda")
+        _lib.check(lib.theta_enumerate_n2_dev(plan.handle, plan.count() // 3, cnt, tiles.data_ptr(), pitch, stream))
+        _lib.check(lib.theta_solve_tiles_n2_dev(plan.handle, tiles.data_ptr(), pitch, cnt, mu.data_ptr(), nll.data_ptr(),
+                                                stt.data_ptr(), stream))
+        torch.cuda.synchronize()
+        nll_ref = nll.clone()
+        for _ in range(3):
+            _lib.check(lib.theta_nll_tiles_n2_dev(plan.handle, tiles.data_ptr(), pitch, cnt, mu.data_ptr(), nll.data_ptr(), stream))
+        torch.cuda.synchronize()
+        reps = 10
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            _lib.check(lib.theta_nll_tiles_n2_dev(plan.handle, tiles.data_ptr(), pitch, cnt, mu.data_ptr(), nll.data_ptr(), stream))
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        t_nll = sum(ev[i].elapsed_time(ev[i + 1]) for i in range(reps)) / reps
+        okm = stt < 8
+        maxrel = float(((nll[okm] - nll_ref[okm]).abs() / nll_ref[okm].abs()).max().item()) if bool(okm.any()) else 0.0
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak = float(json.load(f)["hbm_gbs"])
+                peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+        bytes_alg = cnt * (plan.m + 8 + 8)
+        ach = bytes_alg / (t_nll * 1e-3) / 1e9
+        roof = {"kernel": "tiles_n2_kernel<false> (theta_nll_tiles_n2: Optimizer.L2 over int8 C tiles)",
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "bytes_per_candidate": plan.m + 16, "candidates_per_launch": cnt,
+                "ms_per_launch": t_nll, "tile_bytes": cnt * pitch, "check_max_rel_err_vs_solve": maxrel}
+        del tiles, mu, nll, stt
+        # fused search kernel: device time and fp64 rate
+        fp64 = _lib.fp64_peak_gflops(stream)
+        extra["fp64_peak_gflops_measured"] = fp64
+    # search kernel own numbers (all ranks ran it; report rank 0's)
+    search_kernel = {"kernel": "n2_search_kernel<KT,false>", "ms_pass1_mean": sum(p1_ms) / len(p1_ms),
+                     "ms_pass2_last": st["ms_pass2"], "candidates_per_launch": int(end - begin),
+                     "cand_per_s_kernel": (end - begin) / (sum(p1_ms) / len(p1_ms) * 1e-3),
+                     "newton_iters_mean": st["newton_iters"], "stripes": int(st["n_stripes"]),
+                     "rescanned_stripes": int(st["n_rescanned"])}
+
+    if rank == 0 and not args.no_extra and args.workload == "cfg2" and world == 1:
+        P7 = problem("m150k7")
+        plan7 = _lib.Plan(2, P7["r"], P7["rN"], P7["lower"], P7["upper"])
+        n7 = plan7.count()
+        for _ in range(2):
+            g7 = plan7.pass1(0, n7, stream)
+            plan7.pass2(g7)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g7 = plan7.pass1(0, n7, stream)
+        r7 = plan7.pass2(g7)
+        torch.cuda.synchronize()
+        dt7 = time.perf_counter() - t0
+        extra["m150_k7_full_space"] = {"candidates": n7, "seconds": dt7, "cand_per_s": n7 / dt7, "min_nll": g7,
+                                       "ms_pass1": plan7.stats()["ms_pass1"]}
+        plan7.close()
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cpu = cpu_reference_rate(args.workload, 40000)
+
+    if rank == 0:
+        line = {"metric": "C-candidates/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": P["desc"], "n": 2, "m": P["m"], "k": P["k"], "candidates": int(total),
+                           "sharding": "contiguous rank ranges, %d per GPU" % ((total + world - 1) // world),
+                           "l2_policy": "search kernel streams nothing from HBM (tables in shared memory); the "
+                                        "roofline kernel uses tiles of %d MiB > L2" % (roof["tile_bytes"] >> 20 if roof else 0)},
+                "e2e": e2e, "gpu_launches": launches[0], "clocks": clocks, "roofline": roof,
+                "search_kernel": search_kernel, "cpu_baseline": cpu, "extra": extra,
+                "result": {"min_nll": g, "n_records": int(len(recs)), "n_solved": int(st["n_solved"])}}
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

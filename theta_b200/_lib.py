@@ -181,7 +181,7 @@ class Plan(object):
         return float(g.value)
 
     def pass2(self, global_min, prior_min=float("inf"), stream=None):
-        cap = 1 << 16
+        cap = 1 << 12
         while True:
             buf = np.zeros(cap, dtype=CAND_DTYPE)
             n = C.c_uint64()

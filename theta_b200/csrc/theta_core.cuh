@@ -39,6 +39,7 @@ struct SolveOut {
 };
 
 #define THETA_NEWTON_MAXIT 100
+#define THETA_NEWTON_RTOL 1e-9
 
 // Evaluate f and f' at x over the non-empty groups.
 template <int KV>
@@ -143,11 +144,16 @@ __device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool 
             n2_f_df<KV>(nv, ev, S1, k.A, x, f, fp);
             if (f == 0.0) break;
             if ((f < 0.0) == rising) lo = x; else hi = x;
-            double xn = x - f / fp;
-            if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-            const double dx = fabs(xn - x);
-            x = xn;
-            if (dx <= 1e-14 * fabs(xn)) break;
+            const double dx = -f / fp;
+            double xn = x + dx;
+            const bool inside = (xn > lo && xn < hi);
+            // Newton converges quadratically: once a step is below 1e-9 |x| the iterate after it is
+            // accurate to ~1e-18 relative (the reference's brenth stops at 2e-12 absolute, Optimizer.py:118).
+            if (fabs(dx) <= THETA_NEWTON_RTOL * fabs(x)) {
+                if (inside) x = xn;
+                break;
+            }
+            x = inside ? xn : 0.5 * (lo + hi);
         }
         o.iters = it + 1;
         if (it >= THETA_NEWTON_MAXIT) {

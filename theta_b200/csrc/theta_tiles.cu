@@ -30,7 +30,8 @@
 namespace theta {
 
 static constexpr int kRows = 128;   // rows per tile == threads per CTA
-static constexpr int kStages = 4;
+static constexpr int kStages = 2;
+static constexpr int kMaxRuns = 16;  // run list per row kept in shared memory; longer rows take the direct path
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -80,6 +81,7 @@ struct TileSmem {
     double* PR;
     double* PRN;
     int32_t* ZP;
+    uint16_t* runs;  // [kMaxRuns][kRows]: (value << 10) | end
     double* hist;
 };
 
@@ -89,6 +91,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int64_t pitch, int hist_levels
     o += sizeof(double) * (pitch + 1) * 2;
     o += sizeof(int32_t) * (pitch + 1);
     o = (o + 15) & ~(size_t)15;
+    o += sizeof(uint16_t) * kMaxRuns * kRows;
     o += sizeof(double) * (size_t)hist_levels * kRows;
     return o;
 }
@@ -106,6 +109,8 @@ __device__ __forceinline__ TileSmem tile_smem_bind(unsigned char* base, int64_t 
     s.ZP = reinterpret_cast<int32_t*>(base + o);
     o += sizeof(int32_t) * (pitch + 1);
     o = (o + 15) & ~(size_t)15;
+    s.runs = reinterpret_cast<uint16_t*>(base + o);
+    o += sizeof(uint16_t) * kMaxRuns * kRows;
     s.hist = reinterpret_cast<double*>(base + o);
     return s;
 }
@@ -155,6 +160,40 @@ __device__ __forceinline__ void scan_runs(const unsigned char* row, int words, F
     on_run(cur, start, words * 8);
 }
 
+// Fast scan: collect the runs of a row into the per-thread run list (shared memory, column `tid`).
+// A word whose 8 bytes all equal the current value costs five integer instructions.  Returns the
+// number of runs, or -1 if the row has more than kMaxRuns runs / a value above 63 (caller falls back
+// to scan_runs).  Positions >= m (zero padding) never open a run.
+__device__ __forceinline__ int collect_runs(const unsigned char* row, int words, int m, uint16_t* runs) {
+    const uint2* rw = reinterpret_cast<const uint2*>(row);
+    uint2 w = rw[0];
+    uint32_t cur = w.x & 0xffu;
+    uint32_t curpat = cur * 0x01010101u;
+    int n = 0;
+    bool over = false;
+    for (int wi = 0; wi < words; ++wi) {
+        if (wi) w = rw[wi];
+        if (((w.x ^ curpat) | (w.y ^ curpat)) != 0u) {
+            const uint64_t ww = ((uint64_t)w.y << 32) | w.x;
+            uint64_t x = ww ^ ((ww << 8) | cur);
+            while (x) {
+                const int b = (__ffsll((long long)x) - 1) >> 3;
+                const int pos = wi * 8 + b;
+                if (pos >= m) break;
+                if (n < kMaxRuns - 1 && cur < 64u) runs[n * kRows] = (uint16_t)((cur << 10) | (uint32_t)pos);
+                else over = true;
+                ++n;
+                cur = (uint32_t)(ww >> (8 * b)) & 0xffu;
+                x &= ~(0xffull << (8 * b));
+            }
+            curpat = cur * 0x01010101u;
+        }
+    }
+    if (over || cur >= 64u) return -1;
+    runs[n * kRows] = (uint16_t)((cur << 10) | (uint32_t)m);
+    return n + 1;
+}
+
 template <bool SOLVE, int KT>
 __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -199,16 +238,34 @@ __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
         const int64_t row = t * kRows + tid;
         if (row < p.count) {
             const unsigned char* rp = S.ring + ((size_t)slot * kRows + tid) * p.pitch;
+            uint16_t* myruns = S.runs + tid;
+            const int nr = collect_runs(rp, words, kc.m, myruns);
             if (!SOLVE) {
                 const double mu = p.mu_in[row];
                 const double mu1 = 1.0 - mu;
                 const double tm = kc.tau * mu;
                 double acc = 0.0, s1 = 0.0;
-                scan_runs(rp, words, [&](uint32_t v, int s, int e) {
-                    const double wgt = S.PR[e] - S.PR[s];
-                    s1 = fma((double)v, S.PRN[e] - S.PRN[s], s1);
-                    if (wgt != 0.0) acc = fma(wgt, log(fma((double)v, mu1, tm)), acc);
-                });
+                if (nr >= 0) {
+                    // every lane walks its own (short) run list in lockstep: one log per run
+                    double pr_s = 0.0, prn_s = 0.0;
+                    for (int j = 0; j < nr; ++j) {
+                        const uint32_t code = myruns[j * kRows];
+                        const int e = (int)(code & 1023u);
+                        const double v = (double)(code >> 10);
+                        const double pr_e = S.PR[e], prn_e = S.PRN[e];
+                        const double wgt = pr_e - pr_s;
+                        s1 = fma(v, prn_e - prn_s, s1);
+                        if (wgt != 0.0) acc = fma(wgt, log(fma(v, mu1, tm)), acc);
+                        pr_s = pr_e;
+                        prn_s = prn_e;
+                    }
+                } else {
+                    scan_runs(rp, words, [&](uint32_t v, int s, int e) {
+                        const double wgt = S.PR[e] - S.PR[s];
+                        s1 = fma((double)v, S.PRN[e] - S.PRN[s], s1);
+                        if (wgt != 0.0) acc = fma(wgt, log(fma((double)v, mu1, tm)), acc);
+                    });
+                }
                 const double gbar = (mu * kc.S0 + mu1 * s1) / kc.A;
                 double nll = kc.K0 - (acc - kc.Rtot * log(gbar));
                 if (kc.any_zero_rN) nll = INFINITY;
@@ -219,13 +276,24 @@ __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
                 for (int v = 0; v <= KT; ++v) h[v * kRows] = 0.0;
                 double s1 = 0.0;
                 bool z0 = false, bad = false;
-                scan_runs(rp, words, [&](uint32_t v, int s, int e) {
+                auto on_run = [&](uint32_t v, int s, int e) {
                     const double wgt = S.PR[e] - S.PR[s];
                     if (v > (uint32_t)KT) { if (S.PRN[e] - S.PRN[s] != 0.0 || wgt != 0.0) bad = true; return; }
                     s1 = fma((double)v, S.PRN[e] - S.PRN[s], s1);
                     h[v * kRows] += wgt;
                     if (v == 0 && S.ZP[e] - S.ZP[s] > 0) z0 = true;
-                });
+                };
+                if (nr >= 0) {
+                    int st = 0;
+                    for (int j = 0; j < nr; ++j) {
+                        const uint32_t code = myruns[j * kRows];
+                        const int e = (int)(code & 1023u);
+                        on_run(code >> 10, st, e);
+                        st = e;
+                    }
+                } else {
+                    scan_runs(rp, words, on_run);
+                }
                 double R[KT + 1];
 #pragma unroll
                 for (int v = 0; v <= KT; ++v) R[v] = h[v * kRows];
@@ -263,6 +331,7 @@ static int check_tile_args(const theta_plan* pl, const void* cols, int64_t pitch
     if (!pl || !cols) { set_error("null argument"); return THETA_ERR_INVALID; }
     if (pl->n != 2) { set_error("plan is not n=2"); return THETA_ERR_INVALID; }
     if (count < 0) { set_error("negative count"); return THETA_ERR_INVALID; }
+    if (pl->m > 1023) { set_error("tile kernels support m <= 1023"); return THETA_ERR_UNSUPPORTED; }
     if (pitch != pl->tile_pitch) {
         set_error("pitch %lld invalid: tile kernels need theta_tile_pitch(m) = %lld", (long long)pitch, (long long)pl->tile_pitch);
         return THETA_ERR_INVALID;
