@@ -209,6 +209,8 @@ def gen_n3_small(R):
                                      vals=[float(v) for v in b[3]]) for b in best]))
         print("n3 small", m, "N", len(stream), "none", sum(1 for s in stream if s[1] is None), "best", len(best))
     _dump("n3_small_full.json", cases)
+    import subprocess
+    subprocess.check_call(["gzip", "-9", "-f", os.path.join(GOLD, "n3_small_full.json")])
 
 
 def gen_edge(R):

@@ -1,0 +1,98 @@
+"""CPU, world_size 2 (gloo): the multi-GPU host path of theta_b200.search -- shard ranges, the
+all-reduce(min) / all-gather exchange and the record gather -- driven by a Python model of the two
+device passes, must give every rank the sequential fold's answer."""
+import multiprocessing as mp
+import os
+import socket
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class ModelPlan(object):
+    """Stands in for _lib.Plan on a GPU-less box: same pass1/pass2 contract over a given NLL stream."""
+
+    def __init__(self, nll):
+        self.nll = np.asarray(nll, dtype=np.float64)
+        self.range = (0, 0)
+
+    def count(self):
+        return len(self.nll)
+
+    def pass1(self, b, e, stream=None):
+        self.range = (b, e)
+        v = self.nll[b:e]
+        v = v[~np.isnan(v)]
+        return float(v.min()) if len(v) else float("inf")
+
+    def pass2(self, g, prior=float("inf"), stream=None):
+        from theta_b200 import _lib
+        b, e = self.range
+        keep, run = [], prior
+        for rk in range(b, e):
+            v = self.nll[rk]
+            if np.isnan(v):
+                continue  # None candidate
+            if v < run or v <= g + 2.5e-3:
+                keep.append((rk, v))
+            if v < run:
+                run = v
+        out = np.zeros(len(keep), dtype=_lib.CAND_DTYPE)
+        for i, (rk, v) in enumerate(keep):
+            out[i]["rank"] = rk
+            out[i]["nll"] = v
+            out[i]["mu"][0] = 0.25
+        return out
+
+    def stats(self):
+        b, e = self.range
+        return {"n_solved": int((~np.isnan(self.nll[b:e])).sum()), "n_rescanned": 0, "ms_pass2": 0.0}
+
+
+def _worker(rank, world, port, nll, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from theta_b200 import search
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = search.search_n2(ModelPlan(nll))
+        q.put((rank, [b[0] for b in res.best], res.min_nll, res.n_solved, len(res.records)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_rank_search_matches_sequential_fold():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import theta_oracle as O
+    rng = np.random.default_rng(5)
+    n = 5000
+    nll = 3e9 + np.cumsum(rng.choice([-1, 1], size=n) * rng.choice([0.0, 4e-4, 9e-4, 2.0, 50.0], size=n))
+    nll[rng.integers(0, n, 40)] = np.nan          # None candidates
+    nll[3000] = np.nanmin(nll) - 5e-4              # a late candidate inside the tie window of the minimum
+    seq = O.fold([(0, float(nll[0]))] * (0 if np.isnan(nll[0]) else 1) +
+                 [(i, float(v)) for i, v in enumerate(nll) if not np.isnan(v)])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, nll, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, best, g, solved, nrec in outs:
+        assert best == seq, "rank %d" % rank
+        assert g == float(np.nanmin(nll))
+        assert solved == int((~np.isnan(nll)).sum())

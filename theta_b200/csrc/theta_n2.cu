@@ -55,7 +55,7 @@ __device__ __forceinline__ void stage_tables(unsigned char* smem, const unsigned
 // each thread unranks the first column of its run once and then walks L columns with the
 // odometer, warm-starting the root-finder from the previous column's root.
 template <int KT, bool EMIT>
-__global__ void __launch_bounds__(kBlock) n2_search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(kBlock, 6) n2_search_kernel(const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double s_red[kBlock / 32];
     __shared__ uint32_t s_ticket;
@@ -79,16 +79,24 @@ __global__ void __launch_bounds__(kBlock) n2_search_kernel(const SearchParams p)
             const int cnt = (int)min((uint64_t)p.L, p.end - r0);
             int q[KT];
             n2_unrank<KT>(T, r0, q);
-            double xprev = -1.0;
+            double xprev = -1.0, xprev2 = -1.0;  // roots of the previous two columns (warm start)
             for (int t = 0; t < cnt; ++t) {
                 double R[KT + 1], S1;
                 bool z;
                 n2_groups<KT>(T, q, R, S1, z);
                 SolveOut o;
-                n2_solve<KT + 1>(R, S1, z, kc, xprev, o);
+                // consecutive columns differ in one breakpoint, so the root moves smoothly: start Newton
+                // from the linear extrapolation of the last two roots (falls back to the last root)
+                double x0 = xprev;
+                if (xprev2 > 0.0) {
+                    const double xe = 2.0 * xprev - xprev2;
+                    if (xe > 0.0 && xe < 1.0) x0 = xe;
+                }
+                n2_solve<KT + 1>(R, S1, z, kc, x0, o);
                 if (o.status < THETA_ST_NONE_SIGN) {
                     ++solved;
                     iters += o.iters;
+                    xprev2 = xprev;
                     xprev = o.x;
                     const double nll = o.nll;
                     bool emit = false;
