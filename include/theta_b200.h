@@ -43,6 +43,8 @@ extern "C" {
 #define THETA_ST_ROOT_LB 1     /* brenth: f(lB)==0, returns lB (Q17) */
 #define THETA_ST_ROOT_UB 2     /* brenth: f(uB)==0, returns uB */
 #define THETA_ST_FALLBACK_X0 3 /* n=3: BFGS fallback returned its start point (1/3,1/3,1/3) (H2 outcome a) */
+#define THETA_ST_DEGENERATE 4  /* n=3: both tumour columns zero == all-normal model; NLL valid, mu undefined (Q2/Q8) */
+#define THETA_ST_FALLBACK_MOVED 5 /* n=3: BFGS fallback took a step and stayed inside [0,1]^3 (not observed on the reference) */
 #define THETA_ST_NONE_SIGN 8   /* f(lB), f(uB) have the same sign */
 #define THETA_ST_NONE_NAN 9    /* NaN in the objective (zero column, 0/0) */
 #define THETA_ST_NONE_NOCONV 10
@@ -104,6 +106,9 @@ int theta_plan_create(const theta_problem* p, theta_plan** out);
 void theta_plan_destroy(theta_plan* plan);
 /* TimeEstimate.count_number_matrices_2 (TimeEstimate.py:91-111). */
 int theta_plan_count(const theta_plan* plan, uint64_t* count);
+/* NLL of the all-normal model, -sum r_i log(rN_i / sum rN): what the reference evaluates for the
+ * all-[tau,0,0] matrix that opens every n=3 search (RunTHetA.py:148,188 -- Q2). */
+int theta_plan_null_nll(const theta_plan* plan, double* nll);
 /* Monotonised bounds as used by the search (Q16). */
 int theta_plan_bounds(const theta_plan* plan, int32_t* lower, int32_t* upper);
 
@@ -144,6 +149,26 @@ int theta_nll_tiles_n2_dev(theta_plan* plan, const int8_t* cols_dev, int64_t pit
                            const double* mu_dev, double* nll_dev, void* stream);
 int theta_nll_tiles_n2(theta_plan* plan, const int8_t* cols_host, int64_t pitch, int64_t count, const double* mu_host,
                        double* nll_host);
+
+/* ---- n = 3 (Enumerator._generate_next_C_3, Enumerator.py:172-298; Optimizer._solve_n3plus, Optimizer.py:128-165) ---- */
+/* Row table of the plan: rows[g] = (a_g, b_g) in the reference's order (first component fastest). */
+int theta_n3_rows(const theta_plan* plan, int32_t* a, int32_t* b, int32_t* n_rows);
+/* Cut the DFS forest into lexicographically ordered work items (sub-trees) of at most ~leaf_cap
+ * candidates (count DP of TimeEstimate.count_number_matrices_3, TimeEstimate.py:113-142, per sub-tree). */
+int theta_n3_prepare(theta_plan* plan, int64_t leaf_cap, int64_t max_items, uint64_t* n_items);
+int theta_n3_item_weights(const theta_plan* plan, double* weights /* [n_items] estimated leaves */);
+/* Pass 1 / pass 2 over items [item_begin, item_end): same contract as the n=2 passes; a record's
+ * `rank` is (item << 32) | sequence number inside the item, `flags` indexes paths_host. */
+int theta_search_n3_pass1(theta_plan* plan, uint64_t item_begin, uint64_t item_end, double* local_min, void* stream);
+int theta_search_n3_pass2(theta_plan* plan, double global_min, double prior_min, theta_cand* out_host, uint64_t cap,
+                          uint64_t* n_out, uint8_t* paths_host /* [cap][m] row indices */, void* stream);
+/* Every candidate of items [item_begin, item_end) in enumeration order, as row-index strings. */
+int theta_enumerate_n3(theta_plan* plan, uint64_t item_begin, uint64_t item_end, uint8_t* paths_host, uint64_t cap,
+                       uint64_t* n_out);
+/* Optimizer.solve on explicit candidates given as row-index strings [count][m]. */
+int theta_solve_rows_n3(theta_plan* plan, const uint8_t* paths_host, int64_t count, double* mu_host /* [count][3] */,
+                        double* muhat_host /* [count][3] or NULL */, double* nll_host, int32_t* status_host,
+                        double* vals_host /* [count][m] or NULL */);
 
 /* ---- CalcAllC.L2 / L3 (CalcAllC.py:44-76): masked NLL of one weighted matrix at a given mu ---- */
 /* Cw is [m][n] row-major fp64 (already weighted by rN); valid_i = Cw[i][0] != 0 (L2 with mu==0: Cw[i][1] != 0).

@@ -1,0 +1,128 @@
+"""GPU parity tests for n=3: on-chip DFS enumeration, KKT solve (hybrj restatement + BFGS-fallback
+classification) and the sharded search, against the golden streams of the live reference.
+
+Rank-deficient candidates (distinct rows collinear -> mu not identifiable; the reference's own answer
+depends on rounding noise) are checked for enumeration order only.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from test_n3_solver_host import collinear
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from theta_b200 import _lib
+    _lib.init(0)
+    return _lib
+
+
+def test_enumeration_order_and_per_candidate_parity(lib, golden):
+    for case in golden("n3_small_full.json.gz"):
+        plan = lib.Plan(3, case["r"], case["rN"], case["lower"], case["upper"])
+        rows = plan.rows()
+        assert rows == [tuple(x) for x in case["rows"]]
+        gold = case["stream"][1:]  # [0] is the all-[tau,0,0] matrix (Q2)
+        for cap in (16, 4096):
+            plan.prepare(cap)
+            paths = plan.enumerate_n3()
+            keys = ["".join("%d%d" % rows[g] for g in p) for p in paths]
+            assert keys == [s[0] for s in gold], "enumeration order with leaf_cap=%d" % cap
+        mu, mh, nll, st, vals = plan.solve_rows(paths, want_vals=True)
+        n_reg = 0
+        for i, s in enumerate(gold):
+            if collinear(s[0]):
+                continue
+            n_reg += 1
+            if s[2] is None:
+                assert st[i] >= 8, (s[0], st[i])
+                continue
+            assert st[i] < 8, (s[0], st[i])
+            assert abs(nll[i] - s[2]) <= 1e-10 * abs(s[2]), (s[0], nll[i], s[2])
+            assert max(abs(mu[i][j] - s[1][j]) for j in range(3)) <= 1e-9, (s[0], mu[i], s[1])
+        assert n_reg > 0.9 * len(gold)
+        # the all-normal pseudo candidate: the reference's NLL for the bogus first matrix
+        assert abs(plan.null_nll() - case["stream"][0][2]) <= 1e-12 * case["stream"][0][2]
+        plan.close()
+
+
+def test_search_matches_reference_best(lib, golden):
+    from theta_b200.search import do_optimization_single
+    for case in golden("n3_small_full.json.gz"):
+        best = do_optimization_single(3, case["m"], case["k"], 2, list(case["lower"]), list(case["upper"]), case["r"],
+                                      case["rN"], 1.0, case["sorted_index"], True, False)
+        ref = case["best"]
+        assert len(best) == len(ref)
+        for b, g in zip(best, ref):
+            assert np.array_equal(b[0], np.array(g["C"]))
+            assert np.abs(np.array(b[1]) - np.array(g["mu"])).max() <= 1e-9
+            assert abs(b[2] - g["nll"]) <= 1e-10 * g["nll"]
+            assert np.allclose(b[3], g["vals"], rtol=1e-9, atol=0)
+
+
+def test_search_equals_bruteforce_fold(lib, golden):
+    """pass1/pass2 + replay == the reference fold over every solved candidate (computed on the GPU too)."""
+    from theta_b200.search import fold_replay
+    from theta_b200.search_n3 import search_n3
+    case = golden("n3_small_full.json.gz")[2]
+    plan = lib.Plan(3, case["r"], case["rN"], case["lower"], case["upper"])
+    for cap in (8, 64, 100000):
+        res = search_n3(plan, leaf_cap=cap)
+        paths = plan.enumerate_n3()
+        mu, mh, nll, st, _ = plan.solve_rows(paths)
+        ok = st < 8
+        keys = np.concatenate([[0], np.nonzero(ok)[0] + 1]).astype(np.uint64)
+        vals = np.concatenate([[plan.null_nll()], nll[ok]])
+        full = fold_replay(keys, vals, dup_first=False)
+        want = [None if i == 0 else tuple(paths[int(keys[i]) - 1]) for i in full]
+        got = [None if b[0] is None else tuple(b[0]) for b in res.best]
+        assert got == want
+        assert res.count == len(paths) + 1
+        assert res.n_solved == int(ok.sum()) + 1
+    plan.close()
+
+
+def test_optimizer_and_enumerator_mirrors(lib, golden):
+    from theta_b200.enumerator import Enumerator
+    from theta_b200.optimizer import Optimizer
+    case = golden("n3_small_full.json.gz")[0]
+    m = case["m"]
+    en = Enumerator(3, m, 3, 2, list(case["lower"]), list(case["upper"]), True)
+    opt = Optimizer(case["r"], case["rN"], m, 3, 2)
+    gold = case["stream"][1:]
+    for i in range(40):
+        C = en.generate_next_C()
+        key = "".join("%d%d" % (int(a), int(b)) for a, b in C[:, 1:])
+        assert key == gold[i][0]
+        if collinear(key):
+            continue
+        s = opt.solve(C)
+        if gold[i][2] is None:
+            assert s is None
+        else:
+            assert np.abs(np.array(s[0]) - np.array(gold[i][1])).max() <= 1e-9
+            assert abs(s[1] - gold[i][2]) <= 1e-10 * gold[i][2]
+    # n = 2 mirrors
+    g2 = golden("n2_small_full.json")[3]
+    en2 = Enumerator(2, g2["m"], g2["k"], 2, list(g2["lower"]), list(g2["upper"]))
+    opt2 = Optimizer(g2["r"], g2["rN"], g2["m"], 2, 2, upper_bound=g2["max_normal"])
+    n = 0
+    while True:
+        C = en2.generate_next_C()
+        if C is False:
+            break
+        s = g2["stream"][n]
+        assert "".join(str(int(v)) for v in C[:, 1]) == s[0]
+        if n % 37 == 0:
+            out = opt2.solve(C)
+            if s[2] is None:
+                assert out is None
+            else:
+                assert abs(out[0][0] - s[1]) <= 1e-9 and abs(out[1] - s[2]) <= 1e-10 * s[2]
+                assert len(out[2]) == g2["m"] and abs(sum(out[2]) - 1) < 1e-12
+        n += 1
+    assert n == len(g2["stream"])

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtheta_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_EMPTY, ERR_OVERFLOW, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-ST_OK, ST_ROOT_LB, ST_ROOT_UB, ST_FALLBACK_X0 = 0, 1, 2, 3
+ST_OK, ST_ROOT_LB, ST_ROOT_UB, ST_FALLBACK_X0, ST_DEGENERATE, ST_FALLBACK_MOVED = 0, 1, 2, 3, 4, 5
 ST_NONE_SIGN, ST_NONE_NAN, ST_NONE_NOCONV, ST_NONE_RANGE = 8, 9, 10, 11
 TIE_MARGIN = 10e-4  # Misc.isClose default margin (python/Misc.py:36)
 
@@ -63,6 +63,14 @@ SYMBOLS = {
     "theta_plan_destroy": (None, [_VP]),
     "theta_plan_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "theta_plan_bounds": (C.c_int, [_VP, _VP, _VP]),
+    "theta_plan_null_nll": (C.c_int, [_VP, C.POINTER(C.c_double)]),
+    "theta_n3_rows": (C.c_int, [_VP, _VP, _VP, C.POINTER(C.c_int32)]),
+    "theta_n3_prepare": (C.c_int, [_VP, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
+    "theta_n3_item_weights": (C.c_int, [_VP, _VP]),
+    "theta_search_n3_pass1": (C.c_int, [_VP, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), _VP]),
+    "theta_search_n3_pass2": (C.c_int, [_VP, C.c_double, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP, _VP]),
+    "theta_enumerate_n3": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "theta_solve_rows_n3": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP]),
     "theta_enumerate_n2": (C.c_int, [_VP, C.c_uint64, C.c_int64, _VP, C.c_int64]),
     "theta_enumerate_n2_dev": (C.c_int, [_VP, C.c_uint64, C.c_int64, _VP, C.c_int64, _VP]),
     "theta_tile_pitch": (C.c_int64, [C.c_int32]),
@@ -168,6 +176,79 @@ class Plan(object):
         up = np.zeros(self.m, dtype=np.int32)
         check(load().theta_plan_bounds(self._h, ptr(lo), ptr(up)))
         return lo, up
+
+    def null_nll(self):
+        g = C.c_double()
+        check(load().theta_plan_null_nll(self._h, C.byref(g)))
+        return float(g.value)
+
+    # ---- n = 3 ----
+    def rows(self):
+        a = np.zeros(64, dtype=np.int32)
+        b = np.zeros(64, dtype=np.int32)
+        n = C.c_int32()
+        check(load().theta_n3_rows(self._h, ptr(a), ptr(b), C.byref(n)))
+        return [(int(x), int(y)) for x, y in zip(a[:n.value], b[:n.value])]
+
+    def prepare(self, leaf_cap=256, max_items=1 << 22):
+        n = C.c_uint64()
+        check(load().theta_n3_prepare(self._h, int(leaf_cap), int(max_items), C.byref(n)))
+        self.n_items = int(n.value)
+        return self.n_items
+
+    def item_weights(self):
+        w = np.zeros(self.n_items, dtype=np.float64)
+        if self.n_items:
+            check(load().theta_n3_item_weights(self._h, ptr(w)))
+        return w
+
+    def pass1_n3(self, item_begin, item_end, stream=None):
+        g = C.c_double()
+        check(load().theta_search_n3_pass1(self._h, int(item_begin), int(item_end), C.byref(g), stream))
+        return float(g.value)
+
+    def pass2_n3(self, global_min, prior_min=float("inf"), stream=None):
+        cap = 1 << 12
+        while True:
+            buf = np.zeros(cap, dtype=CAND_DTYPE)
+            paths = np.zeros((cap, self.m), dtype=np.uint8)
+            n = C.c_uint64()
+            rc = load().theta_search_n3_pass2(self._h, float(global_min), float(prior_min), ptr(buf), cap, C.byref(n),
+                                              ptr(paths), stream)
+            if rc == ERR_OVERFLOW and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            check(rc)
+            return buf[:int(n.value)], paths[:int(n.value)]
+
+    def enumerate_n3(self, item_begin=0, item_end=None):
+        """Row-index strings [count, m] of every candidate of the given items, in enumeration order."""
+        if item_end is None:
+            item_end = self.n_items
+        cap = 1 << 16
+        while True:
+            paths = np.zeros((cap, self.m), dtype=np.uint8)
+            n = C.c_uint64()
+            rc = load().theta_enumerate_n3(self._h, int(item_begin), int(item_end), ptr(paths), cap, C.byref(n))
+            if rc == ERR_OVERFLOW and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            check(rc)
+            return paths[:int(n.value)]
+
+    def solve_rows(self, paths, want_vals=False):
+        """Optimizer.solve (n=3) on row-index strings [count, m] -> (mu[count,3], muhat, nll, status, vals)."""
+        paths = np.ascontiguousarray(np.asarray(paths, dtype=np.uint8))
+        cnt = paths.shape[0]
+        mu = np.zeros((cnt, 3))
+        mh = np.zeros((cnt, 3))
+        nll = np.zeros(cnt)
+        st = np.zeros(cnt, dtype=np.int32)
+        vals = np.zeros((cnt, self.m)) if want_vals else None
+        if cnt:
+            check(load().theta_solve_rows_n3(self._h, ptr(paths), cnt, ptr(mu), ptr(mh), ptr(nll), ptr(st),
+                                             ptr(vals) if want_vals else None))
+        return mu, mh, nll, st, vals
 
     def enumerate(self, rank_begin, count):
         """int8 [count, m] tumour columns of consecutive ranks (Enumerator.generate_next_C order)."""

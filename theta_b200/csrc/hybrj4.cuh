@@ -1,0 +1,410 @@
+// hybrj4.cuh -- MINPACK's hybrj (Powell hybrid method with an analytic Jacobian), restated for
+// the fixed size N = 4 that Optimizer._solve_n3plus needs (unknowns mu_hat_0..2 and the Lagrange
+// multiplier; python/Optimizer.py:147-149 calls scipy.optimize.fsolve(..., fprime=jacobian), i.e.
+// MINPACK hybrj with xtol = 1.49012e-8, maxfev = 100*(N+1), factor = 100, mode = 1).
+//
+// The reference never checks fsolve's status and stops at a loose xtol, so mu parity at 1e-9 needs
+// the same iterate sequence, not just the same fixed point.  This file follows the
+// published algorithm (More, Garbow, Hillstrom: "User Guide for MINPACK-1", ANL-80-74; routines
+// hybrj, qrfac, qform, dogleg, r1updt, r1mpyq, enorm) step by step, including its storage
+// conventions (R packed by rows, Givens rotations encoded in a single number).
+// Everything is __host__ __device__ so the same code is unit-tested on the CPU against SciPy
+// (tests/test_hybrj_port.py builds a host harness) and runs inside the CUDA kernels.
+#pragma once
+#include <math.h>
+
+#ifndef __CUDACC__
+#define THETA_HD inline
+#else
+#define THETA_HD __host__ __device__ __forceinline__
+#endif
+
+namespace theta {
+namespace mp {
+
+constexpr int N = 4;
+constexpr int LR = N * (N + 1) / 2;
+constexpr double EPSMCH = 2.220446049250313e-16;   // dpmpar(1)
+constexpr double GIANT = 1.7976931348623157e308;   // dpmpar(3)
+
+THETA_HD double enorm(int n, const double* x) {
+    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0, x1max = 0.0, x3max = 0.0;
+    const double agiant = rgiant / (double)n;
+    for (int i = 0; i < n; ++i) {
+        const double xabs = fabs(x[i]);
+        if (xabs > rdwarf && xabs < agiant) {
+            s2 += xabs * xabs;
+        } else if (xabs <= rdwarf) {
+            if (xabs > x3max) {
+                const double t = x3max / xabs;
+                s3 = 1.0 + s3 * (t * t);
+                x3max = xabs;
+            } else if (xabs != 0.0) {
+                const double t = xabs / x3max;
+                s3 += t * t;
+            }
+        } else {
+            if (xabs > x1max) {
+                const double t = x1max / xabs;
+                s1 = 1.0 + s1 * (t * t);
+                x1max = xabs;
+            } else {
+                const double t = xabs / x1max;
+                s1 += t * t;
+            }
+        }
+    }
+    if (s1 != 0.0) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+    if (s2 != 0.0) {
+        if (s2 >= x3max) return sqrt(s2 * (1.0 + (x3max / s2) * (x3max * s3)));
+        return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
+    }
+    return x3max * sqrt(s3);
+}
+
+// a is column-major N x N: a[i + N*j]
+THETA_HD void qrfac(double* a, double* rdiag, double* acnorm) {
+    for (int j = 0; j < N; ++j) {
+        acnorm[j] = enorm(N, a + N * j);
+        rdiag[j] = acnorm[j];
+    }
+    for (int j = 0; j < N; ++j) {
+        double ajnorm = enorm(N - j, a + j + N * j);
+        if (ajnorm != 0.0) {
+            if (a[j + N * j] < 0.0) ajnorm = -ajnorm;
+            for (int i = j; i < N; ++i) a[i + N * j] /= ajnorm;
+            a[j + N * j] += 1.0;
+            for (int k = j + 1; k < N; ++k) {
+                double sum = 0.0;
+                for (int i = j; i < N; ++i) sum += a[i + N * j] * a[i + N * k];
+                const double temp = sum / a[j + N * j];
+                for (int i = j; i < N; ++i) a[i + N * k] -= temp * a[i + N * j];
+            }
+        }
+        rdiag[j] = -ajnorm;
+    }
+}
+
+THETA_HD void qform(double* q, double* wa) {
+    for (int j = 1; j < N; ++j)
+        for (int i = 0; i < j; ++i) q[i + N * j] = 0.0;
+    for (int l = 0; l < N; ++l) {
+        const int k = N - 1 - l;
+        for (int i = k; i < N; ++i) {
+            wa[i] = q[i + N * k];
+            q[i + N * k] = 0.0;
+        }
+        q[k + N * k] = 1.0;
+        if (wa[k] != 0.0) {
+            for (int j = k; j < N; ++j) {
+                double sum = 0.0;
+                for (int i = k; i < N; ++i) sum += q[i + N * j] * wa[i];
+                const double temp = sum / wa[k];
+                for (int i = k; i < N; ++i) q[i + N * j] -= temp * wa[i];
+            }
+        }
+    }
+}
+
+// r: upper triangle packed by rows (0-based l); x: output step
+THETA_HD void dogleg(const double* r, const double* diag, const double* qtb, double delta, double* x, double* wa1,
+                     double* wa2) {
+    // Gauss-Newton direction
+    int jj = LR;  // 0-based index one past the last diagonal (1-based jj = LR + 1)
+    for (int k = 1; k <= N; ++k) {
+        const int j = N - k;  // 0-based
+        jj -= k;              // now the 0-based index of r(j,j)
+        int l = jj + 1;
+        double sum = 0.0;
+        for (int i = j + 1; i < N; ++i) {
+            sum += r[l] * x[i];
+            ++l;
+        }
+        double temp = r[jj];
+        if (temp == 0.0) {
+            l = j;  // 0-based index of r(0,j)
+            for (int i = 0; i <= j; ++i) {
+                temp = fmax(temp, fabs(r[l]));
+                l += N - 1 - i;
+            }
+            temp = EPSMCH * temp;
+            if (temp == 0.0) temp = EPSMCH;
+        }
+        x[j] = (qtb[j] - sum) / temp;
+    }
+    for (int j = 0; j < N; ++j) {
+        wa1[j] = 0.0;
+        wa2[j] = diag[j] * x[j];
+    }
+    const double qnorm = enorm(N, wa2);
+    if (qnorm <= delta) return;
+    // scaled gradient direction
+    int l = 0;
+    for (int j = 0; j < N; ++j) {
+        const double temp = qtb[j];
+        for (int i = j; i < N; ++i) {
+            wa1[i] += r[l] * temp;
+            ++l;
+        }
+        wa1[j] = wa1[j] / diag[j];
+    }
+    const double gnorm = enorm(N, wa1);
+    double sgnorm = 0.0;
+    double alpha = delta / qnorm;
+    if (gnorm != 0.0) {
+        for (int j = 0; j < N; ++j) wa1[j] = (wa1[j] / gnorm) / diag[j];
+        l = 0;
+        for (int j = 0; j < N; ++j) {
+            double sum = 0.0;
+            for (int i = j; i < N; ++i) {
+                sum += r[l] * wa1[i];
+                ++l;
+            }
+            wa2[j] = sum;
+        }
+        double temp = enorm(N, wa2);
+        sgnorm = (gnorm / temp) / temp;
+        alpha = 0.0;
+        if (sgnorm < delta) {
+            const double bnorm = enorm(N, qtb);
+            temp = (bnorm / gnorm) * (bnorm / qnorm) * (sgnorm / delta);
+            const double dq = delta / qnorm, sd = sgnorm / delta;
+            temp = temp - dq * (sd * sd) + sqrt((temp - dq) * (temp - dq) + (1.0 - dq * dq) * (1.0 - sd * sd));
+            alpha = (dq * (1.0 - sd * sd)) / temp;
+        }
+    }
+    const double temp = (1.0 - alpha) * fmin(sgnorm, delta);
+    for (int j = 0; j < N; ++j) x[j] = temp * wa1[j] + alpha * x[j];
+}
+
+// s: lower triangular stored by columns (== R packed by rows); m = n = N
+THETA_HD void r1updt(double* s, const double* u, double* v, double* w, bool* sing) {
+    const double p5 = 0.5, p25 = 0.25;
+    int jj = LR - 1;  // 0-based index of s(N-1,N-1)
+    w[N - 1] = s[jj];
+    for (int nmj = 1; nmj <= N - 1; ++nmj) {
+        const int j = N - 1 - nmj;  // 0-based
+        jj -= (N - j);              // 0-based index of s(j,j)
+        w[j] = 0.0;
+        if (v[j] != 0.0) {
+            double c, sn, tau;
+            if (fabs(v[N - 1]) < fabs(v[j])) {
+                const double cotan = v[N - 1] / v[j];
+                sn = p5 / sqrt(p25 + p25 * (cotan * cotan));
+                c = sn * cotan;
+                tau = 1.0;
+                if (fabs(c) * GIANT > 1.0) tau = 1.0 / c;
+            } else {
+                const double tn = v[j] / v[N - 1];
+                c = p5 / sqrt(p25 + p25 * (tn * tn));
+                sn = c * tn;
+                tau = sn;
+            }
+            v[N - 1] = sn * v[j] + c * v[N - 1];
+            v[j] = tau;
+            int l = jj;
+            for (int i = j; i < N; ++i) {
+                const double temp = c * s[l] - sn * w[i];
+                w[i] = sn * s[l] + c * w[i];
+                s[l] = temp;
+                ++l;
+            }
+        }
+    }
+    for (int i = 0; i < N; ++i) w[i] += v[N - 1] * u[i];
+    *sing = false;
+    for (int j = 0; j < N - 1; ++j) {
+        if (w[j] != 0.0) {
+            double c, sn, tau;
+            if (fabs(s[jj]) < fabs(w[j])) {
+                const double cotan = s[jj] / w[j];
+                sn = p5 / sqrt(p25 + p25 * (cotan * cotan));
+                c = sn * cotan;
+                tau = 1.0;
+                if (fabs(c) * GIANT > 1.0) tau = 1.0 / c;
+            } else {
+                const double tn = w[j] / s[jj];
+                c = p5 / sqrt(p25 + p25 * (tn * tn));
+                sn = c * tn;
+                tau = sn;
+            }
+            int l = jj;
+            for (int i = j; i < N; ++i) {
+                const double temp = c * s[l] + sn * w[i];
+                w[i] = -sn * s[l] + c * w[i];
+                s[l] = temp;
+                ++l;
+            }
+            w[j] = tau;
+        }
+        if (s[jj] == 0.0) *sing = true;
+        jj += (N - j);
+    }
+    s[jj] = w[N - 1];
+    if (s[jj] == 0.0) *sing = true;
+}
+
+// a: m x N column-major with leading dimension lda
+THETA_HD void r1mpyq(int m, double* a, int lda, const double* v, const double* w) {
+    for (int nmj = 1; nmj <= N - 1; ++nmj) {
+        const int j = N - 1 - nmj;
+        double c, sn;
+        if (fabs(v[j]) > 1.0) {
+            c = 1.0 / v[j];
+            sn = sqrt(1.0 - c * c);
+        } else {
+            sn = v[j];
+            c = sqrt(1.0 - sn * sn);
+        }
+        for (int i = 0; i < m; ++i) {
+            const double temp = c * a[i + lda * j] - sn * a[i + lda * (N - 1)];
+            a[i + lda * (N - 1)] = sn * a[i + lda * j] + c * a[i + lda * (N - 1)];
+            a[i + lda * j] = temp;
+        }
+    }
+    for (int j = 0; j < N - 1; ++j) {
+        double c, sn;
+        if (fabs(w[j]) > 1.0) {
+            c = 1.0 / w[j];
+            sn = sqrt(1.0 - c * c);
+        } else {
+            sn = w[j];
+            c = sqrt(1.0 - sn * sn);
+        }
+        for (int i = 0; i < m; ++i) {
+            const double temp = c * a[i + lda * j] + sn * a[i + lda * (N - 1)];
+            a[i + lda * (N - 1)] = -sn * a[i + lda * j] + c * a[i + lda * (N - 1)];
+            a[i + lda * j] = temp;
+        }
+    }
+}
+
+struct Result {
+    int info, nfev, njev;
+};
+
+// Sys must provide:  void fcn(const double* x, double* fvec);  void jac(const double* x, double* fjac /*col-major*/);
+template <class Sys>
+THETA_HD Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double factor) {
+    const double p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
+    double fvec[N], fjac[N * N], diag[N], r[LR], qtf[N], wa1[N], wa2[N], wa3[N], wa4[N];
+    Result res{0, 0, 0};
+    sys.fcn(x, fvec);
+    res.nfev = 1;
+    double fnorm = enorm(N, fvec);
+    int iter = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0;
+    double delta = 0.0, xnorm = 0.0;
+    for (;;) {  // outer loop: (re)compute the Jacobian
+        bool jeval = true;
+        sys.jac(x, fjac);
+        ++res.njev;
+        qrfac(fjac, wa1, wa2);
+        if (iter == 1) {
+            for (int j = 0; j < N; ++j) {
+                diag[j] = wa2[j];
+                if (wa2[j] == 0.0) diag[j] = 1.0;
+            }
+            for (int j = 0; j < N; ++j) wa3[j] = diag[j] * x[j];
+            xnorm = enorm(N, wa3);
+            delta = factor * xnorm;
+            if (delta == 0.0) delta = factor;
+        }
+        for (int i = 0; i < N; ++i) qtf[i] = fvec[i];
+        for (int j = 0; j < N; ++j) {
+            if (fjac[j + N * j] != 0.0) {
+                double sum = 0.0;
+                for (int i = j; i < N; ++i) sum += fjac[i + N * j] * qtf[i];
+                const double temp = -sum / fjac[j + N * j];
+                for (int i = j; i < N; ++i) qtf[i] += fjac[i + N * j] * temp;
+            }
+        }
+        bool sing = false;
+        for (int j = 0; j < N; ++j) {
+            int l = j;
+            for (int i = 0; i < j; ++i) {
+                r[l] = fjac[i + N * j];
+                l += N - 1 - i;
+            }
+            r[l] = wa1[j];
+            if (wa1[j] == 0.0) sing = true;
+        }
+        qform(fjac, wa1);
+        for (int j = 0; j < N; ++j) diag[j] = fmax(diag[j], wa2[j]);
+        for (;;) {  // inner loop
+            dogleg(r, diag, qtf, delta, wa1, wa2, wa3);
+            for (int j = 0; j < N; ++j) {
+                wa1[j] = -wa1[j];
+                wa2[j] = x[j] + wa1[j];
+                wa3[j] = diag[j] * wa1[j];
+            }
+            const double pnorm = enorm(N, wa3);
+            if (iter == 1) delta = fmin(delta, pnorm);
+            sys.fcn(wa2, wa4);
+            ++res.nfev;
+            const double fnorm1 = enorm(N, wa4);
+            double actred = -1.0;
+            if (fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+            int l = 0;
+            for (int i = 0; i < N; ++i) {
+                double sum = 0.0;
+                for (int j = i; j < N; ++j) {
+                    sum += r[l] * wa1[j];
+                    ++l;
+                }
+                wa3[i] = qtf[i] + sum;
+            }
+            const double temp = enorm(N, wa3);
+            double prered = 0.0;
+            if (temp < fnorm) prered = 1.0 - (temp / fnorm) * (temp / fnorm);
+            double ratio = 0.0;
+            if (prered > 0.0) ratio = actred / prered;
+            if (ratio < p1) {
+                ncsuc = 0;
+                ++ncfail;
+                delta = p5 * delta;
+            } else {
+                ncfail = 0;
+                ++ncsuc;
+                if (ratio >= p5 || ncsuc > 1) delta = fmax(delta, pnorm / p5);
+                if (fabs(ratio - 1.0) <= p1) delta = pnorm / p5;
+            }
+            if (ratio >= p0001) {
+                for (int j = 0; j < N; ++j) {
+                    x[j] = wa2[j];
+                    wa2[j] = diag[j] * x[j];
+                    fvec[j] = wa4[j];
+                }
+                xnorm = enorm(N, wa2);
+                fnorm = fnorm1;
+                ++iter;
+            }
+            ++nslow1;
+            if (actred >= p001) nslow1 = 0;
+            if (jeval) ++nslow2;
+            if (actred >= p1) nslow2 = 0;
+            if (delta <= xtol * xnorm || fnorm == 0.0) res.info = 1;
+            if (res.info != 0) return res;
+            if (res.nfev >= maxfev) res.info = 2;
+            if (p1 * fmax(p1 * delta, pnorm) <= EPSMCH * xnorm) res.info = 3;
+            if (nslow2 == 5) res.info = 4;
+            if (nslow1 == 10) res.info = 5;
+            if (res.info != 0) return res;
+            if (ncfail == 2) break;  // recompute the Jacobian
+            for (int j = 0; j < N; ++j) {
+                double sum = 0.0;
+                for (int i = 0; i < N; ++i) sum += fjac[i + N * j] * wa4[i];
+                wa2[j] = (sum - wa3[j]) / pnorm;
+                wa1[j] = diag[j] * ((diag[j] * wa1[j]) / pnorm);
+                if (ratio >= p0001) qtf[j] = sum;
+            }
+            r1updt(r, wa1, wa2, wa3, &sing);
+            r1mpyq(N, fjac, N, wa2, wa3);
+            r1mpyq(1, qtf, 1, wa2, wa3);
+            jeval = false;
+        }
+    }
+}
+
+}  // namespace mp
+}  // namespace theta

@@ -318,6 +318,13 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
     }
     if (K > THETA_MAX_COPY) { set_error("copy number bound %d exceeds THETA_MAX_COPY=%d", K, THETA_MAX_COPY); delete pl; return THETA_ERR_UNSUPPORTED; }
     pl->K = K;
+    if (p->n == 3) {
+        if (empty) { set_error("No valid Copy Number Profiles exist for these intervals within the bounds specified"); delete pl; return THETA_ERR_EMPTY; }
+        int rc3 = theta_n3_plan_init(pl);
+        if (rc3 != THETA_OK) { theta_plan_destroy(pl); return rc3; }
+        *out = pl;
+        return THETA_OK;
+    }
     pl->KT = pick_KT(std::max(K, 1));
     const int KT = pl->KT;
     // constants
@@ -415,6 +422,7 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
 
 extern "C" void theta_plan_destroy(theta_plan* pl) {
     if (!pl) return;
+    theta_n3_plan_free(pl);
     cudaFree(pl->d_tables); cudaFree(pl->d_r); cudaFree(pl->d_rN);
     cudaFree(pl->d_PR); cudaFree(pl->d_PRN); cudaFree(pl->d_ZP);
     cudaFree(pl->d_stripe_min); cudaFree(pl->d_counters); cudaFree(pl->d_emit);

@@ -115,8 +115,13 @@ __device__ __forceinline__ void n2_groups(const Tables& T, const int (&q)[KT], d
 
 }  // namespace theta
 
+struct theta_n3_state;  // theta_n3.cu
+int theta_n3_plan_init(theta_plan* pl);
+void theta_n3_plan_free(theta_plan* pl);
+
 // Host-side plan (opaque to C callers)
 struct theta_plan {
+    theta_n3_state* n3 = nullptr;
     int device = 0;
     int n = 2, m = 0, tau = 2, K = 0, KT = 0;
     double max_normal = 1.0;

@@ -1,0 +1,183 @@
+"""n = 3 host side: do_optimization* for two tumour populations (python/RunTHetA.py:124-220 with
+Enumerator._generate_next_C_3 and Optimizer._solve_n3plus), on the GPU through the C ABI.
+
+The search runs as for n=2: items (DFS sub-trees in enumeration order) are sharded contiguously
+over the ranks of a torch.distributed group, pass 1 reduces per item, one all-reduce(min) gives the
+global minimum, pass 2 emits the records the reference's fold can keep, the fold is replayed.
+"""
+import sys
+
+import numpy as np
+
+from . import _lib
+from .search import (INF, _dist_state, _reverse_sort_list, _reverse_sort_rows, exchange_minima, fold_replay,
+                     gather_records, is_close)
+
+_NO_PROFILES = ("Error: No valid Copy Number Profiles exist for these intervals within the bounds specified. "
+                "Exiting...")
+
+
+def shard_items(weights, rank, world):
+    """Contiguous item ranges of (about) equal estimated work."""
+    n = len(weights)
+    if world == 1:
+        return 0, n
+    cum = np.concatenate([[0.0], np.cumsum(weights)])
+    total = cum[-1]
+    lo = int(np.searchsorted(cum, total * rank / world, side="left"))
+    hi = int(np.searchsorted(cum, total * (rank + 1) / world, side="left")) if rank + 1 < world else n
+    return min(lo, n), min(max(hi, lo), n)
+
+
+def gather_paths(paths, dist, world):
+    if dist is None:
+        return paths
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    m = paths.shape[1]
+    n = torch.tensor([paths.shape[0]], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    ns = [int(x.item()) for x in ns]
+    cap = max(max(ns), 1)
+    buf = np.zeros((cap, m), dtype=np.uint8)
+    buf[:paths.shape[0]] = paths
+    t = torch.from_numpy(buf).to(dev)
+    outs = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    return np.concatenate([o.cpu().numpy()[:k] for o, k in zip(outs, ns)])
+
+
+class SearchResultN3(object):
+    pass
+
+
+def search_n3(plan, leaf_cap=256, stream=None):
+    """Sharded two-pass n=3 search.  Returns a SearchResultN3 with `best` = list of
+    (path or None for the bogus first matrix, mu[3], nll, status) in fold order."""
+    rank, world, dist = _dist_state()
+    n_items = plan.prepare(leaf_cap)
+    w = plan.item_weights()
+    b, e = shard_items(w, rank, world)
+    local_min = plan.pass1_n3(b, e, stream)
+    st = plan.stats()
+    null_nll = plan.null_nll()
+    g, prior = exchange_minima(local_min, dist, rank, world)
+    recs, paths = plan.pass2_n3(g, prior, stream)
+    st.update({k: v for k, v in plan.stats().items() if k in ("n_rescanned", "ms_pass2")})
+    allrecs = gather_records(recs, dist, world)
+    allpaths = gather_paths(paths, dist, world)
+    n_solved, n_cand = st["n_solved"], st["n_candidates"]
+    if dist is not None:
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor([n_solved, n_cand], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        n_solved, n_cand = int(t[0].item()), int(t[1].item())
+    # the stream the reference folds: the all-[tau,0,0] matrix first (RunTHetA.py:148,188 -- Q2), whose
+    # NLL is the all-normal likelihood, then the candidates in enumeration order
+    keys = np.concatenate([[0], allrecs["rank"].astype(np.uint64) + np.uint64(1)]).astype(np.uint64)
+    nlls = np.concatenate([[null_nll], allrecs["nll"]])
+    idx = fold_replay(keys, nlls, dup_first=False)
+    res = SearchResultN3()
+    res.best = []
+    for i in idx:
+        if i == 0:
+            res.best.append((None, (float("nan"),) * 3, null_nll, _lib.ST_DEGENERATE))
+        else:
+            r = allrecs[i - 1]
+            res.best.append((allpaths[i - 1].copy(), tuple(float(x) for x in r["mu"]), float(r["nll"]), int(r["status"])))
+    res.records, res.paths = allrecs, allpaths
+    res.count = n_cand + 1
+    res.n_solved = n_solved + 1
+    res.min_nll = min(g, null_nll)
+    res.stats = st
+    res.n_items = n_items
+    return res
+
+
+def _matrix(path, rows, tau, m):
+    C = np.zeros((m, 3))
+    C[:, 0] = tau
+    if path is not None:
+        for i, g in enumerate(path):
+            C[i, 1], C[i, 2] = rows[int(g)]
+    return C
+
+
+def do_optimization_n3(m, k, tau, lower_bounds, upper_bounds, r, rN, sorted_index, get_values=False, prefix=None):
+    """The n=3 branch of do_optimization_single (python/RunTHetA.py:173-220)."""
+    try:
+        plan = _lib.Plan(3, r, rN, lower_bounds, upper_bounds, tau=tau)
+    except _lib.EmptySpaceError:
+        print(_NO_PROFILES)
+        sys.exit(1)
+    try:
+        lo, up = plan.bounds()
+        for i in range(len(lower_bounds)):  # Q16
+            lower_bounds[i] = int(lo[i])
+            upper_bounds[i] = int(up[i])
+        rows = plan.rows()
+        res = search_n3(plan)
+        best = []
+        real = [b for b in res.best if b[0] is not None]
+        vals = None
+        if real:
+            _, _, _, _, vals = plan.solve_rows(np.stack([b[0] for b in real]), want_vals=True)
+        j = 0
+        A = float(sum(int(v) for v in rN))
+        for path, mu, nll, st in res.best:
+            C = _matrix(path, rows, tau, m)
+            if path is None:
+                v = [np.float64(int(x) / A) for x in rN]  # all-normal model: p_i = rN_i / sum rN
+            else:
+                v = [np.float64(x) for x in vals[j]]
+                j += 1
+            best.append((_reverse_sort_rows(C, sorted_index), np.array(mu, dtype=np.float64), np.float64(nll),
+                         _reverse_sort_list(v, sorted_index)))
+        if get_values:
+            dump_values_n3(plan, rows, (prefix or "theta") + ".likelihoods")
+        return best
+    finally:
+        plan.close()
+
+
+def dump_values_n3(plan, rows, path):
+    """--GET_VALUES for n=3 (RunTHetA.py:210-215 writes column 1 of C, mu[0], likelihood)."""
+    paths = plan.enumerate_n3()
+    mu, _, nll, st, _ = plan.solve_rows(paths)
+    with open(path, "w") as f:
+        for i in range(len(paths)):
+            if st[i] >= _lib.ST_NONE_SIGN:
+                continue
+            f.write("".join(str(rows[int(g)][0]) for g in paths[i]) + "\t" + str(np.float64(mu[i, 0])) + "\t" +
+                    str(np.float64(nll[i])) + "\n")
+
+
+def enumerator_next_n3(enum):
+    """Enumerator.generate_next_C for n=3 (python/Enumerator.py:74-87,172-223)."""
+    if getattr(enum, "_paths3", None) is None:
+        enum._plan.prepare(1 << 12)
+        enum._paths3 = enum._plan.enumerate_n3()
+        enum._rows3 = enum._plan.rows()
+        enum._next = 0
+    if enum._next >= len(enum._paths3):
+        return False
+    C = _matrix(enum._paths3[enum._next], enum._rows3, enum.tau, enum.m)
+    enum._next += 1
+    return C
+
+
+def optimizer_solve_n3(opt, C):
+    """Optimizer._solve_n3plus (python/Optimizer.py:128-165) for one explicit matrix."""
+    if opt._plan is None:
+        opt._plan = _lib.Plan(3, opt.r, opt.rN, [0] * opt.m, [7] * opt.m, tau=opt.tau)
+        opt._rowidx = {rc: i for i, rc in enumerate(opt._plan.rows())}
+    try:
+        path = np.array([[opt._rowidx[(int(a), int(b))] for a, b in C[:, 1:]]], dtype=np.uint8)
+    except KeyError:
+        raise ValueError("row outside the admissible set (Enumerator._is_valid_row)")
+    mu, _, nll, st, vals = opt._plan.solve_rows(path, want_vals=True)
+    if st[0] >= _lib.ST_NONE_SIGN:
+        return None
+    return (np.array(mu[0]), np.float64(nll[0]), [np.float64(v) for v in vals[0]])
