@@ -157,6 +157,8 @@ int theta_n3_rows(const theta_plan* plan, int32_t* a, int32_t* b, int32_t* n_row
  * candidates (count DP of TimeEstimate.count_number_matrices_3, TimeEstimate.py:113-142, per sub-tree). */
 int theta_n3_prepare(theta_plan* plan, int64_t leaf_cap, int64_t max_items, uint64_t* n_items);
 int theta_n3_item_weights(const theta_plan* plan, double* weights /* [n_items] estimated leaves */);
+/* 1 if theta_n3_prepare stopped at max_items: the items then cover only a lexicographic prefix of the space. */
+int theta_n3_truncated(const theta_plan* plan, int32_t* truncated);
 /* Pass 1 / pass 2 over items [item_begin, item_end): same contract as the n=2 passes; a record's
  * `rank` is (item << 32) | sequence number inside the item, `flags` indexes paths_host. */
 int theta_search_n3_pass1(theta_plan* plan, uint64_t item_begin, uint64_t item_end, double* local_min, void* stream);

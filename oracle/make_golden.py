@@ -213,6 +213,38 @@ def gen_n3_small(R):
     subprocess.check_call(["gzip", "-9", "-f", os.path.join(GOLD, "n3_small_full.json")])
 
 
+def gen_synth_n3(R):
+    """Configs #4 / #5: the live Optimizer.solve on the first candidates in enumeration order and on
+    candidates further into the space (every 997th of the first 60 000 for #4)."""
+    import itertools
+    out = {}
+    for name, m, k, F, tb, n_first, stride, n_far in (("cfg4_m150_k5", 150, 5, 12, False, 120, 997, 60),
+                                                       ("cfg5_m500_k7", 500, 7, 12, True, 30, 0, 0)):
+        P = O.synthetic_problem_n3(m, k, 1, F, tb)
+        rows, _ = O.n3_graph(max(P["upper"]), 2)
+        opt = R.Optimizer.Optimizer(P["r"], P["rN"], m, 3, 2, upper_bound=1.0)
+        recs = []
+        gen = O.enumerate_n3(P["lower"], P["upper"])
+        want = set(range(n_first)) | set(range(n_first, n_first + stride * n_far, stride) if stride else [])
+        last = max(want)
+        for idx_, path in enumerate(gen):
+            if idx_ > last:
+                break
+            if idx_ not in want:
+                continue
+            C = O.rows_to_matrix(path, rows)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                s_ = opt.solve(C)
+            recs.append(dict(index=idx_, path=[int(v) for v in path],
+                             mu=None if s_ is None else [float(v) for v in s_[0]],
+                             nll=None if s_ is None else float(s_[1])))
+        out[name] = dict(m=m, k=k, F=F, tau_bounds=tb, seed=1, r=P["r"], rN=P["rN"], lower=P["lower"], upper=P["upper"],
+                         sorted_index=P["sorted_index"], rows=[list(x) for x in rows], records=recs)
+        print(name, len(recs), "none", sum(1 for q in recs if q["nll"] is None))
+    _dump("synth_n3_candidates.json", out)
+
+
 def gen_edge(R):
     """Edge-case KATs from the live Optimizer.solve."""
     m = 7
@@ -245,7 +277,7 @@ def gen_edge(R):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="kat,edge,n2_small,synth_n2,n3_small,config1")
+    ap.add_argument("--only", default="kat,edge,n2_small,synth_n2,n3_small,synth_n3,config1")
     a = ap.parse_args()
     warnings.simplefilter("ignore")
     R = refshim.modules()
@@ -261,6 +293,8 @@ def main():
         gen_synth_n2(R)
     if "n3_small" in todo:
         gen_n3_small(R)
+    if "synth_n3" in todo:
+        gen_synth_n3(R)
     if "config1" in todo:
         gen_config1(R)
 

@@ -1,0 +1,22 @@
+"""GPU, >= 2 devices: the NCCL-sharded search equals the single-GPU search (tools/dist_check.py under torchrun)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_gpu_search_equals_single_gpu():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 2 if n < 4 else 4
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "tools", "dist_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "DIST_CHECK OK %d" % world in out.stdout

@@ -126,3 +126,36 @@ def test_optimizer_and_enumerator_mirrors(lib, golden):
                 assert len(out[2]) == g2["m"] and abs(sum(out[2]) - 1) < 1e-12
         n += 1
     assert n == len(g2["stream"])
+
+
+def test_synthetic_configs_4_and_5(lib, golden):
+    """BASELINE configs #4 (m=150, k=5) and #5 (m=500, k=7, TAU-style bounds): sampled candidates of the live
+    reference vs solve_rows, and the enumeration prefix vs the on-chip DFS."""
+    data = golden("synth_n3_candidates.json")
+    for name, case in data.items():
+        plan = lib.Plan(3, case["r"], case["rN"], case["lower"], case["upper"])
+        assert plan.rows() == [tuple(x) for x in case["rows"]]
+        recs = case["records"]
+        paths = np.array([q["path"] for q in recs], dtype=np.uint8)
+        mu, mh, nll, st, _ = plan.solve_rows(paths)
+        rows = plan.rows()
+        n_reg = 0
+        for i, q in enumerate(recs):
+            if collinear("".join("%d%d" % rows[g] for g in q["path"])):
+                continue  # rank-deficient: mu split not identifiable
+            n_reg += 1
+            if q["nll"] is None:
+                assert st[i] >= 8
+                continue
+            assert st[i] < 8, (name, i, st[i])
+            assert abs(nll[i] - q["nll"]) <= 1e-10 * abs(q["nll"]), (name, i, nll[i], q["nll"])
+            assert max(abs(mu[i][j] - q["mu"][j]) for j in range(3)) <= 1e-9, (name, i, mu[i], q["mu"])
+        assert n_reg >= 20, (name, n_reg)
+        # enumeration: the first candidates of the first items are the reference's first candidates
+        plan.prepare(64, max_items=2000)
+        assert plan.truncated  # both spaces are far larger than 2000 x 64 candidates: a lexicographic prefix
+        first = plan.enumerate_n3(0, 8)
+        n_chk = min(len(first), sum(1 for q in recs if q["index"] < len(first)))
+        for q in recs[:n_chk]:
+            assert list(first[q["index"]]) == q["path"], (name, q["index"])
+        plan.close()

@@ -111,3 +111,33 @@ def test_fold_quirks():
     assert O.fold([("a", 10.0), ("b", 9.0), ("c", 9.0005), ("d", 8.9)]) == ["d"]
     assert O.fold([("a", 10.0), ("n", float("nan")), ("b", 10.0009)]) == ["a", "n", "b"]
     assert O.is_close(float("nan"), 1.0) and O.in_range([float("nan")])
+
+
+def test_n3_small_space_bit_exact(golden):
+    """n=3: enumeration order and a sample of candidates (incl. BFGS-fallback outcomes) bit for bit."""
+    case = golden("n3_small_full.json.gz")[0]
+    rows, _ = O.n3_graph(3, 2)
+    assert [list(x) for x in rows] == case["rows"]
+    paths = list(O.enumerate_n3(case["lower"], case["upper"]))
+    keys = ["".join("%d%d" % rows[g] for g in p) for p in paths]
+    assert keys == [s[0] for s in case["stream"][1:]]
+    for p, s in list(zip(paths, case["stream"][1:]))[::41]:
+        got = O.solve_n3(O.rows_to_matrix(p, rows), case["r"], case["rN"])
+        if s[2] is None:
+            assert got is None
+        else:
+            assert [float(v) for v in got[0]] == s[1] and float(got[1]) == s[2]
+
+
+def test_n3_synthetic_configs(golden):
+    data = golden("synth_n3_candidates.json")
+    for name, case in data.items():
+        P = O.synthetic_problem_n3(case["m"], case["k"], case["seed"], case["F"], case["tau_bounds"])
+        assert P["r"] == case["r"] and P["lower"] == case["lower"] and P["upper"] == case["upper"]
+        rows = [tuple(x) for x in case["rows"]]
+        gen = O.enumerate_n3(case["lower"], case["upper"])
+        for i, path in zip(range(3), gen):
+            assert path == case["records"][i]["path"]
+        q = case["records"][1]
+        got = O.solve_n3(O.rows_to_matrix(q["path"], rows), case["r"], case["rN"])
+        assert [float(v) for v in got[0]] == q["mu"] and float(got[1]) == q["nll"]

@@ -67,6 +67,7 @@ SYMBOLS = {
     "theta_n3_rows": (C.c_int, [_VP, _VP, _VP, C.POINTER(C.c_int32)]),
     "theta_n3_prepare": (C.c_int, [_VP, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
     "theta_n3_item_weights": (C.c_int, [_VP, _VP]),
+    "theta_n3_truncated": (C.c_int, [_VP, C.POINTER(C.c_int32)]),
     "theta_search_n3_pass1": (C.c_int, [_VP, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), _VP]),
     "theta_search_n3_pass2": (C.c_int, [_VP, C.c_double, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP, _VP]),
     "theta_enumerate_n3": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
@@ -194,6 +195,9 @@ class Plan(object):
         n = C.c_uint64()
         check(load().theta_n3_prepare(self._h, int(leaf_cap), int(max_items), C.byref(n)))
         self.n_items = int(n.value)
+        t = C.c_int32()
+        check(load().theta_n3_truncated(self._h, C.byref(t)))
+        self.truncated = bool(t.value)
         return self.n_items
 
     def item_weights(self):

@@ -17,12 +17,15 @@ static constexpr int kBlock = 128;
 static constexpr int kCounters = 8;
 
 struct SearchParams {
+    const double2* logtab;
     const unsigned char* tables;
     TableLayout layout;
     N2Const kc;
     uint64_t begin, end;
-    int L;
-    uint32_t n_items;  // stripes (pass 1) or listed stripes (pass 2)
+    int L;               // ranks per lane in one stripe (a stripe = 32 * L consecutive ranks, one warp)
+    int Lrun;            // ranks per lane in one work unit (pass 1: L; pass 2: a few, for latency)
+    int units_per_item;  // ceil(L / Lrun)
+    uint32_t n_items;    // stripes (pass 1) or listed stripes (pass 2)
     double* stripe_min;
     unsigned long long* counters;
     const uint32_t* stripe_list;
@@ -30,7 +33,6 @@ struct SearchParams {
     double near_thr;
     theta_cand* emit;
     unsigned long long emit_cap;
-    int emit_all_nan;
 };
 
 __device__ __forceinline__ double warp_min(double v) {
@@ -51,32 +53,39 @@ __device__ __forceinline__ void stage_tables(unsigned char* smem, const unsigned
     __syncthreads();
 }
 
-// One CTA takes stripes from a ticket counter.  A stripe is blockDim.x * L consecutive ranks;
-// each thread unranks the first column of its run once and then walks L columns with the
-// odometer, warm-starting the root-finder from the previous column's root.
+// Persistent warps take work units from a ticket counter (no block-level synchronisation after the
+// tables are staged).  A stripe is 32 * L consecutive ranks; each lane unranks the first column of
+// its run once and then walks it with the odometer, warm-starting the root-finder from the roots of
+// the previous two columns.  Pass 1 (EMIT=false) writes one minimum per stripe; pass 2 (EMIT=true)
+// re-walks listed stripes in short runs and emits candidate records.
 template <int KT, bool EMIT>
 __global__ void __launch_bounds__(kBlock, 6) n2_search_kernel(const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double s_red[kBlock / 32];
-    __shared__ uint32_t s_ticket;
+    __shared__ double2 s_logtab[THETA_LOGTAB_SIZE];
+    for (int i = threadIdx.x; i < THETA_LOGTAB_SIZE; i += blockDim.x) s_logtab[i] = p.logtab[i];
     stage_tables(smem, p.tables, p.layout.bytes);
     Tables T;
     T.bind(smem, p.layout);
     const N2Const kc = p.kc;
+    const int lane = threadIdx.x & 31;
     unsigned long long solved = 0, iters = 0, nan_nll = 0;
+    const unsigned long long n_units = (unsigned long long)p.n_items * p.units_per_item;
 
     for (;;) {
-        if (threadIdx.x == 0) s_ticket = (uint32_t)atomicAdd(&p.counters[0], 1ULL);
-        __syncthreads();
-        const uint32_t ticket = s_ticket;
-        __syncthreads();
-        if (ticket >= p.n_items) break;
-        const uint32_t stripe = EMIT ? p.stripe_list[ticket] : ticket;
-        const double prior = EMIT ? p.stripe_prior[ticket] : 0.0;
-        const uint64_t r0 = p.begin + ((uint64_t)stripe * blockDim.x + threadIdx.x) * (uint64_t)p.L;
+        unsigned long long unit = 0;
+        if (lane == 0) unit = atomicAdd(&p.counters[0], 1ULL);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const uint32_t item = (uint32_t)(unit / p.units_per_item);
+        const uint32_t sub = (uint32_t)(unit % p.units_per_item);
+        const uint32_t stripe = EMIT ? p.stripe_list[item] : item;
+        const double prior = EMIT ? p.stripe_prior[item] : 0.0;
+        const uint64_t s_begin = p.begin + (uint64_t)stripe * 32u * (uint64_t)p.L;
+        const uint64_t s_end = min(p.end, (uint64_t)(s_begin + (uint64_t)32 * (uint64_t)p.L));
+        const uint64_t r0 = s_begin + ((uint64_t)sub * 32u + lane) * (uint64_t)p.Lrun;
         double tmin = INFINITY;
-        if (r0 < p.end) {
-            const int cnt = (int)min((uint64_t)p.L, p.end - r0);
+        if (r0 < s_end) {
+            const int cnt = (int)min((uint64_t)p.Lrun, s_end - r0);
             int q[KT];
             n2_unrank<KT>(T, r0, q);
             double xprev = -1.0, xprev2 = -1.0;  // roots of the previous two columns (warm start)
@@ -92,7 +101,7 @@ __global__ void __launch_bounds__(kBlock, 6) n2_search_kernel(const SearchParams
                     const double xe = 2.0 * xprev - xprev2;
                     if (xe > 0.0 && xe < 1.0) x0 = xe;
                 }
-                n2_solve<KT + 1>(R, S1, z, kc, x0, o);
+                n2_solve<KT + 1>(R, S1, z, kc, x0, o, s_logtab);
                 if (o.status < THETA_ST_NONE_SIGN) {
                     ++solved;
                     iters += o.iters;
@@ -127,21 +136,14 @@ __global__ void __launch_bounds__(kBlock, 6) n2_search_kernel(const SearchParams
         }
         if (!EMIT) {
             const double w = warp_min(tmin);
-            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = w;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double b = s_red[0];
-#pragma unroll
-                for (int i = 1; i < kBlock / 32; ++i) b = fmin(b, s_red[i]);
-                p.stripe_min[stripe] = b;
-            }
+            if (lane == 0) p.stripe_min[stripe] = w;
         }
     }
     if (!EMIT) {
         solved = warp_sum(solved);
         iters = warp_sum(iters);
         nan_nll = warp_sum(nan_nll);
-        if ((threadIdx.x & 31) == 0) {
+        if (lane == 0) {
             if (solved) atomicAdd(&p.counters[1], solved);
             if (iters) atomicAdd(&p.counters[2], iters);
             if (nan_nll) atomicAdd(&p.counters[4], nan_nll);
@@ -277,7 +279,8 @@ static int launch_search(const theta_plan* plan, const SearchParams& sp, cudaStr
     int bps = 1;
     int rc = config_kernel(n2_search_kernel<KT, EMIT>, plan->layout.bytes, &bps);
     if (rc) return rc;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(sp.n_items, (uint64_t)sm_count(plan->device) * bps);
+    const uint64_t units = (uint64_t)sp.n_items * sp.units_per_item;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((units + kBlock / 32 - 1) / (kBlock / 32), (uint64_t)sm_count(plan->device) * bps);
     if (grid == 0) return THETA_OK;
     n2_search_kernel<KT, EMIT><<<grid, kBlock, plan->layout.bytes, st>>>(sp);
     THETA_CUDA(cudaGetLastError());
@@ -393,6 +396,16 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_r, rd.data(), sizeof(double) * m, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_rN, rnd.data(), sizeof(double) * m, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_counters, sizeof(unsigned long long) * kCounters);
+    {   // fast_log table: r_i = 1/(1 + (i+0.5)/256) rounded to fp64 and -ln(r_i) of that very number
+        std::vector<double2> lt(THETA_LOGTAB_SIZE);
+        for (int i = 0; i < THETA_LOGTAB_SIZE; ++i) {
+            const double rinv = (double)(1.0L / (1.0L + ((long double)i + 0.5L) / 256.0L));
+            lt[i].x = rinv;
+            lt[i].y = (double)(-logl((long double)rinv));
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&pl->d_logtab, sizeof(double2) * THETA_LOGTAB_SIZE);
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_logtab, lt.data(), sizeof(double2) * THETA_LOGTAB_SIZE, cudaMemcpyHostToDevice);
+    }
     {   // prefix tables for the tile kernels (theta_tiles.cu)
         const int64_t pitch = theta_tile_pitch(m);
         pl->tile_pitch = pitch;
@@ -426,6 +439,7 @@ extern "C" void theta_plan_destroy(theta_plan* pl) {
     cudaFree(pl->d_tables); cudaFree(pl->d_r); cudaFree(pl->d_rN);
     cudaFree(pl->d_PR); cudaFree(pl->d_PRN); cudaFree(pl->d_ZP);
     cudaFree(pl->d_stripe_min); cudaFree(pl->d_counters); cudaFree(pl->d_emit);
+    cudaFree(pl->d_list); cudaFree(pl->d_prior); cudaFree(pl->d_logtab);
     delete pl;
 }
 
@@ -498,13 +512,13 @@ extern "C" int theta_search_n2_pass1(theta_plan* pl, uint64_t rank_begin, uint64
     pl->stats.min_nll = INFINITY;
     *local_min = INFINITY;
     if (N == 0) { pl->p1_stripes = 0; pl->h_stripe_min.clear(); return THETA_OK; }
-    // run length per thread: enough stripes to balance 148 SMs, few enough to keep the stripe table small
-    const uint64_t target_stripes = (uint64_t)sm_count(pl->device) * 24;
-    uint64_t L = N / (target_stripes * kBlock);
+    // run length per lane: enough stripes (one warp each) to balance the SMs, few enough to keep the stripe table small
+    const uint64_t target_stripes = (uint64_t)sm_count(pl->device) * 24 * (kBlock / 32);
+    uint64_t L = N / (target_stripes * 32);
     L = std::max<uint64_t>(8, std::min<uint64_t>(L, 256));
-    while ((N + L * kBlock - 1) / (L * kBlock) > (1ull << 22)) L *= 2;
+    while ((N + L * 32 - 1) / (L * 32) > (1ull << 22)) L *= 2;
     pl->p1_L = (int)L; pl->p1_block = kBlock;
-    const uint64_t stripes = (N + L * kBlock - 1) / (L * kBlock);
+    const uint64_t stripes = (N + L * 32 - 1) / (L * 32);
     pl->p1_stripes = stripes;
     if (stripes > pl->stripe_cap) {
         cudaFree(pl->d_stripe_min); pl->d_stripe_min = nullptr; pl->stripe_cap = 0;
@@ -513,8 +527,9 @@ extern "C" int theta_search_n2_pass1(theta_plan* pl, uint64_t rank_begin, uint64
     }
     THETA_CUDA(cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kCounters, st));
     SearchParams sp{};
-    sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc;
-    sp.begin = rank_begin; sp.end = rank_end; sp.L = (int)L; sp.n_items = (uint32_t)stripes;
+    sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
+    sp.begin = rank_begin; sp.end = rank_end; sp.L = (int)L; sp.Lrun = (int)L; sp.units_per_item = 1;
+    sp.n_items = (uint32_t)stripes;
     sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters;
     cudaEvent_t e0, e1;
     THETA_CUDA(cudaEventCreate(&e0)); THETA_CUDA(cudaEventCreate(&e1));
@@ -566,10 +581,15 @@ extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double p
     }
     pl->stats.n_rescanned = list.size();
     if (list.empty()) return THETA_OK;
-    uint32_t* d_list = nullptr;
-    double* d_prior = nullptr;
-    THETA_CUDA(cudaMalloc(&d_list, sizeof(uint32_t) * list.size()));
-    THETA_CUDA(cudaMalloc(&d_prior, sizeof(double) * list.size()));
+    if (list.size() > pl->list_cap) {
+        cudaFree(pl->d_list); cudaFree(pl->d_prior); pl->d_list = nullptr; pl->d_prior = nullptr; pl->list_cap = 0;
+        const size_t want_l = std::max<size_t>(1024, list.size() * 2);
+        THETA_CUDA(cudaMalloc(&pl->d_list, sizeof(uint32_t) * want_l));
+        THETA_CUDA(cudaMalloc(&pl->d_prior, sizeof(double) * want_l));
+        pl->list_cap = want_l;
+    }
+    uint32_t* d_list = pl->d_list;
+    double* d_prior = pl->d_prior;
     THETA_CUDA(cudaMemcpyAsync(d_list, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice, st));
     THETA_CUDA(cudaMemcpyAsync(d_prior, prior.data(), sizeof(double) * list.size(), cudaMemcpyHostToDevice, st));
     size_t want = std::max<size_t>(1 << 16, pl->emit_cap);
@@ -586,8 +606,9 @@ extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double p
         }
         cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kCounters, st);
         SearchParams sp{};
-        sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc;
+        sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
         sp.begin = pl->p1_begin; sp.end = pl->p1_end; sp.L = pl->p1_L; sp.n_items = (uint32_t)list.size();
+        sp.Lrun = std::min(pl->p1_L, 4); sp.units_per_item = (pl->p1_L + sp.Lrun - 1) / sp.Lrun;
         sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters;
         sp.stripe_list = d_list; sp.stripe_prior = d_prior; sp.near_thr = near_thr;
         sp.emit = pl->d_emit; sp.emit_cap = pl->emit_cap;
@@ -616,9 +637,20 @@ extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double p
         break;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_list); cudaFree(d_prior);
     if (rc) return rc;
     std::sort(host.begin(), host.end(), [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; });
+    {   // keep exactly: strict prefix minima of the whole stream (w.r.t. everything before this shard),
+        // the near-minimum set, and NaN values -- the per-lane filter on the device emits a superset
+        size_t w = 0;
+        double run = prior_min;
+        for (size_t i = 0; i < host.size(); ++i) {
+            const double v = host[i].nll;
+            const bool keep = (v != v) || v < run || v <= near_thr;
+            if (v < run) run = v;
+            if (keep) host[w++] = host[i];
+        }
+        host.resize(w);
+    }
     *n_out = host.size();
     if (host.size() > cap) {
         set_error("pass2 produced %zu records but the caller's buffer holds %llu", host.size(), (unsigned long long)cap);

@@ -148,5 +148,9 @@ struct theta_plan {
     unsigned long long* d_counters = nullptr;  // [0] stripe ticket, [1] solved, [2] newton iters, [3] emitted, [4] nan-nll
     theta_cand* d_emit = nullptr;
     size_t emit_cap = 0;
+    double2* d_logtab = nullptr;  // fast_log table (theta_core.cuh)
+    uint32_t* d_list = nullptr;   // pass-2 stripe list / per-stripe prior minima
+    double* d_prior = nullptr;
+    size_t list_cap = 0;
     theta_search_stats stats{};
 };

@@ -40,6 +40,7 @@ struct theta_n3_state {
     std::vector<double> h_item_min;
     uint64_t p1_begin = 0, p1_end = 0;
     unsigned long long nan_nll = 0;
+    bool truncated = false;
 };
 
 namespace theta {
@@ -485,13 +486,11 @@ extern "C" int theta_n3_prepare(theta_plan* pl, int64_t leaf_cap, int64_t max_it
     Expander ex{pl, s};
     ex.max_items = (size_t)max_items;
     ex.cap = (double)leaf_cap;
-    for (int attempt = 0; attempt < 24; ++attempt) {
-        ex.overflow = false;
-        ex.run();
-        if (!ex.overflow) break;
-        ex.cap *= 4.0;  // too many items: coarser sub-trees
-    }
-    if (ex.overflow) { set_error("n=3 item list does not fit %lld items", (long long)max_items); return THETA_ERR_OVERFLOW; }
+    // If the space is too large for max_items sub-trees of leaf_cap candidates, the list is cut after
+    // max_items items: the search then covers a lexicographic prefix of the space (a rank budget).
+    ex.overflow = false;
+    ex.run();
+    s->truncated = ex.overflow;
     const size_t ni = s->off.size() - 1;
     cudaFree(s->d_prefix); cudaFree(s->d_off); cudaFree(s->d_item_min);
     s->d_prefix = nullptr; s->d_off = nullptr; s->d_item_min = nullptr;
@@ -503,6 +502,13 @@ extern "C" int theta_n3_prepare(theta_plan* pl, int64_t leaf_cap, int64_t max_it
         THETA_CUDA(cudaMemcpy(s->d_off, s->off.data(), sizeof(uint32_t) * (ni + 1), cudaMemcpyHostToDevice));
     }
     if (n_items) *n_items = ni;
+    return THETA_OK;
+}
+
+extern "C" int theta_n3_truncated(const theta_plan* pl, int32_t* truncated) {
+    int rc = check_n3(pl);
+    if (rc) return rc;
+    if (truncated) *truncated = pl->n3->truncated ? 1 : 0;
     return THETA_OK;
 }
 

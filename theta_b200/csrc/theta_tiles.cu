@@ -30,7 +30,7 @@
 namespace theta {
 
 static constexpr int kRows = 128;   // rows per tile == threads per CTA
-static constexpr int kStages = 2;
+static constexpr int kStages = 1;   // one tile in flight per CTA; 8 CTAs per SM overlap copy and compute
 static constexpr int kMaxRuns = 16;  // run list per row kept in shared memory; longer rows take the direct path
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -62,6 +62,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 struct TileParams {
+    const double2* logtab;
     const int8_t* cols;
     int64_t pitch;
     int64_t count;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
                         const double pr_e = S.PR[e], prn_e = S.PRN[e];
                         const double wgt = pr_e - pr_s;
                         s1 = fma(v, prn_e - prn_s, s1);
-                        if (wgt != 0.0) acc = fma(wgt, log(fma(v, mu1, tm)), acc);
+                        if (wgt != 0.0) acc = fma(wgt, fast_log(fma(v, mu1, tm), p.logtab), acc);
                         pr_s = pr_e;
                         prn_s = prn_e;
                     }
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
                     });
                 }
                 const double gbar = (mu * kc.S0 + mu1 * s1) / kc.A;
-                double nll = kc.K0 - (acc - kc.Rtot * log(gbar));
+                double nll = kc.K0 - (acc - kc.Rtot * fast_log(gbar, p.logtab));
                 if (kc.any_zero_rN) nll = INFINITY;
                 p.nll_out[row] = nll;
             } else {
@@ -353,7 +354,7 @@ extern "C" int theta_nll_tiles_n2_dev(theta_plan* pl, const int8_t* cols_dev, in
     cudaStream_t st = (cudaStream_t)stream;
     TileParams tp{};
     tp.cols = cols_dev; tp.pitch = pitch; tp.count = count; tp.PR = pl->d_PR; tp.PRN = pl->d_PRN; tp.ZP = pl->d_ZP;
-    tp.kc = pl->kc; tp.mu_in = mu_dev; tp.nll_out = nll_dev;
+    tp.kc = pl->kc; tp.mu_in = mu_dev; tp.nll_out = nll_dev; tp.logtab = pl->d_logtab;
     return launch_tiles<false, 1>(pl, tp, st);  // asynchronous on `stream`
 }
 
@@ -367,7 +368,7 @@ extern "C" int theta_solve_tiles_n2_dev(theta_plan* pl, const int8_t* cols_dev, 
     {
         TileParams tp{};
         tp.cols = cols_dev; tp.pitch = pitch; tp.count = count; tp.PR = pl->d_PR; tp.PRN = pl->d_PRN; tp.ZP = pl->d_ZP;
-        tp.kc = pl->kc; tp.mu_out = mu_dev; tp.nll_out = nll_dev; tp.status_out = status_dev;
+        tp.kc = pl->kc; tp.mu_out = mu_dev; tp.nll_out = nll_dev; tp.status_out = status_dev; tp.logtab = pl->d_logtab;
         switch (pl->KT) {
 #define THETA_TS(KTV) case KTV: rc = launch_tiles<true, KTV>(pl, tp, st); break;
             THETA_TS(2) THETA_TS(3) THETA_TS(4) THETA_TS(5) THETA_TS(6) THETA_TS(7) THETA_TS(8) THETA_TS(10) THETA_TS(12) THETA_TS(15)

@@ -59,44 +59,78 @@ def shard_range(total, rank, world):
     return (total * rank) // world, (total * (rank + 1)) // world
 
 
+def _dev(dist):
+    import torch
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
 def exchange_minima(local_min, dist, rank, world):
-    """One all-reduce(min) for the global best NLL + an all-gather of the shard minima.
+    """One all-reduce(min) for the global best NLL + an all-gather of the shard minima, one host sync.
 
     Returns (global_min, prior_min) with prior_min = min over shards before `rank`.
     """
     if dist is None:
         return local_min, INF
     import torch
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    t = torch.tensor([local_min], dtype=torch.float64, device=dev)
+    t = torch.tensor([local_min], dtype=torch.float64, device=_dev(dist))
     g = t.clone()
-    dist.all_reduce(g, op=dist.ReduceOp.MIN)
-    allm = [torch.zeros_like(t) for _ in range(world)]
-    dist.all_gather(allm, t)
-    mins = [float(x.item()) for x in allm]
+    h1 = dist.all_reduce(g, op=dist.ReduceOp.MIN, async_op=True)
+    allm = torch.empty(world, dtype=torch.float64, device=t.device)
+    h2 = dist.all_gather_into_tensor(allm, t, async_op=True)
+    h1.wait()
+    h2.wait()
+    both = torch.cat([g, allm]).cpu().tolist()
+    mins = both[1:]
     prior = min(mins[:rank]) if rank > 0 else INF
-    return float(g.item()), prior
+    return both[0], prior
 
 
-def gather_records(recs, dist, world):
-    """All shards' pass-2 records, concatenated in rank order (they are already sorted per shard)."""
+_GATHER_CAP = 256  # records per shard carried by the fixed-size exchange
+
+
+def gather_records(recs, dist, world, extra=None):
+    """All shards' pass-2 records, concatenated in rank order (they are already sorted per shard).
+
+    One fixed-size all-gather carries up to _GATHER_CAP records per shard plus the shard's record count
+    (and `extra`, a small int64 payload such as the solved-candidate count); only when a shard has more
+    records is a second, variable-size exchange needed.  Returns records, or (records, extras) if extra is given.
+    """
     if dist is None:
-        return recs
+        return recs if extra is None else (recs, [list(extra)])
     import torch
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    n = torch.tensor([len(recs)], dtype=torch.int64, device=dev)
-    ns = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(ns, n)
-    ns = [int(x.item()) for x in ns]
-    cap = max(max(ns), 1)
     item = _lib.CAND_DTYPE.itemsize
-    buf = np.zeros(cap * item, dtype=np.uint8)
-    buf[:len(recs) * item] = np.frombuffer(recs.tobytes(), dtype=np.uint8)
+    dev = _dev(dist)
+    nx = 0 if extra is None else len(extra)
+    head = np.zeros(1 + nx, dtype=np.int64)
+    head[0] = len(recs)
+    if nx:
+        head[1:] = extra
+    k = min(len(recs), _GATHER_CAP)
+    buf = np.zeros(head.nbytes + _GATHER_CAP * item, dtype=np.uint8)
+    buf[:head.nbytes] = np.frombuffer(head.tobytes(), dtype=np.uint8)
+    buf[head.nbytes:head.nbytes + k * item] = np.frombuffer(recs[:k].tobytes(), dtype=np.uint8)
     t = torch.from_numpy(buf).to(dev)
-    outs = [torch.zeros_like(t) for _ in range(world)]
-    dist.all_gather(outs, t)
-    parts = [np.frombuffer(o.cpu().numpy().tobytes(), dtype=_lib.CAND_DTYPE)[:k] for o, k in zip(outs, ns)]
-    return np.concatenate(parts) if parts else recs
+    out = torch.empty(world * buf.size, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, t)
+    raw = out.cpu().numpy().reshape(world, buf.size)
+    heads = [np.frombuffer(raw[r, :head.nbytes].tobytes(), dtype=np.int64) for r in range(world)]
+    ns = [int(h[0]) for h in heads]
+    if max(ns) <= _GATHER_CAP:
+        parts = [np.frombuffer(raw[r, head.nbytes:head.nbytes + ns[r] * item].tobytes(), dtype=_lib.CAND_DTYPE)
+                 for r in range(world)]
+    else:
+        cap = max(ns)
+        big = np.zeros(cap * item, dtype=np.uint8)
+        big[:len(recs) * item] = np.frombuffer(recs.tobytes(), dtype=np.uint8)
+        tb = torch.from_numpy(big).to(dev)
+        outb = torch.empty(world * big.size, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(outb, tb)
+        rawb = outb.cpu().numpy().reshape(world, big.size)
+        parts = [np.frombuffer(rawb[r, :ns[r] * item].tobytes(), dtype=_lib.CAND_DTYPE) for r in range(world)]
+    allrecs = np.concatenate(parts) if parts else recs
+    if extra is None:
+        return allrecs
+    return allrecs, [[int(v) for v in h[1:]] for h in heads]
 
 
 class SearchResult(object):
@@ -119,20 +153,13 @@ def search_n2(plan, stream=None):
     g, prior = exchange_minima(local_min, dist, rank, world)
     recs = plan.pass2(g, prior, stream)
     stats.update({k: v for k, v in plan.stats().items() if k in ("n_rescanned", "ms_pass2")})
-    allrecs = gather_records(recs, dist, world)
+    allrecs, extras = gather_records(recs, dist, world, extra=[stats["n_solved"]])
     res = SearchResult()
     res.records = allrecs
     res.count = total
     res.min_nll = g
     res.stats = stats
-    n_solved = stats["n_solved"]
-    if dist is not None:
-        import torch
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-        t = torch.tensor([n_solved], dtype=torch.int64, device=dev)
-        dist.all_reduce(t)
-        n_solved = int(t.item())
-    res.n_solved = n_solved
+    res.n_solved = sum(e[0] for e in extras)
     idx = fold_replay(allrecs["rank"], allrecs["nll"], dup_first=True)
     res.best = [(int(allrecs["rank"][i]), float(allrecs["mu"][i][0]), float(allrecs["nll"][i]), int(allrecs["status"][i]))
                 for i in idx]

@@ -65,15 +65,10 @@ def search_n3(plan, leaf_cap=256, stream=None):
     g, prior = exchange_minima(local_min, dist, rank, world)
     recs, paths = plan.pass2_n3(g, prior, stream)
     st.update({k: v for k, v in plan.stats().items() if k in ("n_rescanned", "ms_pass2")})
-    allrecs = gather_records(recs, dist, world)
+    allrecs, extras = gather_records(recs, dist, world, extra=[st["n_solved"], st["n_candidates"]])
     allpaths = gather_paths(paths, dist, world)
-    n_solved, n_cand = st["n_solved"], st["n_candidates"]
-    if dist is not None:
-        import torch
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-        t = torch.tensor([n_solved, n_cand], dtype=torch.int64, device=dev)
-        dist.all_reduce(t)
-        n_solved, n_cand = int(t[0].item()), int(t[1].item())
+    n_solved = sum(e[0] for e in extras)
+    n_cand = sum(e[1] for e in extras)
     # the stream the reference folds: the all-[tau,0,0] matrix first (RunTHetA.py:148,188 -- Q2), whose
     # NLL is the all-normal likelihood, then the candidates in enumeration order
     keys = np.concatenate([[0], allrecs["rank"].astype(np.uint64) + np.uint64(1)]).astype(np.uint64)
