@@ -329,22 +329,42 @@ def main():
                      "newton_iters_mean": st["newton_iters"], "stripes": int(st["n_stripes"]),
                      "rescanned_stripes": int(st["n_rescanned"])}
 
-    if rank == 0 and not args.no_extra and args.workload == "cfg2" and world == 1:
+    if not args.no_extra and args.workload == "cfg2":
+        # (a) the >=100x target shape of BASELINE.json (m=150, k=7, 6.07e8 candidates), sharded over all ranks
         P7 = problem("m150k7")
         plan7 = _lib.Plan(2, P7["r"], P7["rN"], P7["lower"], P7["upper"])
         n7 = plan7.count()
+        b7, e7 = search.shard_range(n7, rank, world)
+
+        def step7():
+            lm = plan7.pass1(b7, e7, stream)
+            g_, pr_ = search.exchange_minima(lm, D, rank, world)
+            return search.gather_records(plan7.pass2(g_, pr_, stream), D, world), g_
         for _ in range(2):
-            g7 = plan7.pass1(0, n7, stream)
-            plan7.pass2(g7)
-        torch.cuda.synchronize()
+            step7()
+        barrier()
         t0 = time.perf_counter()
-        g7 = plan7.pass1(0, n7, stream)
-        r7 = plan7.pass2(g7)
-        torch.cuda.synchronize()
+        r7, g7 = step7()
+        barrier()
         dt7 = time.perf_counter() - t0
         extra["m150_k7_full_space"] = {"candidates": n7, "seconds": dt7, "cand_per_s": n7 / dt7, "min_nll": g7,
-                                       "ms_pass1": plan7.stats()["ms_pass1"]}
+                                       "ms_pass1_rank0": plan7.stats()["ms_pass1"], "n_gpus": world}
         plan7.close()
+        # (b) n = 3: BASELINE configs[3] shape (m=150, k=5, explicit bounds, F=12), whole space, sharded by items
+        import theta_oracle as O
+        from theta_b200 import search_n3
+        P3 = O.synthetic_problem_n3(150, 5, 1, 12, False)
+        plan3 = _lib.Plan(3, P3["r"], P3["rN"], P3["lower"], P3["upper"])
+        search_n3.search_n3(plan3, leaf_cap=512)
+        barrier()
+        t0 = time.perf_counter()
+        res3 = search_n3.search_n3(plan3, leaf_cap=512)
+        barrier()
+        dt3 = time.perf_counter() - t0
+        extra["n3_m150_k5_full_space"] = {"candidates": res3.count, "seconds": dt3, "cand_per_s": res3.count / dt3,
+                                          "min_nll": res3.min_nll, "items": res3.n_items, "n_gpus": world,
+                                          "ms_pass1_rank0": res3.stats["ms_pass1"], "hybrj_fevals_mean": res3.stats["newton_iters"]}
+        plan3.close()
 
     cpu = None
     if rank == 0 and not args.no_cpu:

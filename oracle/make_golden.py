@@ -245,6 +245,26 @@ def gen_synth_n3(R):
     _dump("synth_n3_candidates.json", out)
 
 
+def gen_config1_cli(R):
+    """The reference's own CLI on config #1 (RunTHetA.main, ~3 min): .n2.results and .n2.withBounds as text fixtures,
+    plus the input file itself (the reference's example *data*, needed on the GPU box)."""
+    import shutil
+    src = os.path.join(REFPY, "..", "example", "Example.intervals")
+    out = "/tmp/theta_golden_cli"
+    os.makedirs(out, exist_ok=True)
+    argv = sys.argv
+    sys.argv = ["RunTHetA.py", src, "-n", "2", "-k", "3", "--NUM_PROCESSES", "1", "-d", out, "-p", "ex"]
+    try:
+        with _quiet():
+            R.RunTHetA.main()
+    finally:
+        sys.argv = argv
+    shutil.copy(src, os.path.join(GOLD, "Example.intervals"))
+    shutil.copy(os.path.join(out, "ex.n2.results"), os.path.join(GOLD, "config1_cli.n2.results"))
+    shutil.copy(os.path.join(out, "ex.n2.withBounds"), os.path.join(GOLD, "config1_cli.n2.withBounds"))
+    print("wrote config1 CLI fixtures")
+
+
 def gen_edge(R):
     """Edge-case KATs from the live Optimizer.solve."""
     m = 7
@@ -297,6 +317,8 @@ def main():
         gen_synth_n3(R)
     if "config1" in todo:
         gen_config1(R)
+    if "config1_cli" in todo:
+        gen_config1_cli(R)
 
 
 if __name__ == "__main__":

@@ -36,7 +36,7 @@ struct DcState {
 };
 
 // scipy _dcsrch.py: dcstep
-THETA_HD void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp, double fp,
+THETA_HDN void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp, double fp,
                      double dp, bool& brackt, double stpmin, double stpmax) {
     const double sgnd = np_sign(dp) * np_sign(dx);
     double stpf;
@@ -117,7 +117,7 @@ THETA_HD void dcstep(double& stx, double& fx, double& dx, double& sty, double& f
 enum Task { START = 0, FG = 1, CONV = 2, WARN = 3, ERROR = 4 };
 
 // scipy _dcsrch.py: DCSRCH._iterate
-THETA_HD Task dcsrch_iterate(DcState& S, double& stp, double f, double g, Task task, double ftol, double gtol, double xtol,
+THETA_HDN Task dcsrch_iterate(DcState& S, double& stp, double f, double g, Task task, double ftol, double gtol, double xtol,
                              double stpmin, double stpmax) {
     const double p5 = 0.5, p66 = 0.66, xtrapl = 1.1, xtrapu = 4.0;
     if (task == START) {
@@ -177,7 +177,7 @@ THETA_HD Task dcsrch_iterate(DcState& S, double& stp, double f, double g, Task t
 }
 
 // scipy _linesearch.py: _cubicmin / _quadmin (None <=> returns false)
-THETA_HD bool cubicmin(double a, double fa, double fpa, double b, double fb, double c, double fc, double& xmin) {
+THETA_HDN bool cubicmin(double a, double fa, double fpa, double b, double fb, double c, double fc, double& xmin) {
     const double Cc = fpa;
     const double db = b - a, dc = c - a;
     const double denom = (db * dc) * (db * dc) * (db - dc);
@@ -193,7 +193,7 @@ THETA_HD bool cubicmin(double a, double fa, double fpa, double b, double fb, dou
     xmin = a + (-B + sqrt(radical)) / (3 * A);
     return finite_(xmin);
 }
-THETA_HD bool quadmin(double a, double fa, double fpa, double b, double fb, double& xmin) {
+THETA_HDN bool quadmin(double a, double fa, double fpa, double b, double fb, double& xmin) {
     const double D = fa, Cc = fpa;
     const double db = b - a * 1.0;
     if (db * db == 0.0) return false;
@@ -205,7 +205,7 @@ THETA_HD bool quadmin(double a, double fa, double fpa, double b, double fb, doub
 
 // Fn provides double phi(double alpha), double derphi(double alpha)
 template <class Fn>
-THETA_HD bool zoom(Fn& fn, double a_lo, double a_hi, double phi_lo, double phi_hi, double derphi_lo, double phi0,
+THETA_HDN bool zoom(Fn& fn, double a_lo, double a_hi, double phi_lo, double phi_hi, double derphi_lo, double phi0,
                    double derphi0, double c1, double c2, double& a_star) {
     const int maxiter = 10;
     int i = 0;
@@ -247,7 +247,7 @@ THETA_HD bool zoom(Fn& fn, double a_lo, double a_hi, double phi_lo, double phi_h
 // _line_search_wolfe12 as called by _minimize_bfgs (amin=1e-100, amax=1e100, c1=1e-4, c2=0.9).
 // Returns true and the step length if a step is taken, false if _LineSearchError is raised.
 template <class Fn>
-THETA_HD bool line_search_wolfe12(Fn& fn, double phi0, double old_phi0, double derphi0, double& alpha_out) {
+THETA_HDN bool line_search_wolfe12(Fn& fn, double phi0, double old_phi0, double derphi0, double& alpha_out) {
     const double c1 = 1e-4, c2 = 0.9, amax = 1e100, amin = 1e-100, xtol = 1e-14;
     // ---- scalar_search_wolfe1 (DCSRCH)
     {

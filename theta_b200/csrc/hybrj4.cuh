@@ -15,8 +15,11 @@
 
 #ifndef __CUDACC__
 #define THETA_HD inline
+#define THETA_HDN inline
 #else
 #define THETA_HD __host__ __device__ __forceinline__
+// the solver is large: out-of-line routines keep the kernels within the instruction cache
+#define THETA_HDN __host__ __device__ __noinline__
 #endif
 
 namespace theta {
@@ -27,7 +30,7 @@ constexpr int LR = N * (N + 1) / 2;
 constexpr double EPSMCH = 2.220446049250313e-16;   // dpmpar(1)
 constexpr double GIANT = 1.7976931348623157e308;   // dpmpar(3)
 
-THETA_HD double enorm(int n, const double* x) {
+THETA_HDN double enorm(int n, const double* x) {
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0, x1max = 0.0, x3max = 0.0;
     const double agiant = rgiant / (double)n;
@@ -64,7 +67,7 @@ THETA_HD double enorm(int n, const double* x) {
 }
 
 // a is column-major N x N: a[i + N*j]
-THETA_HD void qrfac(double* a, double* rdiag, double* acnorm) {
+THETA_HDN void qrfac(double* a, double* rdiag, double* acnorm) {
     for (int j = 0; j < N; ++j) {
         acnorm[j] = enorm(N, a + N * j);
         rdiag[j] = acnorm[j];
@@ -86,7 +89,7 @@ THETA_HD void qrfac(double* a, double* rdiag, double* acnorm) {
     }
 }
 
-THETA_HD void qform(double* q, double* wa) {
+THETA_HDN void qform(double* q, double* wa) {
     for (int j = 1; j < N; ++j)
         for (int i = 0; i < j; ++i) q[i + N * j] = 0.0;
     for (int l = 0; l < N; ++l) {
@@ -108,7 +111,7 @@ THETA_HD void qform(double* q, double* wa) {
 }
 
 // r: upper triangle packed by rows (0-based l); x: output step
-THETA_HD void dogleg(const double* r, const double* diag, const double* qtb, double delta, double* x, double* wa1,
+THETA_HDN void dogleg(const double* r, const double* diag, const double* qtb, double delta, double* x, double* wa1,
                      double* wa2) {
     // Gauss-Newton direction
     int jj = LR;  // 0-based index one past the last diagonal (1-based jj = LR + 1)
@@ -179,7 +182,7 @@ THETA_HD void dogleg(const double* r, const double* diag, const double* qtb, dou
 }
 
 // s: lower triangular stored by columns (== R packed by rows); m = n = N
-THETA_HD void r1updt(double* s, const double* u, double* v, double* w, bool* sing) {
+THETA_HDN void r1updt(double* s, const double* u, double* v, double* w, bool* sing) {
     const double p5 = 0.5, p25 = 0.25;
     int jj = LR - 1;  // 0-based index of s(N-1,N-1)
     w[N - 1] = s[jj];
@@ -246,7 +249,7 @@ THETA_HD void r1updt(double* s, const double* u, double* v, double* w, bool* sin
 }
 
 // a: m x N column-major with leading dimension lda
-THETA_HD void r1mpyq(int m, double* a, int lda, const double* v, const double* w) {
+THETA_HDN void r1mpyq(int m, double* a, int lda, const double* v, const double* w) {
     for (int nmj = 1; nmj <= N - 1; ++nmj) {
         const int j = N - 1 - nmj;
         double c, sn;
@@ -286,7 +289,7 @@ struct Result {
 
 // Sys must provide:  void fcn(const double* x, double* fvec);  void jac(const double* x, double* fjac /*col-major*/);
 template <class Sys>
-THETA_HD Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double factor) {
+THETA_HDN Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double factor) {
     const double p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
     double fvec[N], fjac[N * N], diag[N], r[LR], qtf[N], wa1[N], wa2[N], wa3[N], wa4[N];
     Result res{0, 0, 0};

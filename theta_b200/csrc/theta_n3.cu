@@ -203,7 +203,7 @@ struct Search3Params {
 };
 
 template <int MAXM, bool EMIT>
-__global__ void __launch_bounds__(kBlock3) n3_search_kernel(const Search3Params p) {
+__global__ void __launch_bounds__(kBlock3, 8) n3_search_kernel(const Search3Params p) {
     __shared__ N3Dev D;
     if (threadIdx.x == 0) D = p.D;
     __syncthreads();

@@ -38,7 +38,7 @@ struct Groups3 {
 struct Kkt3 {
     const Groups3* g;
     double t0, t1, t2;
-    THETA_HD void fcn(const double* x, double* f) {
+    THETA_HDN void fcn(const double* x, double* f) {
         const double u0 = x[0] * t0, u1 = x[1] * t1, u2 = x[2] * t2;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         for (int i = 0; i < g->G; ++i) {
@@ -53,7 +53,7 @@ struct Kkt3 {
         f[2] = -(t2 * s2) - x[3];
         f[3] = 1.0 - ((x[0] + x[1]) + x[2]);
     }
-    THETA_HD void jac(const double* x, double* J) {
+    THETA_HDN void jac(const double* x, double* J) {
         const double u0 = x[0] * t0, u1 = x[1] * t1, u2 = x[2] * t2;
         double j00 = 0, j01 = 0, j02 = 0, j11 = 0, j12 = 0, j22 = 0;
         for (int i = 0; i < g->G; ++i) {
@@ -87,7 +87,7 @@ struct Ray3 {
     const Groups3* g;
     double t0, t1, t2, Kr;
     double x0[2], pk[2];
-    THETA_HD double L3_hat(double m0, double m1) const {
+    THETA_HDN double L3_hat(double m0, double m1) const {
         const double m2 = 1.0 - (m0 + m1);
         double s = 0.0;
         for (int i = 0; i < g->G; ++i) {
@@ -96,7 +96,7 @@ struct Ray3 {
         }
         return Kr - s;
     }
-    THETA_HD void dL3_hat(double m0, double m1, double* out) const {
+    THETA_HDN void dL3_hat(double m0, double m1, double* out) const {
         double v0 = 0.0, v1 = 0.0;
         for (int i = 0; i < g->G; ++i) {
             const double c2 = g->b[i] * t2;
@@ -125,7 +125,7 @@ struct Solve3Out {
 };
 
 // L3 on grouped statistics at normalised-coordinate solution muhat
-THETA_HD void n3_finish(const Groups3& g, double S1, double S2, const N3Const& k, const double* muhat, Solve3Out& o) {
+THETA_HDN void n3_finish(const Groups3& g, double S1, double S2, const N3Const& k, const double* muhat, Solve3Out& o) {
     // M3: mu_j proportional to muhat_j / S_j (S_0 = tau A)
     const double w0 = muhat[0] / (k.tau * k.A), w1 = muhat[1] / S1, w2 = muhat[2] / S2;
     const double ws = (w0 + w1) + w2;
@@ -148,7 +148,7 @@ THETA_HD void n3_finish(const Groups3& g, double S1, double S2, const N3Const& k
     o.nll = k.K0 - acc;
 }
 
-THETA_HD void n3_solve(const Groups3& g, double S1, double S2, const N3Const& k, Solve3Out& o) {
+THETA_HDN void n3_solve(const Groups3& g, double S1, double S2, const N3Const& k, Solve3Out& o) {
     o.nfev = 0;
     o.nll = 0.0;
     o.mu[0] = o.mu[1] = o.mu[2] = 0.0;

@@ -31,7 +31,7 @@ namespace theta {
 
 static constexpr int kRows = 128;   // rows per tile == threads per CTA
 static constexpr int kStages = 1;   // one tile in flight per CTA; 8 CTAs per SM overlap copy and compute
-static constexpr int kMaxRuns = 16;  // run list per row kept in shared memory; longer rows take the direct path
+static constexpr int kMaxRuns = 12;  // run list per row kept in shared memory; longer rows take the direct path
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -79,9 +79,9 @@ struct TileParams {
 // Shared-memory carve-up (dynamic): ring of tiles | PR | PRN | ZP | [histogram] ; barriers are static.
 struct TileSmem {
     unsigned char* ring;
-    double* PR;
-    double* PRN;
     int32_t* ZP;
+    double2* PRP;    // [pitch+1] (PR, PRN) interleaved: one 16-byte read per run end
+    double2* LT;     // fast_log table (4 KB)
     uint16_t* runs;  // [kMaxRuns][kRows]: (value << 10) | end
     double* hist;
 };
@@ -89,9 +89,10 @@ struct TileSmem {
 __host__ __device__ inline size_t tile_smem_bytes(int64_t pitch, int hist_levels) {
     size_t o = (size_t)kStages * kRows * pitch;
     o = (o + 15) & ~(size_t)15;
-    o += sizeof(double) * (pitch + 1) * 2;
     o += sizeof(int32_t) * (pitch + 1);
     o = (o + 15) & ~(size_t)15;
+    o += sizeof(double2) * (pitch + 1);
+    o += sizeof(double2) * THETA_LOGTAB_SIZE;
     o += sizeof(uint16_t) * kMaxRuns * kRows;
     o += sizeof(double) * (size_t)hist_levels * kRows;
     return o;
@@ -103,13 +104,13 @@ __device__ __forceinline__ TileSmem tile_smem_bind(unsigned char* base, int64_t 
     s.ring = base;
     o = (size_t)kStages * kRows * pitch;
     o = (o + 15) & ~(size_t)15;
-    s.PR = reinterpret_cast<double*>(base + o);
-    o += sizeof(double) * (pitch + 1);
-    s.PRN = reinterpret_cast<double*>(base + o);
-    o += sizeof(double) * (pitch + 1);
     s.ZP = reinterpret_cast<int32_t*>(base + o);
     o += sizeof(int32_t) * (pitch + 1);
     o = (o + 15) & ~(size_t)15;
+    s.PRP = reinterpret_cast<double2*>(base + o);
+    o += sizeof(double2) * (pitch + 1);
+    s.LT = reinterpret_cast<double2*>(base + o);
+    o += sizeof(double2) * THETA_LOGTAB_SIZE;
     s.runs = reinterpret_cast<uint16_t*>(base + o);
     o += sizeof(uint16_t) * kMaxRuns * kRows;
     s.hist = reinterpret_cast<double*>(base + o);
@@ -165,29 +166,37 @@ __device__ __forceinline__ void scan_runs(const unsigned char* row, int words, F
 // A word whose 8 bytes all equal the current value costs five integer instructions.  Returns the
 // number of runs, or -1 if the row has more than kMaxRuns runs / a value above 63 (caller falls back
 // to scan_runs).  Positions >= m (zero padding) never open a run.
+__device__ __forceinline__ uint32_t nz_bytes4(uint32_t d) {
+    // bit b set <=> byte b of d is non-zero (bit 7 of each byte, gathered by a carry-free multiply)
+    const uint32_t t = ((((d | 0x80808080u) - 0x01010101u) | d) & 0x80808080u) >> 7;
+    return (t * 0x00204081u) >> 21 & 0xfu;
+}
+
 __device__ __forceinline__ int collect_runs(const unsigned char* row, int words, int m, uint16_t* runs) {
     const uint2* rw = reinterpret_cast<const uint2*>(row);
-    uint2 w = rw[0];
-    uint32_t cur = w.x & 0xffu;
+    uint32_t cur = rw[0].x & 0xffu;  // value of the open run == last byte seen
     uint32_t curpat = cur * 0x01010101u;
     int n = 0;
     bool over = false;
     for (int wi = 0; wi < words; ++wi) {
-        if (wi) w = rw[wi];
+        const uint2 w = rw[wi];
         if (((w.x ^ curpat) | (w.y ^ curpat)) != 0u) {
-            const uint64_t ww = ((uint64_t)w.y << 32) | w.x;
-            uint64_t x = ww ^ ((ww << 8) | cur);
-            while (x) {
-                const int b = (__ffsll((long long)x) - 1) >> 3;
+            // change points: byte b differs from its predecessor
+            const uint32_t dlo = w.x ^ ((w.x << 8) | cur);
+            const uint32_t dhi = w.y ^ __funnelshift_l(w.x, w.y, 8);
+            uint32_t cm = nz_bytes4(dlo) | (nz_bytes4(dhi) << 4);
+            while (cm) {
+                const int b = __ffs((int)cm) - 1;
                 const int pos = wi * 8 + b;
-                if (pos >= m) break;
+                if (pos >= m) break;  // zero padding
                 if (n < kMaxRuns - 1 && cur < 64u) runs[n * kRows] = (uint16_t)((cur << 10) | (uint32_t)pos);
                 else over = true;
                 ++n;
-                cur = (uint32_t)(ww >> (8 * b)) & 0xffu;
-                x &= ~(0xffull << (8 * b));
+                cur = __byte_perm(w.x, w.y, (uint32_t)b) & 0xffu;
+                cm &= cm - 1;
             }
-            curpat = cur * 0x01010101u;
+            if (cm == 0u) cur = w.y >> 24;  // (when we stopped inside the padding the open run keeps its value)
+            curpat = (cm == 0u) ? cur * 0x01010101u : 0u;  // padding words are all zero
         }
     }
     if (over || cur >= 64u) return -1;
@@ -203,10 +212,10 @@ __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
     const int tid = threadIdx.x;
     const int words = (int)(p.pitch >> 3);
     for (int i = tid; i <= p.pitch; i += kRows) {
-        S.PR[i] = p.PR[i];
-        S.PRN[i] = p.PRN[i];
         S.ZP[i] = p.ZP[i];
+        S.PRP[i] = make_double2(p.PR[i], p.PRN[i]);
     }
+    for (int i = tid; i < THETA_LOGTAB_SIZE; i += kRows) S.LT[i] = p.logtab[i];
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -253,22 +262,23 @@ __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
                         const uint32_t code = myruns[j * kRows];
                         const int e = (int)(code & 1023u);
                         const double v = (double)(code >> 10);
-                        const double pr_e = S.PR[e], prn_e = S.PRN[e];
+                        const double2 pp = S.PRP[e];
+                        const double pr_e = pp.x, prn_e = pp.y;
                         const double wgt = pr_e - pr_s;
                         s1 = fma(v, prn_e - prn_s, s1);
-                        if (wgt != 0.0) acc = fma(wgt, fast_log(fma(v, mu1, tm), p.logtab), acc);
+                        if (wgt != 0.0) acc = fma(wgt, fast_log(fma(v, mu1, tm), S.LT), acc);
                         pr_s = pr_e;
                         prn_s = prn_e;
                     }
                 } else {
                     scan_runs(rp, words, [&](uint32_t v, int s, int e) {
-                        const double wgt = S.PR[e] - S.PR[s];
-                        s1 = fma((double)v, S.PRN[e] - S.PRN[s], s1);
+                        const double wgt = S.PRP[e].x - S.PRP[s].x;
+                        s1 = fma((double)v, S.PRP[e].y - S.PRP[s].y, s1);
                         if (wgt != 0.0) acc = fma(wgt, log(fma((double)v, mu1, tm)), acc);
                     });
                 }
                 const double gbar = (mu * kc.S0 + mu1 * s1) / kc.A;
-                double nll = kc.K0 - (acc - kc.Rtot * fast_log(gbar, p.logtab));
+                double nll = kc.K0 - (acc - kc.Rtot * fast_log(gbar, S.LT));
                 if (kc.any_zero_rN) nll = INFINITY;
                 p.nll_out[row] = nll;
             } else {
@@ -278,9 +288,9 @@ __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
                 double s1 = 0.0;
                 bool z0 = false, bad = false;
                 auto on_run = [&](uint32_t v, int s, int e) {
-                    const double wgt = S.PR[e] - S.PR[s];
-                    if (v > (uint32_t)KT) { if (S.PRN[e] - S.PRN[s] != 0.0 || wgt != 0.0) bad = true; return; }
-                    s1 = fma((double)v, S.PRN[e] - S.PRN[s], s1);
+                    const double wgt = S.PRP[e].x - S.PRP[s].x;
+                    if (v > (uint32_t)KT) { if (S.PRP[e].y - S.PRP[s].y != 0.0 || wgt != 0.0) bad = true; return; }
+                    s1 = fma((double)v, S.PRP[e].y - S.PRP[s].y, s1);
                     h[v * kRows] += wgt;
                     if (v == 0 && S.ZP[e] - S.ZP[s] > 0) z0 = true;
                 };
