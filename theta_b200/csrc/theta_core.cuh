@@ -60,9 +60,10 @@ __device__ __forceinline__ double fast_rcp(double a) {
 // Absolute error ~1e-16, i.e. as accurate as libm's log here, at about half the instructions.
 #define THETA_LOGTAB_SIZE 256
 __device__ __forceinline__ double fast_log(double g, const double2* __restrict__ LT) {
-    if (!(g > 1e-300 && g < 1e300)) return log(g);  // zero, negative, NaN, denormal: the library path
     const long long bits = __double_as_longlong(g);
     const int hi = (int)(bits >> 32);
+    // zero, negative, denormal, inf, NaN: the library path (one integer compare on the exponent word)
+    if ((uint32_t)(hi - 0x00100000) >= 0x7fe00000u) return log(g);
     const int e = (hi >> 20) - 1023;
     const int idx = (hi >> 12) & 0xff;
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
@@ -234,6 +235,22 @@ __device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool 
 namespace theta {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+// Caching allocators (theta_rt.cu).  Blocks are size-bucketed and kept per device until
+// theta_shutdown(), so a search call allocates nothing from the driver after its first use:
+// cudaMalloc / cudaFree cost 0.1-0.5 ms each and cudaFree synchronises the whole device, which
+// dominated the end-to-end latency of a 1.4 ms search.  Callers free only after the work that
+// uses a block has been synchronised (every host-facing entry point ends with a stream sync).
+cudaError_t dmalloc_bytes(void** p, size_t bytes);
+void dfree(void* p);
+template <typename T>
+inline cudaError_t dmalloc(T** p, size_t bytes) { return dmalloc_bytes(reinterpret_cast<void**>(p), bytes); }
+// pinned host staging blocks, same policy
+cudaError_t hmalloc_bytes(void** p, size_t bytes);
+void hfree(void* p);
+template <typename T>
+inline cudaError_t hmalloc(T** p, size_t bytes) { return hmalloc_bytes(reinterpret_cast<void**>(p), bytes); }
+void cache_release();  // returns every cached block to the driver
 }  // namespace theta
 
 #define THETA_CUDA(expr)                                                        \

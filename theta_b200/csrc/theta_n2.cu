@@ -387,15 +387,15 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
         pl->count = (empty || qlo[KT - 1] > qhi[KT - 1]) ? 0 : swK[qlo[KT - 1]];
         if (empty) pl->count = 0;
     }
-    cudaError_t e = cudaMalloc(&pl->d_tables, pl->layout.bytes);
+    cudaError_t e = theta::dmalloc(&pl->d_tables, pl->layout.bytes);
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_tables, blob.data(), pl->layout.bytes, cudaMemcpyHostToDevice);
     std::vector<double> rd(m), rnd(m);
     for (int i = 0; i < m; ++i) { rd[i] = (double)pl->r[i]; rnd[i] = (double)pl->rN[i]; }
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_r, sizeof(double) * m);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_rN, sizeof(double) * m);
+    if (e == cudaSuccess) e = theta::dmalloc(&pl->d_r, sizeof(double) * m);
+    if (e == cudaSuccess) e = theta::dmalloc(&pl->d_rN, sizeof(double) * m);
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_r, rd.data(), sizeof(double) * m, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_rN, rnd.data(), sizeof(double) * m, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_counters, sizeof(unsigned long long) * kCounters);
+    if (e == cudaSuccess) e = theta::dmalloc(&pl->d_counters, sizeof(unsigned long long) * kCounters);
     {   // fast_log table: r_i = 1/(1 + (i+0.5)/256) rounded to fp64 and -ln(r_i) of that very number
         std::vector<double2> lt(THETA_LOGTAB_SIZE);
         for (int i = 0; i < THETA_LOGTAB_SIZE; ++i) {
@@ -403,7 +403,7 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
             lt[i].x = rinv;
             lt[i].y = (double)(-logl((long double)rinv));
         }
-        if (e == cudaSuccess) e = cudaMalloc(&pl->d_logtab, sizeof(double2) * THETA_LOGTAB_SIZE);
+        if (e == cudaSuccess) e = theta::dmalloc(&pl->d_logtab, sizeof(double2) * THETA_LOGTAB_SIZE);
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_logtab, lt.data(), sizeof(double2) * THETA_LOGTAB_SIZE, cudaMemcpyHostToDevice);
     }
     {   // prefix tables for the tile kernels (theta_tiles.cu)
@@ -417,9 +417,9 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
             if (i < m) { s += pl->r[i]; sn += pl->rN[i]; z += pl->r[i] == 0 ? 1 : 0; }
             PR[i + 1] = (double)s; PRN[i + 1] = (double)sn; ZP[i + 1] = z;
         }
-        if (e == cudaSuccess) e = cudaMalloc(&pl->d_PR, sizeof(double) * (pitch + 1));
-        if (e == cudaSuccess) e = cudaMalloc(&pl->d_PRN, sizeof(double) * (pitch + 1));
-        if (e == cudaSuccess) e = cudaMalloc(&pl->d_ZP, sizeof(int32_t) * (pitch + 1));
+        if (e == cudaSuccess) e = theta::dmalloc(&pl->d_PR, sizeof(double) * (pitch + 1));
+        if (e == cudaSuccess) e = theta::dmalloc(&pl->d_PRN, sizeof(double) * (pitch + 1));
+        if (e == cudaSuccess) e = theta::dmalloc(&pl->d_ZP, sizeof(int32_t) * (pitch + 1));
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_PR, PR.data(), sizeof(double) * (pitch + 1), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_PRN, PRN.data(), sizeof(double) * (pitch + 1), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(pl->d_ZP, ZP.data(), sizeof(int32_t) * (pitch + 1), cudaMemcpyHostToDevice);
@@ -436,10 +436,10 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
 extern "C" void theta_plan_destroy(theta_plan* pl) {
     if (!pl) return;
     theta_n3_plan_free(pl);
-    cudaFree(pl->d_tables); cudaFree(pl->d_r); cudaFree(pl->d_rN);
-    cudaFree(pl->d_PR); cudaFree(pl->d_PRN); cudaFree(pl->d_ZP);
-    cudaFree(pl->d_stripe_min); cudaFree(pl->d_counters); cudaFree(pl->d_emit);
-    cudaFree(pl->d_list); cudaFree(pl->d_prior); cudaFree(pl->d_logtab);
+    theta::dfree(pl->d_tables); theta::dfree(pl->d_r); theta::dfree(pl->d_rN);
+    theta::dfree(pl->d_PR); theta::dfree(pl->d_PRN); theta::dfree(pl->d_ZP);
+    theta::dfree(pl->d_stripe_min); theta::dfree(pl->d_counters); theta::dfree(pl->d_emit);
+    theta::dfree(pl->d_list); theta::dfree(pl->d_prior); theta::dfree(pl->d_logtab);
     delete pl;
 }
 
@@ -486,13 +486,13 @@ extern "C" int theta_enumerate_n2(theta_plan* pl, uint64_t rank_begin, int64_t c
     if (!pl || !cols_host) { set_error("null argument"); return THETA_ERR_INVALID; }
     if (count <= 0) return THETA_OK;
     int8_t* d = nullptr;
-    THETA_CUDA(cudaMalloc(&d, (size_t)count * pitch));
+    THETA_CUDA(theta::dmalloc(&d, (size_t)count * pitch));
     int rc = theta_enumerate_n2_dev(pl, rank_begin, count, d, pitch, nullptr);
     if (rc == THETA_OK) {
         cudaError_t e = cudaMemcpy(cols_host, d, (size_t)count * pitch, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "enumerate D2H", __FILE__, __LINE__);
     }
-    cudaFree(d);
+    theta::dfree(d);
     return rc;
 }
 
@@ -521,8 +521,8 @@ extern "C" int theta_search_n2_pass1(theta_plan* pl, uint64_t rank_begin, uint64
     const uint64_t stripes = (N + L * 32 - 1) / (L * 32);
     pl->p1_stripes = stripes;
     if (stripes > pl->stripe_cap) {
-        cudaFree(pl->d_stripe_min); pl->d_stripe_min = nullptr; pl->stripe_cap = 0;
-        THETA_CUDA(cudaMalloc(&pl->d_stripe_min, sizeof(double) * stripes));
+        theta::dfree(pl->d_stripe_min); pl->d_stripe_min = nullptr; pl->stripe_cap = 0;
+        THETA_CUDA(theta::dmalloc(&pl->d_stripe_min, sizeof(double) * stripes));
         pl->stripe_cap = stripes;
     }
     THETA_CUDA(cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kCounters, st));
@@ -582,10 +582,10 @@ extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double p
     pl->stats.n_rescanned = list.size();
     if (list.empty()) return THETA_OK;
     if (list.size() > pl->list_cap) {
-        cudaFree(pl->d_list); cudaFree(pl->d_prior); pl->d_list = nullptr; pl->d_prior = nullptr; pl->list_cap = 0;
+        theta::dfree(pl->d_list); theta::dfree(pl->d_prior); pl->d_list = nullptr; pl->d_prior = nullptr; pl->list_cap = 0;
         const size_t want_l = std::max<size_t>(1024, list.size() * 2);
-        THETA_CUDA(cudaMalloc(&pl->d_list, sizeof(uint32_t) * want_l));
-        THETA_CUDA(cudaMalloc(&pl->d_prior, sizeof(double) * want_l));
+        THETA_CUDA(theta::dmalloc(&pl->d_list, sizeof(uint32_t) * want_l));
+        THETA_CUDA(theta::dmalloc(&pl->d_prior, sizeof(double) * want_l));
         pl->list_cap = want_l;
     }
     uint32_t* d_list = pl->d_list;
@@ -599,8 +599,8 @@ extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double p
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int attempt = 0; attempt < 8; ++attempt) {
         if (want > pl->emit_cap) {
-            cudaFree(pl->d_emit); pl->d_emit = nullptr; pl->emit_cap = 0;
-            cudaError_t e = cudaMalloc(&pl->d_emit, sizeof(theta_cand) * want);
+            theta::dfree(pl->d_emit); pl->d_emit = nullptr; pl->emit_cap = 0;
+            cudaError_t e = theta::dmalloc(&pl->d_emit, sizeof(theta_cand) * want);
             if (e != cudaSuccess) { rc = cuda_fail(e, "emit buffer", __FILE__, __LINE__); break; }
             pl->emit_cap = want;
         }
@@ -683,9 +683,9 @@ extern "C" int theta_eval_ranks_n2(theta_plan* pl, const uint64_t* ranks_host, i
         if (ranks_host[i] >= pl->count) { set_error("rank %llu out of range", (unsigned long long)ranks_host[i]); return THETA_ERR_INVALID; }
     uint64_t* d_ranks = nullptr; theta_cand* d_out = nullptr; double* d_vals = nullptr;
     const int m = pl->m;
-    THETA_CUDA(cudaMalloc(&d_ranks, sizeof(uint64_t) * count));
-    THETA_CUDA(cudaMalloc(&d_out, sizeof(theta_cand) * count));
-    if (vals_host) THETA_CUDA(cudaMalloc(&d_vals, sizeof(double) * count * m));
+    THETA_CUDA(theta::dmalloc(&d_ranks, sizeof(uint64_t) * count));
+    THETA_CUDA(theta::dmalloc(&d_out, sizeof(theta_cand) * count));
+    if (vals_host) THETA_CUDA(theta::dmalloc(&d_vals, sizeof(double) * count * m));
     THETA_CUDA(cudaMemcpy(d_ranks, ranks_host, sizeof(uint64_t) * count, cudaMemcpyHostToDevice));
     const int grid = (int)((count + kBlock - 1) / kBlock);
     THETA_KT_DISPATCH(pl->KT, {
@@ -696,6 +696,6 @@ extern "C" int theta_eval_ranks_n2(theta_plan* pl, const uint64_t* ranks_host, i
     THETA_CUDA(cudaGetLastError());
     THETA_CUDA(cudaMemcpy(out_host, d_out, sizeof(theta_cand) * count, cudaMemcpyDeviceToHost));
     if (vals_host) THETA_CUDA(cudaMemcpy(vals_host, d_vals, sizeof(double) * count * m, cudaMemcpyDeviceToHost));
-    cudaFree(d_ranks); cudaFree(d_out); cudaFree(d_vals);
+    theta::dfree(d_ranks); theta::dfree(d_out); theta::dfree(d_vals);
     return THETA_OK;
 }

@@ -361,10 +361,10 @@ int theta_n3_plan_init(theta_plan* pl) {
     s->kc.m = m; s->kc.NR = s->NR; s->kc.any_zero_rN = zero_rN;
     std::vector<double> rd(m), rnd(m);
     for (int i = 0; i < m; ++i) { rd[i] = (double)pl->r[i]; rnd[i] = (double)pl->rN[i]; }
-    THETA_CUDA(cudaMalloc(&s->d_allow, sizeof(uint64_t) * m));
-    THETA_CUDA(cudaMalloc(&s->d_r, sizeof(double) * m));
-    THETA_CUDA(cudaMalloc(&s->d_rN, sizeof(double) * m));
-    THETA_CUDA(cudaMalloc(&s->d_ctr, sizeof(unsigned long long) * 8));
+    THETA_CUDA(theta::dmalloc(&s->d_allow, sizeof(uint64_t) * m));
+    THETA_CUDA(theta::dmalloc(&s->d_r, sizeof(double) * m));
+    THETA_CUDA(theta::dmalloc(&s->d_rN, sizeof(double) * m));
+    THETA_CUDA(theta::dmalloc(&s->d_ctr, sizeof(unsigned long long) * 8));
     THETA_CUDA(cudaMemcpy(s->d_allow, s->allow.data(), sizeof(uint64_t) * m, cudaMemcpyHostToDevice));
     THETA_CUDA(cudaMemcpy(s->d_r, rd.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
     THETA_CUDA(cudaMemcpy(s->d_rN, rnd.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
@@ -374,8 +374,8 @@ int theta_n3_plan_init(theta_plan* pl) {
 void theta_n3_plan_free(theta_plan* pl) {
     theta_n3_state* s = pl->n3;
     if (!s) return;
-    cudaFree(s->d_allow); cudaFree(s->d_r); cudaFree(s->d_rN); cudaFree(s->d_prefix); cudaFree(s->d_off);
-    cudaFree(s->d_item_min); cudaFree(s->d_ctr);
+    theta::dfree(s->d_allow); theta::dfree(s->d_r); theta::dfree(s->d_rN); theta::dfree(s->d_prefix); theta::dfree(s->d_off);
+    theta::dfree(s->d_item_min); theta::dfree(s->d_ctr);
     delete s;
     pl->n3 = nullptr;
 }
@@ -492,12 +492,12 @@ extern "C" int theta_n3_prepare(theta_plan* pl, int64_t leaf_cap, int64_t max_it
     ex.run();
     s->truncated = ex.overflow;
     const size_t ni = s->off.size() - 1;
-    cudaFree(s->d_prefix); cudaFree(s->d_off); cudaFree(s->d_item_min);
+    theta::dfree(s->d_prefix); theta::dfree(s->d_off); theta::dfree(s->d_item_min);
     s->d_prefix = nullptr; s->d_off = nullptr; s->d_item_min = nullptr;
     if (ni) {
-        THETA_CUDA(cudaMalloc(&s->d_prefix, std::max<size_t>(1, s->prefix.size())));
-        THETA_CUDA(cudaMalloc(&s->d_off, sizeof(uint32_t) * (ni + 1)));
-        THETA_CUDA(cudaMalloc(&s->d_item_min, sizeof(double) * ni));
+        THETA_CUDA(theta::dmalloc(&s->d_prefix, std::max<size_t>(1, s->prefix.size())));
+        THETA_CUDA(theta::dmalloc(&s->d_off, sizeof(uint32_t) * (ni + 1)));
+        THETA_CUDA(theta::dmalloc(&s->d_item_min, sizeof(double) * ni));
         THETA_CUDA(cudaMemcpy(s->d_prefix, s->prefix.data(), s->prefix.size(), cudaMemcpyHostToDevice));
         THETA_CUDA(cudaMemcpy(s->d_off, s->off.data(), sizeof(uint32_t) * (ni + 1), cudaMemcpyHostToDevice));
     }
@@ -589,16 +589,16 @@ static int run_emit(theta_plan* pl, const std::vector<uint32_t>& list, const std
     if (list.empty()) return THETA_OK;
     uint32_t* d_list = nullptr; double* d_prior = nullptr; theta_cand* d_emit = nullptr; uint8_t* d_paths = nullptr;
     int rc = THETA_OK;
-    cudaError_t e = cudaMalloc(&d_list, sizeof(uint32_t) * list.size());
-    if (e == cudaSuccess) e = cudaMalloc(&d_prior, sizeof(double) * list.size());
+    cudaError_t e = theta::dmalloc(&d_list, sizeof(uint32_t) * list.size());
+    if (e == cudaSuccess) e = theta::dmalloc(&d_prior, sizeof(double) * list.size());
     if (e == cudaSuccess) e = cudaMemcpy(d_list, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_prior, prior.data(), sizeof(double) * list.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) rc = cuda_fail(e, "n3 emit setup", __FILE__, __LINE__);
     size_t cap = 1 << 14;
     for (int attempt = 0; rc == THETA_OK && attempt < 8; ++attempt) {
-        cudaFree(d_emit); cudaFree(d_paths); d_emit = nullptr; d_paths = nullptr;
-        e = cudaMalloc(&d_emit, sizeof(theta_cand) * cap);
-        if (e == cudaSuccess) e = cudaMalloc(&d_paths, cap * (size_t)m);
+        theta::dfree(d_emit); theta::dfree(d_paths); d_emit = nullptr; d_paths = nullptr;
+        e = theta::dmalloc(&d_emit, sizeof(theta_cand) * cap);
+        if (e == cudaSuccess) e = theta::dmalloc(&d_paths, cap * (size_t)m);
         if (e == cudaSuccess) e = cudaMemsetAsync(s->d_ctr, 0, sizeof(unsigned long long) * 8, st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "n3 emit buffers", __FILE__, __LINE__); break; }
         Search3Params sp{};
@@ -630,7 +630,7 @@ static int run_emit(theta_plan* pl, const std::vector<uint32_t>& list, const std
         }
         break;
     }
-    cudaFree(d_list); cudaFree(d_prior); cudaFree(d_emit); cudaFree(d_paths);
+    theta::dfree(d_list); theta::dfree(d_prior); theta::dfree(d_emit); theta::dfree(d_paths);
     if (rc) return rc;
     // sort by enumeration order, carrying the paths along
     std::vector<uint32_t> idx(recs->size());
@@ -710,12 +710,12 @@ extern "C" int theta_solve_rows_n3(theta_plan* pl, const uint8_t* paths_host, in
     if (count <= 0) return THETA_OK;
     const int m = pl->m;
     uint8_t* d_p = nullptr; double *d_mu = nullptr, *d_mh = nullptr, *d_nll = nullptr, *d_vals = nullptr; int32_t* d_st = nullptr;
-    cudaError_t e = cudaMalloc(&d_p, (size_t)count * m);
-    if (e == cudaSuccess) e = cudaMalloc(&d_mu, sizeof(double) * 3 * count);
-    if (e == cudaSuccess) e = cudaMalloc(&d_mh, sizeof(double) * 3 * count);
-    if (e == cudaSuccess) e = cudaMalloc(&d_nll, sizeof(double) * count);
-    if (e == cudaSuccess) e = cudaMalloc(&d_st, sizeof(int32_t) * count);
-    if (e == cudaSuccess && vals_host) e = cudaMalloc(&d_vals, sizeof(double) * (size_t)count * m);
+    cudaError_t e = theta::dmalloc(&d_p, (size_t)count * m);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_mu, sizeof(double) * 3 * count);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_mh, sizeof(double) * 3 * count);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_nll, sizeof(double) * count);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_st, sizeof(int32_t) * count);
+    if (e == cudaSuccess && vals_host) e = theta::dmalloc(&d_vals, sizeof(double) * (size_t)count * m);
     if (e == cudaSuccess) e = cudaMemcpy(d_p, paths_host, (size_t)count * m, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && vals_host) e = cudaMemset(d_vals, 0, sizeof(double) * (size_t)count * m);
     if (e == cudaSuccess) {
@@ -731,6 +731,6 @@ extern "C" int theta_solve_rows_n3(theta_plan* pl, const uint8_t* paths_host, in
     if (e == cudaSuccess) e = cudaMemcpy(status_host, d_st, sizeof(int32_t) * count, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && vals_host) e = cudaMemcpy(vals_host, d_vals, sizeof(double) * (size_t)count * m, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = cuda_fail(e, "solve_rows_n3", __FILE__, __LINE__);
-    cudaFree(d_p); cudaFree(d_mu); cudaFree(d_mh); cudaFree(d_nll); cudaFree(d_st); cudaFree(d_vals);
+    theta::dfree(d_p); theta::dfree(d_mu); theta::dfree(d_mh); theta::dfree(d_nll); theta::dfree(d_st); theta::dfree(d_vals);
     return rc;
 }

@@ -2,6 +2,9 @@
 // roofline probe, and the single-matrix masked NLL of CalcAllC.L2 / L3.
 #include <cstdarg>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "theta_core.cuh"
@@ -22,6 +25,64 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     cudaGetLastError();
     return THETA_ERR_CUDA;
 }
+
+// ---------------------------------------------------------------- caching allocators
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::map<std::pair<int, size_t>, std::vector<void*>> free_;      // (device, bucket) -> blocks
+    std::unordered_map<void*, std::pair<int, size_t>> live_;         // block -> (device, bucket)
+    bool pinned;
+    explicit BlockCache(bool pinned_) : pinned(pinned_) {}
+    static size_t bucket(size_t bytes) {
+        if (bytes < 512) bytes = 512;
+        if (bytes > (size_t)32 << 20) return (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);  // 2 MiB granules
+        size_t b = 512;
+        while (b < bytes) b <<= 1;
+        return b;
+    }
+    cudaError_t get(void** p, size_t bytes) {
+        *p = nullptr;
+        int dev = 0;
+        if (!pinned) { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
+        const size_t b = bucket(bytes);
+        std::lock_guard<std::mutex> lk(mu);
+        auto& fl = free_[{dev, b}];
+        if (!fl.empty()) { *p = fl.back(); fl.pop_back(); }
+        else {
+            cudaError_t e = pinned ? cudaHostAlloc(p, b, cudaHostAllocDefault) : cudaMalloc(p, b);
+            if (e != cudaSuccess) {  // give cached blocks back and retry once
+                for (auto& kv : free_) { for (void* q : kv.second) { if (pinned) cudaFreeHost(q); else cudaFree(q); } kv.second.clear(); }
+                cudaGetLastError();
+                e = pinned ? cudaHostAlloc(p, b, cudaHostAllocDefault) : cudaMalloc(p, b);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        live_[*p] = {dev, b};
+        return cudaSuccess;
+    }
+    void put(void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = live_.find(p);
+        if (it == live_.end()) { if (pinned) cudaFreeHost(p); else cudaFree(p); return; }
+        free_[it->second].push_back(p);
+        live_.erase(it);
+    }
+    void release() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& kv : free_) { for (void* q : kv.second) { if (pinned) cudaFreeHost(q); else cudaFree(q); } kv.second.clear(); }
+    }
+};
+BlockCache& dcache() { static BlockCache* c = new BlockCache(false); return *c; }
+BlockCache& hcache() { static BlockCache* c = new BlockCache(true); return *c; }
+}  // namespace
+
+cudaError_t dmalloc_bytes(void** p, size_t bytes) { return dcache().get(p, bytes); }
+void dfree(void* p) { dcache().put(p); }
+cudaError_t hmalloc_bytes(void** p, size_t bytes) { return hcache().get(p, bytes); }
+void hfree(void* p) { hcache().put(p); }
+void cache_release() { dcache().release(); hcache().release(); }
 
 // Dependent-free DFMA streams: 8 accumulators per thread, enough warps to saturate the fp64 pipe.
 __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
@@ -102,7 +163,7 @@ extern "C" int theta_init(int device) {
     return THETA_OK;
 }
 
-extern "C" void theta_shutdown(void) { cudaDeviceSynchronize(); }
+extern "C" void theta_shutdown(void) { cudaDeviceSynchronize(); theta::cache_release(); }
 
 extern "C" int theta_fp64_peak(double* gflops, void* stream) {
     if (!gflops) { set_error("null argument"); return THETA_ERR_INVALID; }
@@ -112,7 +173,7 @@ extern "C" int theta_fp64_peak(double* gflops, void* stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int block = 256, grid = sms * 8, iters = 1 << 14;
     double* d = nullptr;
-    THETA_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)grid * block));
+    THETA_CUDA(theta::dmalloc(&d, sizeof(double) * (size_t)grid * block));
     cudaEvent_t e0, e1;
     THETA_CUDA(cudaEventCreate(&e0));
     THETA_CUDA(cudaEventCreate(&e1));
@@ -129,7 +190,7 @@ extern "C" int theta_fp64_peak(double* gflops, void* stream) {
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(d);
+    theta::dfree(d);
     THETA_CUDA(cudaGetLastError());
     *gflops = best;
     return THETA_OK;
@@ -144,12 +205,12 @@ extern "C" int theta_nll(int32_t n, int32_t m, const double* mu, const double* C
     std::vector<double> rd(m);
     for (int i = 0; i < m; ++i) rd[i] = (double)r[i];
     int rc = THETA_OK;
-    cudaError_t e = cudaMalloc(&d_mu, sizeof(double) * 3);
-    if (e == cudaSuccess) e = cudaMalloc(&d_C, sizeof(double) * (size_t)m * n);
-    if (e == cudaSuccess) e = cudaMalloc(&d_r, sizeof(double) * m);
-    if (e == cudaSuccess) e = cudaMalloc(&d_nll, sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_vals, sizeof(double) * m);
-    if (e == cudaSuccess) e = cudaMalloc(&d_valid, m);
+    cudaError_t e = theta::dmalloc(&d_mu, sizeof(double) * 3);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_C, sizeof(double) * (size_t)m * n);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_r, sizeof(double) * m);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_nll, sizeof(double));
+    if (e == cudaSuccess) e = theta::dmalloc(&d_vals, sizeof(double) * m);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_valid, m);
     if (e == cudaSuccess) e = cudaMemcpy(d_mu, mu, sizeof(double) * n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_C, Cw, sizeof(double) * (size_t)m * n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_r, rd.data(), sizeof(double) * m, cudaMemcpyHostToDevice);
@@ -163,6 +224,6 @@ extern "C" int theta_nll(int32_t n, int32_t m, const double* mu, const double* C
     if (e == cudaSuccess) e = cudaMemcpy(vals, d_vals, sizeof(double) * m, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(valid, d_valid, m, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = cuda_fail(e, "theta_nll", __FILE__, __LINE__);
-    cudaFree(d_mu); cudaFree(d_C); cudaFree(d_r); cudaFree(d_nll); cudaFree(d_vals); cudaFree(d_valid);
+    theta::dfree(d_mu); theta::dfree(d_C); theta::dfree(d_r); theta::dfree(d_nll); theta::dfree(d_vals); theta::dfree(d_valid);
     return rc;
 }

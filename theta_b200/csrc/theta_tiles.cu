@@ -23,6 +23,7 @@
 // a handful of integer instructions; arbitrary rows are handled by the same code at a
 // cost proportional to their number of runs.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "theta_n2.cuh"
@@ -250,38 +251,7 @@ __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
             const unsigned char* rp = S.ring + ((size_t)slot * kRows + tid) * p.pitch;
             uint16_t* myruns = S.runs + tid;
             const int nr = collect_runs(rp, words, kc.m, myruns);
-            if (!SOLVE) {
-                const double mu = p.mu_in[row];
-                const double mu1 = 1.0 - mu;
-                const double tm = kc.tau * mu;
-                double acc = 0.0, s1 = 0.0;
-                if (nr >= 0) {
-                    // every lane walks its own (short) run list in lockstep: one log per run
-                    double pr_s = 0.0, prn_s = 0.0;
-                    for (int j = 0; j < nr; ++j) {
-                        const uint32_t code = myruns[j * kRows];
-                        const int e = (int)(code & 1023u);
-                        const double v = (double)(code >> 10);
-                        const double2 pp = S.PRP[e];
-                        const double pr_e = pp.x, prn_e = pp.y;
-                        const double wgt = pr_e - pr_s;
-                        s1 = fma(v, prn_e - prn_s, s1);
-                        if (wgt != 0.0) acc = fma(wgt, fast_log(fma(v, mu1, tm), S.LT), acc);
-                        pr_s = pr_e;
-                        prn_s = prn_e;
-                    }
-                } else {
-                    scan_runs(rp, words, [&](uint32_t v, int s, int e) {
-                        const double wgt = S.PRP[e].x - S.PRP[s].x;
-                        s1 = fma((double)v, S.PRP[e].y - S.PRP[s].y, s1);
-                        if (wgt != 0.0) acc = fma(wgt, log(fma((double)v, mu1, tm)), acc);
-                    });
-                }
-                const double gbar = (mu * kc.S0 + mu1 * s1) / kc.A;
-                double nll = kc.K0 - (acc - kc.Rtot * fast_log(gbar, S.LT));
-                if (kc.any_zero_rN) nll = INFINITY;
-                p.nll_out[row] = nll;
-            } else {
+            {
                 double* h = S.hist + tid;  // hist[v * kRows + tid]
 #pragma unroll
                 for (int v = 0; v <= KT; ++v) h[v * kRows] = 0.0;
@@ -317,6 +287,215 @@ __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming NLL kernel (Optimizer.L2, python/Optimizer.py:187-196, at a given mu per candidate).
+//
+// Warp-granular pipeline: every warp owns a ring of STAGES sub-tiles (32 rows x pitch bytes,
+// contiguous in HBM) filled by TMA bulk copies on the warp's own mbarriers -- no block-level
+// synchronisation after the tables are staged.  Lane l evaluates row l of the sub-tile in two
+// phases so that the warp stays converged:
+//   phase 1 (branch-free, 6 instructions per 8-byte word): mark the words that are not a
+//            repetition of the last byte seen (a word inside a run never is marked);
+//   phase 2: for each marked word, walk its change points; a run [s, e) of copy number v adds
+//            (PR[e]-PR[s]) * log(tau mu + v (1-mu)) and v * (PRN[e]-PRN[s]) from the exact prefix
+//            sums in shared memory.  Positions past m carry zero weight (the prefix tables are
+//            flat there), so the zero padding needs no special case.
+// Any byte values and any number of runs are handled; cost is proportional to the number of runs.
+template <int WARPS, int STAGES>
+struct NllCfg {
+    static constexpr int kThreads = WARPS * 32;
+    __host__ __device__ static size_t smem_bytes(int64_t pitch) {
+        size_t o = sizeof(double2) * (size_t)(pitch + 1);
+        o = (o + 127) & ~(size_t)127;
+        o += sizeof(double2) * THETA_LOGTAB_SIZE;
+        o += (size_t)WARPS * STAGES * 32 * (size_t)pitch;
+        return o + 32;  // slack: phase 1 of the last row may read up to 24 bytes past its end
+    }
+};
+
+__device__ __forceinline__ void issue_subtile(const TileParams& p, unsigned char* dst, uint64_t* bar, int64_t t) {
+    const int64_t row0 = t * 32;
+    const int64_t rows = min((int64_t)32, p.count - row0);
+    const uint32_t bytes = (uint32_t)(rows * p.pitch);
+    const uint32_t body = bytes & ~15u;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.cols) + row0 * p.pitch;
+    if (body < bytes) *reinterpret_cast<uint64_t*>(dst + body) = *reinterpret_cast<const uint64_t*>(src + body);
+    if (body) {
+        mbar_expect_tx(bar, body);
+        tma_load_1d(dst, src, body, bar);
+    } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    }
+}
+
+__device__ __forceinline__ double nll_row(const unsigned char* rp, int words, const double2* __restrict__ PRP,
+                                          const double2* __restrict__ LT, double mu, const N2Const& kc) {
+    const uint2* rw = reinterpret_cast<const uint2*>(rp);
+    const double mu1 = 1.0 - mu;
+    const double tm = kc.tau * mu;
+    double acc = 0.0, s1 = 0.0, pr_s = 0.0, prn_s = 0.0;
+    uint32_t cur = rw[0].x & 0xffu;     // copy number of the open run
+    uint32_t pat = cur * 0x01010101u;   // phase 1: last byte seen, replicated
+    auto close_run = [&](uint32_t v, int e) {
+        const double2 pp = PRP[e];
+        const double wgt = pp.x - pr_s;
+        const double dv = (double)v;
+        s1 = fma(dv, pp.y - prn_s, s1);
+        if (wgt != 0.0) acc = fma(wgt, fast_log(fma(dv, mu1, tm), LT), acc);
+        pr_s = pp.x;
+        prn_s = pp.y;
+    };
+    for (int w0 = 0; w0 < words; w0 += 32) {
+        const int nw = min(32, words - w0);
+        // blocks of four words with compile-time bit positions; a block may run up to three words past the
+        // row (into the next row / the slack behind the ring): those bits are masked off below
+        uint32_t mask = 0;
+        const int nblk = (nw + 3) >> 2;
+        for (int jb = 0; jb < nblk; ++jb) {
+            uint32_t m4 = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint2 w = rw[w0 + jb * 4 + u];
+                uint32_t diff;  // (w.x ^ pat) | (w.y ^ pat) as one LOP3 (the compiler otherwise emits two compares)
+                asm("lop3.b32 %0, %1, %2, %3, 0x7e;" : "=r"(diff) : "r"(w.x), "r"(w.y), "r"(pat));
+                if (diff != 0u) m4 |= 1u << u;
+                pat = __byte_perm(w.y, 0u, 0x3333u);
+            }
+            mask |= m4 << (jb * 4);
+        }
+        if (nw < 32) mask &= (1u << nw) - 1u;
+        unsigned long long d = 0ull;
+        uint2 w = make_uint2(0u, 0u);
+        int base = 0;
+        for (;;) {
+            if (d == 0ull) {
+                if (mask == 0u) break;
+                const int wi = w0 + __ffs((int)mask) - 1;
+                mask &= mask - 1u;
+                w = rw[wi];
+                base = wi * 8;
+                const uint32_t dlo = w.x ^ ((w.x << 8) | cur);
+                const uint32_t dhi = w.y ^ __funnelshift_l(w.x, w.y, 8);
+                d = ((unsigned long long)dhi << 32) | dlo;  // non-zero: the word is not a repetition of `cur`
+            }
+            const int b = (__ffsll((long long)d) - 1) >> 3;  // first byte that differs from its predecessor
+            close_run(cur, base + b);
+            cur = __byte_perm(w.x, w.y, (uint32_t)b) & 0xffu;
+            d &= ~(0xffull << (8 * b));
+        }
+    }
+    close_run(cur, kc.m);
+    const double gbar = (mu * kc.S0 + mu1 * s1) / kc.A;
+    double nll = kc.K0 - (acc - kc.Rtot * fast_log(gbar, LT));
+    if (kc.any_zero_rN) nll = INFINITY;
+    return nll;
+}
+
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32) nll_tiles_kernel(const TileParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[WARPS * STAGES];
+    double2* PRP = reinterpret_cast<double2*>(smem);
+    size_t o = sizeof(double2) * (size_t)(p.pitch + 1);
+    o = (o + 127) & ~(size_t)127;
+    double2* LT = reinterpret_cast<double2*>(smem + o);
+    o += sizeof(double2) * THETA_LOGTAB_SIZE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t slot_bytes = (size_t)32 * p.pitch;
+    unsigned char* ring = smem + o + (size_t)warp * STAGES * slot_bytes;
+    uint64_t* bar = bars + warp * STAGES;
+    for (int i = tid; i <= p.pitch; i += WARPS * 32) PRP[i] = make_double2(p.PR[i], p.PRN[i]);
+    for (int i = tid; i < THETA_LOGTAB_SIZE; i += WARPS * 32) LT[i] = p.logtab[i];
+    if (tid == 0) {
+        for (int s = 0; s < WARPS * STAGES; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int words = (int)(p.pitch >> 3);
+    const int64_t n_sub = (p.count + 31) >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t GW = (int64_t)gridDim.x * WARPS;
+    const N2Const kc = p.kc;
+    if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < (STAGES > 1 ? STAGES - 1 : 1); ++s) {
+            const int64_t t = gw + (int64_t)s * GW;
+            if (t < n_sub) issue_subtile(p, ring + (size_t)s * slot_bytes, &bar[s], t);
+        }
+    }
+    int it = 0;
+    for (int64_t t = gw; t < n_sub; t += GW, ++it) {
+        const int slot = it % STAGES;
+        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+        const int64_t row = t * 32 + lane;
+        const bool live = row < p.count;
+        const double mu = live ? __ldg(p.mu_in + row) : 0.5;
+        if (STAGES > 1) {
+            __syncwarp();  // every lane is done with the slot about to be refilled
+            if (lane == 0) {
+                const int64_t tn = t + (int64_t)(STAGES - 1) * GW;
+                if (tn < n_sub) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue_subtile(p, ring + (size_t)((it + STAGES - 1) % STAGES) * slot_bytes, &bar[(it + STAGES - 1) % STAGES], tn);
+                }
+            }
+        }
+        mbar_wait(&bar[slot], parity);
+        __syncwarp();  // a hand-copied 8-byte tail (last sub-tile only) becomes visible to every lane
+        double nll = 0.0;
+        if (live) nll = nll_row(ring + (size_t)slot * slot_bytes + (size_t)lane * p.pitch, words, PRP, LT, mu, kc);
+        if (STAGES == 1) {
+            __syncwarp();
+            if (lane == 0) {
+                const int64_t tn = t + GW;
+                if (tn < n_sub) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue_subtile(p, ring, &bar[0], tn);
+                }
+            }
+        }
+        if (live) p.nll_out[row] = nll;
+    }
+}
+
+static int g_nll_variant = -1;  // THETA_NLL_VARIANT: 0 = 8 warps x 2 stages, 1 = 4 x 2, 2 = 8 x 1, 3 = 4 x 1, 4 = 16 x 1
+
+template <int WARPS, int STAGES>
+static int launch_nll(const theta_plan* pl, const TileParams& tp, cudaStream_t st) {
+    using Cfg = NllCfg<WARPS, STAGES>;
+    const size_t smem = Cfg::smem_bytes(tp.pitch);
+    auto kern = nll_tiles_kernel<WARPS, STAGES>;
+    if (smem > 227 * 1024) { set_error("sub-tiles of 32 rows x %lld bytes do not fit shared memory", (long long)tp.pitch); return THETA_ERR_UNSUPPORTED; }
+    THETA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 1;
+    THETA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, Cfg::kThreads, smem));
+    if (bps < 1) bps = 1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    const int64_t n_sub = (tp.count + 31) / 32;
+    const int grid = (int)std::min<int64_t>((n_sub + WARPS - 1) / WARPS, (int64_t)sms * bps);
+    kern<<<grid, Cfg::kThreads, smem, st>>>(tp);
+    THETA_CUDA(cudaGetLastError());
+    return THETA_OK;
+}
+
+static int launch_nll_auto(const theta_plan* pl, const TileParams& tp, cudaStream_t st) {
+    if (g_nll_variant < 0) {
+        const char* e = getenv("THETA_NLL_VARIANT");
+        g_nll_variant = e ? atoi(e) : 0;
+    }
+    int v = g_nll_variant;
+    // large pitches: fall back to the leanest shared-memory footprint that fits
+    if (NllCfg<8, 2>::smem_bytes(tp.pitch) > 227 * 1024 && (v == 0 || v == 4)) v = 3;
+    switch (v) {
+        case 1: return launch_nll<4, 2>(pl, tp, st);
+        case 2: return launch_nll<8, 1>(pl, tp, st);
+        case 3: return launch_nll<4, 1>(pl, tp, st);
+        case 4: return launch_nll<16, 1>(pl, tp, st);
+        default: return launch_nll<8, 2>(pl, tp, st);
     }
 }
 
@@ -365,7 +544,7 @@ extern "C" int theta_nll_tiles_n2_dev(theta_plan* pl, const int8_t* cols_dev, in
     TileParams tp{};
     tp.cols = cols_dev; tp.pitch = pitch; tp.count = count; tp.PR = pl->d_PR; tp.PRN = pl->d_PRN; tp.ZP = pl->d_ZP;
     tp.kc = pl->kc; tp.mu_in = mu_dev; tp.nll_out = nll_dev; tp.logtab = pl->d_logtab;
-    return launch_tiles<false, 1>(pl, tp, st);  // asynchronous on `stream`
+    return launch_nll_auto(pl, tp, st);  // asynchronous on `stream`
 }
 
 extern "C" int theta_solve_tiles_n2_dev(theta_plan* pl, const int8_t* cols_dev, int64_t pitch, int64_t count,
@@ -395,15 +574,15 @@ extern "C" int theta_nll_tiles_n2(theta_plan* pl, const int8_t* cols_host, int64
     if (count <= 0) return THETA_OK;
     int8_t* d_c = nullptr; double *d_mu = nullptr, *d_nll = nullptr;
     int rc = THETA_OK;
-    cudaError_t e = cudaMalloc(&d_c, (size_t)count * pitch);
-    if (e == cudaSuccess) e = cudaMalloc(&d_mu, sizeof(double) * count);
-    if (e == cudaSuccess) e = cudaMalloc(&d_nll, sizeof(double) * count);
+    cudaError_t e = theta::dmalloc(&d_c, (size_t)count * pitch);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_mu, sizeof(double) * count);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_nll, sizeof(double) * count);
     if (e == cudaSuccess) e = cudaMemcpy(d_c, cols_host, (size_t)count * pitch, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_mu, mu_host, sizeof(double) * count, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) rc = cuda_fail(e, "nll_tiles H2D", __FILE__, __LINE__);
     if (rc == THETA_OK) rc = theta_nll_tiles_n2_dev(pl, d_c, pitch, count, d_mu, d_nll, nullptr);
     if (rc == THETA_OK) { e = cudaMemcpy(nll_host, d_nll, sizeof(double) * count, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = cuda_fail(e, "nll_tiles D2H", __FILE__, __LINE__); }
-    cudaFree(d_c); cudaFree(d_mu); cudaFree(d_nll);
+    theta::dfree(d_c); theta::dfree(d_mu); theta::dfree(d_nll);
     return rc;
 }
 
@@ -413,10 +592,10 @@ extern "C" int theta_solve_tiles_n2(theta_plan* pl, const int8_t* cols_host, int
     if (count <= 0) return THETA_OK;
     int8_t* d_c = nullptr; double *d_mu = nullptr, *d_nll = nullptr; int32_t* d_st = nullptr;
     int rc = THETA_OK;
-    cudaError_t e = cudaMalloc(&d_c, (size_t)count * pitch);
-    if (e == cudaSuccess) e = cudaMalloc(&d_mu, sizeof(double) * count);
-    if (e == cudaSuccess) e = cudaMalloc(&d_nll, sizeof(double) * count);
-    if (e == cudaSuccess) e = cudaMalloc(&d_st, sizeof(int32_t) * count);
+    cudaError_t e = theta::dmalloc(&d_c, (size_t)count * pitch);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_mu, sizeof(double) * count);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_nll, sizeof(double) * count);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_st, sizeof(int32_t) * count);
     if (e == cudaSuccess) e = cudaMemcpy(d_c, cols_host, (size_t)count * pitch, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) rc = cuda_fail(e, "solve_tiles H2D", __FILE__, __LINE__);
     if (rc == THETA_OK) rc = theta_solve_tiles_n2_dev(pl, d_c, pitch, count, d_mu, d_nll, d_st, nullptr);
@@ -426,6 +605,6 @@ extern "C" int theta_solve_tiles_n2(theta_plan* pl, const int8_t* cols_host, int
         if (e == cudaSuccess) e = cudaMemcpy(status_host, d_st, sizeof(int32_t) * count, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "solve_tiles D2H", __FILE__, __LINE__);
     }
-    cudaFree(d_c); cudaFree(d_mu); cudaFree(d_nll); cudaFree(d_st);
+    theta::dfree(d_c); theta::dfree(d_mu); theta::dfree(d_nll); theta::dfree(d_st);
     return rc;
 }
