@@ -4,10 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|m150k7|cfg3win]
 
 One "step" = one complete search (enumerate every admissible C, solve mu, NLL, keep the
-best with the reference's tie fold) of the workload's candidate space.  Default workload is
-BASELINE.json configs[1]: synthetic m=150, n=2, k=5 (seed 1) -> 25,251,200 candidates.
-For N>1 (torchrun, one rank per GPU) the rank range is sharded contiguously (strong scaling on
-the same space); the only communication is the min exchange + the record gather.
+best with the reference's tie fold) of the workload's candidate space.  At N=1 the workload is
+BASELINE.json configs[1]: synthetic m=150, n=2, k=5 (seed 1) -> 25,251,156 candidates.
+For N>1 (torchrun, one rank per GPU) the scaling is WEAK: every GPU keeps the same 25,251,156
+candidates per step; the job is the first N x 25,251,156 ranks of the same data's search with the
+upper bounds widened by two copies (same r, rN, m, K=5 -> same cost per candidate; 4.196e8 candidates),
+cut into contiguous rank ranges.  The only communication is the min exchange + the record gather.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   roofline      the streaming NLL kernel (theta_nll_tiles_n2) on tiles larger than L2, HBM-bound
@@ -26,8 +28,13 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+PER_GPU = 25251156  # candidates of BASELINE configs[1]; the per-GPU unit count of the weak-scaling runs
+
 WORKLOADS = {
     "cfg2": dict(m=150, k=5, seed=1, desc="synthetic m=150 n=2 k=5 seed=1 (BASELINE configs[1]), full space"),
+    "cfg2w": dict(m=150, k=5, seed=1, widen=2,
+                  desc="synthetic m=150 n=2 k=5 seed=1 (BASELINE configs[1] data), upper bounds +2 copies (4.196e8 "
+                       "candidates), first n_gpus x 25,251,156 ranks"),
     "m150k7": dict(m=150, k=7, seed=1, desc="synthetic m=150 n=2 k=7 seed=1 (>=100x target shape), full space"),
     "cfg3win": dict(m=300, k=7, seed=1, window=1 << 33,
                     desc="synthetic m=300 n=2 k=7 seed=1 (BASELINE configs[2]), first 2^33 ranks"),
@@ -39,6 +46,8 @@ def problem(name):
     import theta_oracle as O  # input generator only; not on the measured path
     w = WORKLOADS[name]
     P = O.synthetic_problem_n2(w["m"], w["k"], seed=w["seed"])
+    if w.get("widen"):
+        P["upper"] = [min(w["k"], u + w["widen"]) for u in P["upper"]]
     P["window"] = w.get("window")
     P["desc"] = w["desc"]
     return P
@@ -152,6 +161,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.workload == "cfg2":
+        args.workload = "cfg2w"  # same config as our arm at this N
     per_core = 40000
     vals = []
     for _ in range(args.warmup and 1 or 0):
@@ -167,7 +178,7 @@ def run_reference(args):
     P = problem(args.workload)
     line = {"impl": "reference", "metric": "C-candidates/sec", "value": v, "unit": "candidates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": P["desc"], "n": 2, "m": P["m"], "k": P["k"]},
             "cpu_baseline": res,
             "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -206,9 +217,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.current_stream().cuda_stream
 
+    if world > 1 and args.workload == "cfg2":
+        args.workload = "cfg2w"  # weak scaling: same data and K, wider bounds, PER_GPU ranks per GPU
     P = problem(args.workload)
     plan = _lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"])
     total = plan.count()
+    if args.workload == "cfg2w":
+        total = min(total, PER_GPU * world)
     if P["window"]:
         total = min(total, P["window"])
     begin, end = search.shard_range(total, rank, world)
@@ -251,28 +266,30 @@ def main():
     st = plan.stats()
     value = total * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: the public call (host buffers in, Python `best` list out), every step from scratch
+    # ---- e2e: the public call (host lists in, the reference-shaped Python `best` list out), every step from
+    # scratch: plan creation + H2D of the tables, both passes, D2H of stripe minima and records, fold replay,
+    # `vals` of the winners.
     def e2e_step():
         return search.do_optimization_single(2, P["m"], P["k"], 2, list(P["lower"]), list(P["upper"]), P["r"], P["rN"],
-                                             1.0, P["sorted_index"], True, False)
-    e2e = None
-    if not P["window"]:
-        for _ in range(2):
-            best = e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            best = e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-        h2d = plan.m * (8 + 8 + 4 + 4) + 2 * 8 * (plan.pitch + 1) * 2
-        d2h = 8 * st["n_stripes"] + 48 * max(1, len(recs)) + (48 + 8 * plan.m + plan.pitch) * max(1, len(best))
-        e2e = {"value": total * args.steps / float(tdt.item()), "unit": "candidates/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "best_nll": float(best[0][2]), "best_mu0": float(best[0][1][0]), "n_best": len(best)}
+                                             1.0, P["sorted_index"], True, False, rank_limit=total)
+    for _ in range(max(3, args.warmup)):
+        best = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        best = e2e_step()
+    barrier()
+    dt = time.perf_counter() - t0
+    tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+    h2d = plan.table_bytes() + plan.m * (8 + 8) + 2 * 8 * (plan.pitch + 1) + 4 * (plan.pitch + 1) + 16 * 256 \
+        + 12 * int(st["n_rescanned"]) + 8 * max(1, len(best))
+    d2h = 8 * st["n_stripes"] + 64 * 2 + 48 * max(1, len(recs)) + (48 + 8 * plan.m + plan.pitch) * max(1, len(best))
+    e2e = {"value": total * args.steps / float(tdt.item()), "unit": "candidates/s",
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(tdt.item()) / args.steps,
+           "api": "theta_b200.search.do_optimization_single (RunTHetA.py:173 signature), host lists in / best list out",
+           "best_nll": float(best[0][2]), "best_mu0": float(best[0][1][0]), "n_best": len(best)}
 
     clocks = sampler.stop() if rank == 0 else None
 
@@ -314,8 +331,16 @@ def main():
             pass
         bytes_alg = cnt * (plan.m + 8 + 8)
         ach = bytes_alg / (t_nll * 1e-3) / 1e9
-        roof = {"kernel": "tiles_n2_kernel<false> (theta_nll_tiles_n2: Optimizer.L2 over int8 C tiles)",
-                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None  # dram__bytes_read+write per launch from the committed ncu --set full capture, scaled to this launch
+        try:
+            with open(os.path.join(ROOT, "profiles", "nll_traffic.json")) as f:
+                tj = json.load(f)
+            if tj["m"] == plan.m:
+                traffic = tj["dram_bytes_per_candidate"] * cnt
+        except Exception:
+            pass
+        roof = {"kernel": "nll_tiles_kernel (theta_nll_tiles_n2_dev: Optimizer.L2 over int8 C tiles, TMA-staged)",
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_candidate": plan.m + 16, "candidates_per_launch": cnt,
                 "ms_per_launch": t_nll, "tile_bytes": cnt * pitch, "check_max_rel_err_vs_solve": maxrel}
         del tiles, mu, nll, stt
@@ -329,7 +354,7 @@ def main():
                      "newton_iters_mean": st["newton_iters"], "stripes": int(st["n_stripes"]),
                      "rescanned_stripes": int(st["n_rescanned"])}
 
-    if not args.no_extra and args.workload == "cfg2":
+    if not args.no_extra and args.workload == "cfg2" and world == 1:
         # (a) the >=100x target shape of BASELINE.json (m=150, k=7, 6.07e8 candidates), sharded over all ranks
         P7 = problem("m150k7")
         plan7 = _lib.Plan(2, P7["r"], P7["rN"], P7["lower"], P7["upper"])
@@ -367,16 +392,17 @@ def main():
         plan3.close()
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu and world == 1:
         cpu = cpu_reference_rate(args.workload, 40000)
 
     if rank == 0:
         line = {"metric": "C-candidates/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": P["desc"], "n": 2, "m": P["m"], "k": P["k"], "candidates": int(total),
-                           "sharding": "contiguous rank ranges, %d per GPU" % ((total + world - 1) // world),
+                           "sharding": "contiguous rank ranges, %d per GPU; one all-reduce(min) + record gather per step"
+                                       % ((total + world - 1) // world),
                            "l2_policy": "search kernel streams nothing from HBM (tables in shared memory); the "
                                         "roofline kernel uses tiles of %d MiB > L2" % (roof["tile_bytes"] >> 20 if roof else 0)},
                 "e2e": e2e, "gpu_launches": launches[0], "clocks": clocks, "roofline": roof,

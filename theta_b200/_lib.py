@@ -167,6 +167,13 @@ class Plan(object):
     def handle(self):
         return self._h
 
+    def table_bytes(self):
+        """Size of the n=2 table blob copied to the device by theta_plan_create (TableLayout, theta_n2.cuh)."""
+        K = max(1, int(self._up.max()))
+        KT = next(o for o in (2, 3, 4, 5, 6, 7, 8, 10, 12, 15) if K <= o)
+        o = 8 * (self.m + 1) * 2 + 8 * KT * (self.m + 2) + 4 * (self.m + 1) + 4 * KT * 2
+        return (o + 15) & ~15
+
     def count(self):
         c = C.c_uint64()
         check(load().theta_plan_count(self._h, C.byref(c)))

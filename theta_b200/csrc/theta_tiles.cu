@@ -331,8 +331,15 @@ __device__ __forceinline__ void issue_subtile(const TileParams& p, unsigned char
     }
 }
 
-__device__ __forceinline__ double nll_row(const unsigned char* rp, int words, const double2* __restrict__ PRP,
-                                          const double2* __restrict__ LT, double mu, const N2Const& kc) {
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// prp_s: shared-space address of the (PR, PRN) table (explicit ld.shared keeps the address arithmetic to one LEA)
+__device__ __forceinline__ double nll_row(const unsigned char* rp, int words, uint32_t prp_s,
+                                          const double2* __restrict__ LT, double mu, const N2Const& kc, double inv_A) {
     const uint2* rw = reinterpret_cast<const uint2*>(rp);
     const double mu1 = 1.0 - mu;
     const double tm = kc.tau * mu;
@@ -340,7 +347,7 @@ __device__ __forceinline__ double nll_row(const unsigned char* rp, int words, co
     uint32_t cur = rw[0].x & 0xffu;     // copy number of the open run
     uint32_t pat = cur * 0x01010101u;   // phase 1: last byte seen, replicated
     auto close_run = [&](uint32_t v, int e) {
-        const double2 pp = PRP[e];
+        const double2 pp = lds_f64x2(prp_s + (uint32_t)e * 16u);
         const double wgt = pp.x - pr_s;
         const double dv = (double)v;
         s1 = fma(dv, pp.y - prn_s, s1);
@@ -367,35 +374,37 @@ __device__ __forceinline__ double nll_row(const unsigned char* rp, int words, co
             mask |= m4 << (jb * 4);
         }
         if (nw < 32) mask &= (1u << nw) - 1u;
-        unsigned long long d = 0ull;
+        uint32_t dlo = 0u, dhi = 0u;  // bytes of the current word that differ from their predecessor
         uint2 w = make_uint2(0u, 0u);
         int base = 0;
         for (;;) {
-            if (d == 0ull) {
+            if ((dlo | dhi) == 0u) {
                 if (mask == 0u) break;
                 const int wi = w0 + __ffs((int)mask) - 1;
                 mask &= mask - 1u;
                 w = rw[wi];
                 base = wi * 8;
-                const uint32_t dlo = w.x ^ ((w.x << 8) | cur);
-                const uint32_t dhi = w.y ^ __funnelshift_l(w.x, w.y, 8);
-                d = ((unsigned long long)dhi << 32) | dlo;  // non-zero: the word is not a repetition of `cur`
+                dlo = w.x ^ ((w.x << 8) | cur);
+                dhi = w.y ^ __funnelshift_l(w.x, w.y, 8);  // non-zero pair: the word is not a repetition of `cur`
             }
-            const int b = (__ffsll((long long)d) - 1) >> 3;  // first byte that differs from its predecessor
-            close_run(cur, base + b);
-            cur = __byte_perm(w.x, w.y, (uint32_t)b) & 0xffu;
-            d &= ~(0xffull << (8 * b));
+            const bool in_lo = dlo != 0u;
+            const uint32_t x = in_lo ? dlo : dhi;
+            const int bit8 = (__ffs((int)x) - 1) & 24;  // first byte that differs from its predecessor
+            close_run(cur, base + (bit8 >> 3) + (in_lo ? 0 : 4));
+            cur = ((in_lo ? w.x : w.y) >> bit8) & 0xffu;
+            const uint32_t keep = ~(0xffu << bit8);
+            if (in_lo) dlo &= keep; else dhi &= keep;
         }
     }
     close_run(cur, kc.m);
-    const double gbar = (mu * kc.S0 + mu1 * s1) / kc.A;
+    const double gbar = (mu * kc.S0 + mu1 * s1) * inv_A;
     double nll = kc.K0 - (acc - kc.Rtot * fast_log(gbar, LT));
     if (kc.any_zero_rN) nll = INFINITY;
     return nll;
 }
 
-template <int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32) nll_tiles_kernel(const TileParams p) {
+template <int WARPS, int STAGES, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) nll_tiles_kernel(const TileParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[WARPS * STAGES];
     double2* PRP = reinterpret_cast<double2*>(smem);
@@ -419,6 +428,9 @@ __global__ void __launch_bounds__(WARPS * 32) nll_tiles_kernel(const TileParams 
     const int64_t gw = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t GW = (int64_t)gridDim.x * WARPS;
     const N2Const kc = p.kc;
+    const double inv_A = 1.0 / kc.A;
+    uint32_t prp_s = smem_u32(PRP);
+    asm volatile("" : "+r"(prp_s));  // keep it in a register (the compiler otherwise re-derives it per run)
     if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int s = 0; s < (STAGES > 1 ? STAGES - 1 : 1); ++s) {
@@ -446,7 +458,7 @@ __global__ void __launch_bounds__(WARPS * 32) nll_tiles_kernel(const TileParams 
         mbar_wait(&bar[slot], parity);
         __syncwarp();  // a hand-copied 8-byte tail (last sub-tile only) becomes visible to every lane
         double nll = 0.0;
-        if (live) nll = nll_row(ring + (size_t)slot * slot_bytes + (size_t)lane * p.pitch, words, PRP, LT, mu, kc);
+        if (live) nll = nll_row(ring + (size_t)slot * slot_bytes + (size_t)lane * p.pitch, words, prp_s, LT, mu, kc, inv_A);
         if (STAGES == 1) {
             __syncwarp();
             if (lane == 0) {
@@ -461,13 +473,13 @@ __global__ void __launch_bounds__(WARPS * 32) nll_tiles_kernel(const TileParams 
     }
 }
 
-static int g_nll_variant = -1;  // THETA_NLL_VARIANT: 0 = 8 warps x 2 stages, 1 = 4 x 2, 2 = 8 x 1, 3 = 4 x 1, 4 = 16 x 1
+static int g_nll_variant = -1;  // THETA_NLL_VARIANT: 0 = 8 warps x 2 stages, 1 = 4 x 2, 2 = 8 x 1, 3 = 4 x 1, 4 = 16 x 1, 5/6 = 8 x 1 with a register cap
 
-template <int WARPS, int STAGES>
+template <int WARPS, int STAGES, int MINB>
 static int launch_nll(const theta_plan* pl, const TileParams& tp, cudaStream_t st) {
     using Cfg = NllCfg<WARPS, STAGES>;
     const size_t smem = Cfg::smem_bytes(tp.pitch);
-    auto kern = nll_tiles_kernel<WARPS, STAGES>;
+    auto kern = nll_tiles_kernel<WARPS, STAGES, MINB>;
     if (smem > 227 * 1024) { set_error("sub-tiles of 32 rows x %lld bytes do not fit shared memory", (long long)tp.pitch); return THETA_ERR_UNSUPPORTED; }
     THETA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = 1;
@@ -485,17 +497,19 @@ static int launch_nll(const theta_plan* pl, const TileParams& tp, cudaStream_t s
 static int launch_nll_auto(const theta_plan* pl, const TileParams& tp, cudaStream_t st) {
     if (g_nll_variant < 0) {
         const char* e = getenv("THETA_NLL_VARIANT");
-        g_nll_variant = e ? atoi(e) : 0;
+        g_nll_variant = e ? atoi(e) : 4;
     }
     int v = g_nll_variant;
     // large pitches: fall back to the leanest shared-memory footprint that fits
     if (NllCfg<8, 2>::smem_bytes(tp.pitch) > 227 * 1024 && (v == 0 || v == 4)) v = 3;
     switch (v) {
-        case 1: return launch_nll<4, 2>(pl, tp, st);
-        case 2: return launch_nll<8, 1>(pl, tp, st);
-        case 3: return launch_nll<4, 1>(pl, tp, st);
-        case 4: return launch_nll<16, 1>(pl, tp, st);
-        default: return launch_nll<8, 2>(pl, tp, st);
+        case 1: return launch_nll<4, 2, 5>(pl, tp, st);
+        case 2: return launch_nll<8, 1, 4>(pl, tp, st);
+        case 3: return launch_nll<4, 1, 8>(pl, tp, st);
+        case 4: return launch_nll<16, 1, 2>(pl, tp, st);
+        case 5: return launch_nll<8, 1, 5>(pl, tp, st);   // <= 48 registers: 40 warps per SM
+        case 6: return launch_nll<8, 1, 6>(pl, tp, st);   // <= 40 registers: 48 warps per SM
+        default: return launch_nll<8, 2, 2>(pl, tp, st);
     }
 }
 

@@ -143,10 +143,15 @@ class SearchResult(object):
         self.stats = {}
 
 
-def search_n2(plan, stream=None):
-    """Sharded two-pass search; every rank returns the same SearchResult."""
+def search_n2(plan, stream=None, rank_limit=None):
+    """Sharded two-pass search; every rank returns the same SearchResult.
+
+    rank_limit (optional, not in the reference): search only the first `rank_limit` candidates of the
+    enumeration order -- the rank-budget runs of SURVEY 8d for spaces too large to finish."""
     rank, world, dist = _dist_state()
     total = plan.count()
+    if rank_limit is not None:
+        total = min(total, int(rank_limit))
     begin, end = shard_range(total, rank, world)
     local_min = plan.pass1(begin, end, stream)
     stats = plan.stats()
@@ -206,7 +211,7 @@ _NO_PROFILES = ("Error: No valid Copy Number Profiles exist for these intervals 
 
 
 def do_optimization_single(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_normal, sorted_index, multi_event,
-                           get_values, prefix=None):
+                           get_values, prefix=None, rank_limit=None):
     """RunTHetA.do_optimization_single (python/RunTHetA.py:173-220) on the GPU.
 
     Same arguments and return value: a list of (C_new, mu, likelihood, vals) with
@@ -228,7 +233,7 @@ def do_optimization_single(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_
             lower_bounds[i] = int(lo[i])
             upper_bounds[i] = int(up[i])
         try:
-            res = search_n2(plan)
+            res = search_n2(plan, rank_limit=rank_limit)
         except _lib.EmptySpaceError:
             print(_NO_PROFILES)
             sys.exit(1)
