@@ -214,6 +214,8 @@ def main():
     torch.cuda.set_device(local)
     _lib.init(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -232,10 +234,9 @@ def main():
     launches = [0]
 
     def step():
-        lm = plan.pass1(begin, end, stream)
-        g, prior = search.exchange_minima(lm, D, rank, world)
-        recs = plan.pass2(g, prior, stream)
-        launches[0] += 1 + (1 if plan.stats()["n_rescanned"] else 0)
+        g, _lm = search.pass1_allreduce(plan, begin, end, D, world, stream)  # search kernel + min reduction [+ NCCL]
+        recs = plan.pass2(g, float("inf"), stream)
+        launches[0] += 2 + (1 if plan.stats()["n_rescanned"] else 0)
         return search.gather_records(recs, D, world), g
 
     def barrier():
@@ -362,9 +363,8 @@ def main():
         b7, e7 = search.shard_range(n7, rank, world)
 
         def step7():
-            lm = plan7.pass1(b7, e7, stream)
-            g_, pr_ = search.exchange_minima(lm, D, rank, world)
-            return search.gather_records(plan7.pass2(g_, pr_, stream), D, world), g_
+            g_, _ = search.pass1_allreduce(plan7, b7, e7, D, world, stream)
+            return search.gather_records(plan7.pass2(g_, float("inf"), stream), D, world), g_
         for _ in range(2):
             step7()
         barrier()

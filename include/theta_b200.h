@@ -124,6 +124,13 @@ int64_t theta_tile_pitch(int32_t m); /* row pitch used by the tile kernels (smal
 /* Pass 1: evaluate ranks [rank_begin, rank_end): enumerate on chip, solve mu, NLL, reduce per stripe.
  * Returns the minimum NLL of the range (+inf if no candidate solved). */
 int theta_search_n2_pass1(theta_plan* plan, uint64_t rank_begin, uint64_t rank_end, double* local_min, void* stream);
+/* Pass 1 split for multi-GPU runs (replaces the merge of the workers' results, RunTHetA.py:107-122,162-171):
+ * _begin enqueues the search on `stream` and, when local_min_dev is not NULL, also writes the shard minimum to
+ * that DEVICE double -- so the caller can enqueue ncclAllReduce(min) on it right behind, with no host round
+ * trip; _end waits for the stream and returns the shard minimum on the host. */
+int theta_search_n2_pass1_begin(theta_plan* plan, uint64_t rank_begin, uint64_t rank_end, double* local_min_dev,
+                                void* stream);
+int theta_search_n2_pass1_end(theta_plan* plan, double* local_min);
 /* Pass 2: given the global minimum (all shards) and the minimum over all ranks *before* this shard
  * (+inf for the first shard), re-evaluate only the stripes that can matter and emit, in rank order,
  * a superset of the candidates the reference's running-min fold (RunTHetA.py:198-206) can ever keep:

@@ -76,6 +76,8 @@ SYMBOLS = {
     "theta_enumerate_n2_dev": (C.c_int, [_VP, C.c_uint64, C.c_int64, _VP, C.c_int64, _VP]),
     "theta_tile_pitch": (C.c_int64, [C.c_int32]),
     "theta_search_n2_pass1": (C.c_int, [_VP, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), _VP]),
+    "theta_search_n2_pass1_begin": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, _VP]),
+    "theta_search_n2_pass1_end": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "theta_search_n2_pass2": (C.c_int, [_VP, C.c_double, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP]),
     "theta_search_stats_get": (C.c_int, [_VP, C.POINTER(SearchStats)]),
     "theta_search_n2": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
@@ -157,9 +159,12 @@ class Plan(object):
         self.pitch = int(load().theta_tile_pitch(self.m))
 
     def close(self):
-        if getattr(self, "_h", None):
-            load().theta_plan_destroy(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:  # (module globals may already be gone at interpreter shutdown)
+            try:
+                _lib.theta_plan_destroy(h)
+            except Exception:
+                pass
 
     __del__ = close
 
@@ -272,10 +277,19 @@ class Plan(object):
         check(load().theta_search_n2_pass1(self._h, int(rank_begin), int(rank_end), C.byref(g), stream))
         return float(g.value)
 
+    def pass1_begin(self, rank_begin, rank_end, local_min_dev=None, stream=None):
+        """Asynchronous pass 1; local_min_dev: device address of a double that receives the shard minimum."""
+        check(load().theta_search_n2_pass1_begin(self._h, int(rank_begin), int(rank_end), local_min_dev, stream))
+
+    def pass1_end(self):
+        g = C.c_double()
+        check(load().theta_search_n2_pass1_end(self._h, C.byref(g)))
+        return float(g.value)
+
     def pass2(self, global_min, prior_min=float("inf"), stream=None):
-        cap = 1 << 12
+        cap = 1 << 10
         while True:
-            buf = np.zeros(cap, dtype=CAND_DTYPE)
+            buf = np.empty(cap, dtype=CAND_DTYPE)
             n = C.c_uint64()
             rc = load().theta_search_n2_pass2(self._h, float(global_min), float(prior_min), ptr(buf), cap, C.byref(n), stream)
             if rc == ERR_OVERFLOW and n.value > cap:

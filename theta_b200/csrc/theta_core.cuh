@@ -251,6 +251,8 @@ void hfree(void* p);
 template <typename T>
 inline cudaError_t hmalloc(T** p, size_t bytes) { return hmalloc_bytes(reinterpret_cast<void**>(p), bytes); }
 void cache_release();  // returns every cached block to the driver
+// the fast_log table of the current device (uploaded on first use, kept until theta_shutdown)
+cudaError_t logtab_device(double2** out);
 }  // namespace theta
 
 #define THETA_CUDA(expr)                                                        \

@@ -117,16 +117,21 @@ __global__ void __launch_bounds__(kBlock, 6) n2_search_kernel(const SearchParams
                         tmin = fmin(tmin, nll);
                     }
                     if (EMIT && emit) {
+                        // The record must not depend on the warm start (i.e. on how the rank range was cut into
+                        // shards / stripes / runs): solve the emitted candidate again from the cold start, so
+                        // that G GPUs return bit-identical (mu, NLL) to one GPU.
+                        SolveOut oc;
+                        n2_solve<KT + 1>(R, S1, z, kc, -1.0, oc, s_logtab);
                         const unsigned long long slot = atomicAdd(&p.counters[3], 1ULL);
                         if (slot < p.emit_cap) {
                             theta_cand c;
                             c.rank = r0 + t;
-                            c.nll = nll;
-                            c.mu[0] = o.mu;
-                            c.mu[1] = 1.0 - o.mu;
+                            c.nll = oc.nll;
+                            c.mu[0] = oc.mu;
+                            c.mu[1] = 1.0 - oc.mu;
                             c.mu[2] = 0.0;
-                            c.status = o.status;
-                            c.flags = o.iters;
+                            c.status = oc.status;
+                            c.flags = oc.iters;
                             p.emit[slot] = c;
                         }
                     }
@@ -387,42 +392,52 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
         pl->count = (empty || qlo[KT - 1] > qhi[KT - 1]) ? 0 : swK[qlo[KT - 1]];
         if (empty) pl->count = 0;
     }
-    cudaError_t e = theta::dmalloc(&pl->d_tables, pl->layout.bytes);
-    if (e == cudaSuccess) e = cudaMemcpy(pl->d_tables, blob.data(), pl->layout.bytes, cudaMemcpyHostToDevice);
-    std::vector<double> rd(m), rnd(m);
-    for (int i = 0; i < m; ++i) { rd[i] = (double)pl->r[i]; rnd[i] = (double)pl->rN[i]; }
-    if (e == cudaSuccess) e = theta::dmalloc(&pl->d_r, sizeof(double) * m);
-    if (e == cudaSuccess) e = theta::dmalloc(&pl->d_rN, sizeof(double) * m);
-    if (e == cudaSuccess) e = cudaMemcpy(pl->d_r, rd.data(), sizeof(double) * m, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(pl->d_rN, rnd.data(), sizeof(double) * m, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = theta::dmalloc(&pl->d_counters, sizeof(unsigned long long) * kCounters);
-    {   // fast_log table: r_i = 1/(1 + (i+0.5)/256) rounded to fp64 and -ln(r_i) of that very number
-        std::vector<double2> lt(THETA_LOGTAB_SIZE);
-        for (int i = 0; i < THETA_LOGTAB_SIZE; ++i) {
-            const double rinv = (double)(1.0L / (1.0L + ((long double)i + 0.5L) / 256.0L));
-            lt[i].x = rinv;
-            lt[i].y = (double)(-logl((long double)rinv));
-        }
-        if (e == cudaSuccess) e = theta::dmalloc(&pl->d_logtab, sizeof(double2) * THETA_LOGTAB_SIZE);
-        if (e == cudaSuccess) e = cudaMemcpy(pl->d_logtab, lt.data(), sizeof(double2) * THETA_LOGTAB_SIZE, cudaMemcpyHostToDevice);
-    }
-    {   // prefix tables for the tile kernels (theta_tiles.cu)
-        const int64_t pitch = theta_tile_pitch(m);
-        pl->tile_pitch = pitch;
-        std::vector<double> PR(pitch + 1, 0.0), PRN(pitch + 1, 0.0);
-        std::vector<int32_t> ZP(pitch + 1, 0);
+    // One device arena and one H2D copy (from a pinned staging block) for everything the kernels read:
+    //   tables | r | rN | PR | PRN | ZP | counters.   The fast_log table is per device, uploaded once.
+    const int64_t pitch = theta_tile_pitch(m);
+    pl->tile_pitch = pitch;
+    auto up256 = [](size_t o) { return (o + 255) & ~(size_t)255; };
+    size_t o = 0;
+    const size_t o_tab = o; o = up256(o + pl->layout.bytes);
+    const size_t o_r = o;   o = up256(o + sizeof(double) * m);
+    const size_t o_rN = o;  o = up256(o + sizeof(double) * m);
+    const size_t o_PR = o;  o = up256(o + sizeof(double) * (pitch + 1));
+    const size_t o_PRN = o; o = up256(o + sizeof(double) * (pitch + 1));
+    const size_t o_ZP = o;  o = up256(o + sizeof(int32_t) * (pitch + 1));
+    const size_t o_ctr = o; o = up256(o + sizeof(unsigned long long) * kCounters);
+    const size_t arena_bytes = o;
+    unsigned char* stage = nullptr;
+    cudaError_t e = theta::hmalloc(&stage, arena_bytes);
+    if (e == cudaSuccess) {
+        std::memset(stage, 0, arena_bytes);
+        std::memcpy(stage + o_tab, blob.data(), pl->layout.bytes);
+        double* rd = reinterpret_cast<double*>(stage + o_r);
+        double* rnd = reinterpret_cast<double*>(stage + o_rN);
+        for (int i = 0; i < m; ++i) { rd[i] = (double)pl->r[i]; rnd[i] = (double)pl->rN[i]; }
+        // prefix tables for the tile kernels (theta_tiles.cu), flat past m
+        double* PR = reinterpret_cast<double*>(stage + o_PR);
+        double* PRN = reinterpret_cast<double*>(stage + o_PRN);
+        int32_t* ZP = reinterpret_cast<int32_t*>(stage + o_ZP);
         int64_t s = 0, sn = 0;
         int z = 0;
         for (int64_t i = 0; i < pitch; ++i) {
             if (i < m) { s += pl->r[i]; sn += pl->rN[i]; z += pl->r[i] == 0 ? 1 : 0; }
             PR[i + 1] = (double)s; PRN[i + 1] = (double)sn; ZP[i + 1] = z;
         }
-        if (e == cudaSuccess) e = theta::dmalloc(&pl->d_PR, sizeof(double) * (pitch + 1));
-        if (e == cudaSuccess) e = theta::dmalloc(&pl->d_PRN, sizeof(double) * (pitch + 1));
-        if (e == cudaSuccess) e = theta::dmalloc(&pl->d_ZP, sizeof(int32_t) * (pitch + 1));
-        if (e == cudaSuccess) e = cudaMemcpy(pl->d_PR, PR.data(), sizeof(double) * (pitch + 1), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(pl->d_PRN, PRN.data(), sizeof(double) * (pitch + 1), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(pl->d_ZP, ZP.data(), sizeof(int32_t) * (pitch + 1), cudaMemcpyHostToDevice);
+        e = theta::dmalloc(&pl->d_arena, arena_bytes);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_arena, stage, arena_bytes, cudaMemcpyHostToDevice, nullptr);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    theta::hfree(stage);
+    if (e == cudaSuccess) {
+        pl->d_tables = pl->d_arena + o_tab;
+        pl->d_r = reinterpret_cast<double*>(pl->d_arena + o_r);
+        pl->d_rN = reinterpret_cast<double*>(pl->d_arena + o_rN);
+        pl->d_PR = reinterpret_cast<double*>(pl->d_arena + o_PR);
+        pl->d_PRN = reinterpret_cast<double*>(pl->d_arena + o_PRN);
+        pl->d_ZP = reinterpret_cast<int32_t*>(pl->d_arena + o_ZP);
+        pl->d_counters = reinterpret_cast<unsigned long long*>(pl->d_arena + o_ctr);
+        e = theta::logtab_device(&pl->d_logtab);
     }
     if (e != cudaSuccess) {
         int rc = cuda_fail(e, "plan allocation", __FILE__, __LINE__);
@@ -436,10 +451,11 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
 extern "C" void theta_plan_destroy(theta_plan* pl) {
     if (!pl) return;
     theta_n3_plan_free(pl);
-    theta::dfree(pl->d_tables); theta::dfree(pl->d_r); theta::dfree(pl->d_rN);
-    theta::dfree(pl->d_PR); theta::dfree(pl->d_PRN); theta::dfree(pl->d_ZP);
-    theta::dfree(pl->d_stripe_min); theta::dfree(pl->d_counters); theta::dfree(pl->d_emit);
-    theta::dfree(pl->d_list); theta::dfree(pl->d_prior); theta::dfree(pl->d_logtab);
+    theta::dfree(pl->d_arena);  // tables, r, rN, PR, PRN, ZP, counters (d_logtab is the per-device table: not owned)
+    theta::dfree(pl->d_stripe_min); theta::dfree(pl->d_emit);
+    theta::dfree(pl->d_list); theta::dfree(pl->d_prior);
+    theta::hfree(pl->h_stripe_min); theta::hfree(pl->h_emit); theta::hfree(pl->h_list); theta::hfree(pl->h_ctr);
+    if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
     delete pl;
 }
 
@@ -497,21 +513,45 @@ extern "C" int theta_enumerate_n2(theta_plan* pl, uint64_t rank_begin, int64_t c
 }
 
 // ======================================================================= search
-extern "C" int theta_search_n2_pass1(theta_plan* pl, uint64_t rank_begin, uint64_t rank_end, double* local_min,
-                                     void* stream) {
-    if (!pl || !local_min) { set_error("null argument"); return THETA_ERR_INVALID; }
+namespace theta {
+// min over the stripe minima -> one double in device memory (the operand of the NCCL all-reduce(min))
+__global__ void __launch_bounds__(1024) stripe_min_reduce_kernel(const double* __restrict__ v, uint64_t n, double* out0, double* out1) {
+    __shared__ double s_w[32];
+    double m = INFINITY;
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmin(m, v[i]);
+    m = warp_min(m);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = warp_min(s_w[threadIdx.x]);
+        if (threadIdx.x == 0) { *out0 = m; if (out1) *out1 = m; }
+    }
+}
+}  // namespace theta
+
+static int plan_events(theta_plan* pl) {
+    if (!pl->ev0) { THETA_CUDA(cudaEventCreate(&pl->ev0)); THETA_CUDA(cudaEventCreate(&pl->ev1)); }
+    if (!pl->h_ctr) THETA_CUDA(theta::hmalloc(&pl->h_ctr, sizeof(unsigned long long) * 2 * kCounters + sizeof(double)));
+    return THETA_OK;
+}
+
+// Pass 1, asynchronous part: everything is enqueued on `stream` and nothing is waited for, so the caller can
+// enqueue the NCCL all-reduce(min) on `local_min_dev` right behind it.
+extern "C" int theta_search_n2_pass1_begin(theta_plan* pl, uint64_t rank_begin, uint64_t rank_end, double* local_min_dev,
+                                           void* stream) {
+    if (!pl) { set_error("null argument"); return THETA_ERR_INVALID; }
     if (pl->n != 2) { set_error("plan is not n=2"); return THETA_ERR_INVALID; }
     if (pl->count == 0) { set_error("No valid Copy Number Profiles exist for these intervals within the bounds specified"); return THETA_ERR_EMPTY; }
     if (rank_end > pl->count) rank_end = pl->count;
     if (rank_begin > rank_end) { set_error("bad rank range"); return THETA_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = plan_events(pl);
+    if (rc) return rc;
     const uint64_t N = rank_end - rank_begin;
-    pl->p1_begin = rank_begin; pl->p1_end = rank_end;
+    pl->p1_begin = rank_begin; pl->p1_end = rank_end; pl->p1_stream = stream; pl->p1_pending = true;
     pl->stats = theta_search_stats{};
     pl->stats.n_candidates = N;
     pl->stats.min_nll = INFINITY;
-    *local_min = INFINITY;
-    if (N == 0) { pl->p1_stripes = 0; pl->h_stripe_min.clear(); return THETA_OK; }
     // run length per lane: enough stripes (one warp each) to balance the SMs, few enough to keep the stripe table small
     const uint64_t target_stripes = (uint64_t)sm_count(pl->device) * 24 * (kBlock / 32);
     uint64_t L = N / (target_stripes * 32);
@@ -520,33 +560,42 @@ extern "C" int theta_search_n2_pass1(theta_plan* pl, uint64_t rank_begin, uint64
     pl->p1_L = (int)L; pl->p1_block = kBlock;
     const uint64_t stripes = (N + L * 32 - 1) / (L * 32);
     pl->p1_stripes = stripes;
-    if (stripes > pl->stripe_cap) {
-        theta::dfree(pl->d_stripe_min); pl->d_stripe_min = nullptr; pl->stripe_cap = 0;
-        THETA_CUDA(theta::dmalloc(&pl->d_stripe_min, sizeof(double) * stripes));
-        pl->stripe_cap = stripes;
+    if (stripes + 1 > pl->stripe_cap) {
+        theta::dfree(pl->d_stripe_min); theta::hfree(pl->h_stripe_min);
+        pl->d_stripe_min = nullptr; pl->h_stripe_min = nullptr; pl->stripe_cap = 0;
+        THETA_CUDA(theta::dmalloc(&pl->d_stripe_min, sizeof(double) * (stripes + 1)));
+        THETA_CUDA(theta::hmalloc(&pl->h_stripe_min, sizeof(double) * (stripes + 1)));
+        pl->stripe_cap = stripes + 1;
     }
     THETA_CUDA(cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kCounters, st));
-    SearchParams sp{};
-    sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
-    sp.begin = rank_begin; sp.end = rank_end; sp.L = (int)L; sp.Lrun = (int)L; sp.units_per_item = 1;
-    sp.n_items = (uint32_t)stripes;
-    sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters;
-    cudaEvent_t e0, e1;
-    THETA_CUDA(cudaEventCreate(&e0)); THETA_CUDA(cudaEventCreate(&e1));
-    THETA_CUDA(cudaEventRecord(e0, st));
-    THETA_KT_DISPATCH(pl->KT, { int rc = launch_search<KT, false>(pl, sp, st); if (rc) return rc; });
-    THETA_CUDA(cudaEventRecord(e1, st));
-    pl->h_stripe_min.resize(stripes);
-    THETA_CUDA(cudaMemcpyAsync(pl->h_stripe_min.data(), pl->d_stripe_min, sizeof(double) * stripes, cudaMemcpyDeviceToHost, st));
-    unsigned long long ctr[kCounters];
-    THETA_CUDA(cudaMemcpyAsync(ctr, pl->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, st));
-    THETA_CUDA(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&pl->stats.ms_pass1, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    double g = INFINITY;
-    for (double v : pl->h_stripe_min) if (v < g) g = v;
+    THETA_CUDA(cudaEventRecord(pl->ev0, st));
+    if (N) {
+        SearchParams sp{};
+        sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
+        sp.begin = rank_begin; sp.end = rank_end; sp.L = (int)L; sp.Lrun = (int)L; sp.units_per_item = 1;
+        sp.n_items = (uint32_t)stripes;
+        sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters;
+        THETA_KT_DISPATCH(pl->KT, { int rc2 = launch_search<KT, false>(pl, sp, st); if (rc2) return rc2; });
+    }
+    THETA_CUDA(cudaEventRecord(pl->ev1, st));
+    // slot [stripes] of the stripe table receives the shard minimum (and so does the caller's device double)
+    stripe_min_reduce_kernel<<<1, 1024, 0, st>>>(pl->d_stripe_min, stripes, pl->d_stripe_min + stripes, local_min_dev);
+    THETA_CUDA(cudaGetLastError());
+    THETA_CUDA(cudaMemcpyAsync(pl->h_stripe_min, pl->d_stripe_min, sizeof(double) * (stripes + 1), cudaMemcpyDeviceToHost, st));
+    THETA_CUDA(cudaMemcpyAsync(pl->h_ctr, pl->d_counters, sizeof(unsigned long long) * kCounters, cudaMemcpyDeviceToHost, st));
+    return THETA_OK;
+}
+
+extern "C" int theta_search_n2_pass1_end(theta_plan* pl, double* local_min) {
+    if (!pl || !local_min) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (!pl->p1_pending) { set_error("pass1_end without pass1_begin"); return THETA_ERR_INVALID; }
+    pl->p1_pending = false;
+    THETA_CUDA(cudaStreamSynchronize((cudaStream_t)pl->p1_stream));
+    cudaEventElapsedTime(&pl->stats.ms_pass1, pl->ev0, pl->ev1);
+    const unsigned long long* ctr = pl->h_ctr;
+    const double g = pl->h_stripe_min[pl->p1_stripes];
     pl->stats.n_solved = ctr[1];
-    pl->stats.n_stripes = stripes;
+    pl->stats.n_stripes = pl->p1_stripes;
     pl->stats.newton_iters = ctr[1] ? (double)ctr[2] / (double)ctr[1] : 0.0;
     pl->stats.min_nll = g;
     pl->stats.n_rescanned = ctr[4];  // provisional: number of NaN-NLL candidates, consumed by pass 2
@@ -554,49 +603,68 @@ extern "C" int theta_search_n2_pass1(theta_plan* pl, uint64_t rank_begin, uint64
     return THETA_OK;
 }
 
+extern "C" int theta_search_n2_pass1(theta_plan* pl, uint64_t rank_begin, uint64_t rank_end, double* local_min,
+                                     void* stream) {
+    if (!local_min) { set_error("null argument"); return THETA_ERR_INVALID; }
+    *local_min = INFINITY;
+    int rc = theta_search_n2_pass1_begin(pl, rank_begin, rank_end, nullptr, stream);
+    if (rc) return rc;
+    return theta_search_n2_pass1_end(pl, local_min);
+}
+
 extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double prior_min, theta_cand* out_host,
                                      uint64_t cap, uint64_t* n_out, void* stream) {
     if (!pl || !n_out) { set_error("null argument"); return THETA_ERR_INVALID; }
     *n_out = 0;
+    if (pl->p1_pending) { set_error("pass2 before pass1_end"); return THETA_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t stripes = pl->p1_stripes;
     const bool any_nan = pl->stats.n_rescanned != 0;
     pl->stats.n_rescanned = 0;
-    if (stripes == 0) return THETA_OK;
+    if (stripes == 0 || pl->p1_begin == pl->p1_end) return THETA_OK;
     // A stripe matters if it holds a strict prefix minimum of the NLL stream (every reset of the
     // reference fold is one, RunTHetA.py:203-206) or a candidate within two margins of the global minimum
     // (every member of the final tie list is, RunTHetA.py:199-202).
     const double near_thr = global_min + 2.5 * THETA_TIE_MARGIN;
-    std::vector<uint32_t> list;
-    std::vector<double> prior;
-    double P = prior_min;
-    for (uint64_t s = 0; s < stripes; ++s) {
-        const double v = pl->h_stripe_min[s];
-        const bool rec = v < P, near = v <= near_thr;
-        if (rec || near || any_nan) {
-            list.push_back((uint32_t)s);
-            prior.push_back(rec ? P : -INFINITY);
+    size_t n_list = 0;
+    {
+        double P = prior_min;
+        for (uint64_t s = 0; s < stripes; ++s) {
+            const double v = pl->h_stripe_min[s];
+            if (v < P || v <= near_thr || any_nan) ++n_list;
+            if (v < P) P = v;
         }
-        if (v < P) P = v;
     }
-    pl->stats.n_rescanned = list.size();
-    if (list.empty()) return THETA_OK;
-    if (list.size() > pl->list_cap) {
-        theta::dfree(pl->d_list); theta::dfree(pl->d_prior); pl->d_list = nullptr; pl->d_prior = nullptr; pl->list_cap = 0;
-        const size_t want_l = std::max<size_t>(1024, list.size() * 2);
+    pl->stats.n_rescanned = n_list;
+    if (n_list == 0) return THETA_OK;
+    if (n_list > pl->list_cap) {
+        theta::dfree(pl->d_list); theta::dfree(pl->d_prior); theta::hfree(pl->h_list);
+        pl->d_list = nullptr; pl->d_prior = nullptr; pl->h_list = nullptr; pl->list_cap = 0;
+        const size_t want_l = std::max<size_t>(1024, n_list * 2);
         THETA_CUDA(theta::dmalloc(&pl->d_list, sizeof(uint32_t) * want_l));
         THETA_CUDA(theta::dmalloc(&pl->d_prior, sizeof(double) * want_l));
+        THETA_CUDA(theta::hmalloc(&pl->h_list, (sizeof(uint32_t) + sizeof(double)) * want_l));
         pl->list_cap = want_l;
     }
-    uint32_t* d_list = pl->d_list;
-    double* d_prior = pl->d_prior;
-    THETA_CUDA(cudaMemcpyAsync(d_list, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice, st));
-    THETA_CUDA(cudaMemcpyAsync(d_prior, prior.data(), sizeof(double) * list.size(), cudaMemcpyHostToDevice, st));
-    size_t want = std::max<size_t>(1 << 16, pl->emit_cap);
-    std::vector<theta_cand> host;
+    double* h_prior = reinterpret_cast<double*>(pl->h_list);
+    uint32_t* h_list = reinterpret_cast<uint32_t*>(pl->h_list + sizeof(double) * pl->list_cap);
+    {
+        double P = prior_min;
+        size_t w = 0;
+        for (uint64_t s = 0; s < stripes; ++s) {
+            const double v = pl->h_stripe_min[s];
+            const bool rec = v < P, near = v <= near_thr;
+            if (rec || near || any_nan) { h_list[w] = (uint32_t)s; h_prior[w] = rec ? P : -INFINITY; ++w; }
+            if (v < P) P = v;
+        }
+    }
+    THETA_CUDA(cudaMemcpyAsync(pl->d_list, h_list, sizeof(uint32_t) * n_list, cudaMemcpyHostToDevice, st));
+    THETA_CUDA(cudaMemcpyAsync(pl->d_prior, h_prior, sizeof(double) * n_list, cudaMemcpyHostToDevice, st));
+    size_t want = std::max<size_t>(1 << 14, pl->emit_cap);
+    const size_t spec = 1024;  // records copied back speculatively together with the counters (one sync)
+    theta_cand* host = nullptr;
+    size_t n_host = 0;
     int rc = THETA_OK;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int attempt = 0; attempt < 8; ++attempt) {
         if (want > pl->emit_cap) {
             theta::dfree(pl->d_emit); pl->d_emit = nullptr; pl->emit_cap = 0;
@@ -604,15 +672,21 @@ extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double p
             if (e != cudaSuccess) { rc = cuda_fail(e, "emit buffer", __FILE__, __LINE__); break; }
             pl->emit_cap = want;
         }
+        if (std::max(spec, want) > pl->h_emit_cap) {
+            theta::hfree(pl->h_emit); pl->h_emit = nullptr; pl->h_emit_cap = 0;
+            cudaError_t e = theta::hmalloc(&pl->h_emit, sizeof(theta_cand) * std::max(spec, want));
+            if (e != cudaSuccess) { rc = cuda_fail(e, "emit staging", __FILE__, __LINE__); break; }
+            pl->h_emit_cap = std::max(spec, want);
+        }
         cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kCounters, st);
         SearchParams sp{};
         sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
-        sp.begin = pl->p1_begin; sp.end = pl->p1_end; sp.L = pl->p1_L; sp.n_items = (uint32_t)list.size();
+        sp.begin = pl->p1_begin; sp.end = pl->p1_end; sp.L = pl->p1_L; sp.n_items = (uint32_t)n_list;
         sp.Lrun = std::min(pl->p1_L, 4); sp.units_per_item = (pl->p1_L + sp.Lrun - 1) / sp.Lrun;
         sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters;
-        sp.stripe_list = d_list; sp.stripe_prior = d_prior; sp.near_thr = near_thr;
+        sp.stripe_list = pl->d_list; sp.stripe_prior = pl->d_prior; sp.near_thr = near_thr;
         sp.emit = pl->d_emit; sp.emit_cap = pl->emit_cap;
-        cudaEventRecord(e0, st);
+        cudaEventRecord(pl->ev0, st);
         rc = THETA_OK;
         switch (pl->KT) {
 #define THETA_P2(KTV) case KTV: rc = launch_search<KTV, true>(pl, sp, st); break;
@@ -621,42 +695,45 @@ extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double p
             default: set_error("unsupported level count"); rc = THETA_ERR_UNSUPPORTED;
         }
         if (rc) break;
-        cudaEventRecord(e1, st);
-        unsigned long long ctr[kCounters];
-        cudaError_t e = cudaMemcpyAsync(ctr, pl->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(pl->ev1, st);
+        unsigned long long* ctr = pl->h_ctr + kCounters;
+        cudaError_t e = cudaMemcpyAsync(ctr, pl->d_counters, sizeof(unsigned long long) * kCounters, cudaMemcpyDeviceToHost, st);
+        const size_t n_spec = std::min(spec, pl->emit_cap);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pl->h_emit, pl->d_emit, sizeof(theta_cand) * n_spec, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "pass2", __FILE__, __LINE__); break; }
-        cudaEventElapsedTime(&pl->stats.ms_pass2, e0, e1);
+        cudaEventElapsedTime(&pl->stats.ms_pass2, pl->ev0, pl->ev1);
         const unsigned long long emitted = ctr[3];
         if (emitted > pl->emit_cap) { want = (size_t)emitted + 1024; continue; }
-        host.resize(emitted);
-        if (emitted) {
-            e = cudaMemcpy(host.data(), pl->d_emit, sizeof(theta_cand) * emitted, cudaMemcpyDeviceToHost);
+        if (emitted > n_spec) {
+            e = cudaMemcpyAsync(pl->h_emit + n_spec, pl->d_emit + n_spec, sizeof(theta_cand) * (emitted - n_spec), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) { rc = cuda_fail(e, "pass2 D2H", __FILE__, __LINE__); break; }
         }
+        host = pl->h_emit;
+        n_host = (size_t)emitted;
         break;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (rc) return rc;
-    std::sort(host.begin(), host.end(), [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; });
+    std::sort(host, host + n_host, [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; });
     {   // keep exactly: strict prefix minima of the whole stream (w.r.t. everything before this shard),
         // the near-minimum set, and NaN values -- the per-lane filter on the device emits a superset
         size_t w = 0;
         double run = prior_min;
-        for (size_t i = 0; i < host.size(); ++i) {
+        for (size_t i = 0; i < n_host; ++i) {
             const double v = host[i].nll;
             const bool keep = (v != v) || v < run || v <= near_thr;
             if (v < run) run = v;
             if (keep) host[w++] = host[i];
         }
-        host.resize(w);
+        n_host = w;
     }
-    *n_out = host.size();
-    if (host.size() > cap) {
-        set_error("pass2 produced %zu records but the caller's buffer holds %llu", host.size(), (unsigned long long)cap);
+    *n_out = n_host;
+    if (n_host > cap) {
+        set_error("pass2 produced %zu records but the caller's buffer holds %llu", n_host, (unsigned long long)cap);
         return THETA_ERR_OVERFLOW;
     }
-    if (out_host && !host.empty()) std::memcpy(out_host, host.data(), sizeof(theta_cand) * host.size());
+    if (out_host && n_host) std::memcpy(out_host, host, sizeof(theta_cand) * n_host);
     return THETA_OK;
 }
 

@@ -1,6 +1,7 @@
 // theta_rt.cu -- runtime entry points: device selection, error reporting, the fp64
 // roofline probe, and the single-matrix masked NLL of CalcAllC.L2 / L3.
 #include <cstdarg>
+#include <cmath>
 #include <cstdio>
 #include <map>
 #include <mutex>
@@ -83,6 +84,31 @@ void dfree(void* p) { dcache().put(p); }
 cudaError_t hmalloc_bytes(void** p, size_t bytes) { return hcache().get(p, bytes); }
 void hfree(void* p) { hcache().put(p); }
 void cache_release() { dcache().release(); hcache().release(); }
+
+// fast_log table: r_i = 1/(1 + (i+0.5)/256) rounded to fp64 and -ln(r_i) of that very number
+cudaError_t logtab_device(double2** out) {
+    static std::mutex mu;
+    static std::map<int, double2*> tabs;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = tabs.find(dev);
+    if (it != tabs.end()) { *out = it->second; return cudaSuccess; }
+    std::vector<double2> lt(THETA_LOGTAB_SIZE);
+    for (int i = 0; i < THETA_LOGTAB_SIZE; ++i) {
+        const double rinv = (double)(1.0L / (1.0L + ((long double)i + 0.5L) / 256.0L));
+        lt[i].x = rinv;
+        lt[i].y = (double)(-logl((long double)rinv));
+    }
+    double2* d = nullptr;
+    e = cudaMalloc(&d, sizeof(double2) * THETA_LOGTAB_SIZE);
+    if (e == cudaSuccess) e = cudaMemcpy(d, lt.data(), sizeof(double2) * THETA_LOGTAB_SIZE, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return e; }
+    tabs[dev] = d;
+    *out = d;
+    return cudaSuccess;
+}
 
 // Dependent-free DFMA streams: 8 accumulators per thread, enough warps to saturate the fp64 pipe.
 __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {

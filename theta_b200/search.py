@@ -65,72 +65,114 @@ def _dev(dist):
 
 
 def exchange_minima(local_min, dist, rank, world):
-    """One all-reduce(min) for the global best NLL + an all-gather of the shard minima, one host sync.
+    """One all-reduce(min) for the global best NLL (host value in, host value out; the gloo / test path).
 
-    Returns (global_min, prior_min) with prior_min = min over shards before `rank`.
+    Returns (global_min, prior_min).  prior_min is always +inf: every shard emits the strict prefix minima of
+    its own range, a superset of the global ones, and the fold replay over the union is unchanged by the extra
+    records (each is >= an earlier record - margin, so it can neither reset the fold nor survive in the final
+    tie list unless it is within two margins of the global minimum, in which case it is emitted anyway).
     """
     if dist is None:
         return local_min, INF
     import torch
     t = torch.tensor([local_min], dtype=torch.float64, device=_dev(dist))
-    g = t.clone()
-    h1 = dist.all_reduce(g, op=dist.ReduceOp.MIN, async_op=True)
-    allm = torch.empty(world, dtype=torch.float64, device=t.device)
-    h2 = dist.all_gather_into_tensor(allm, t, async_op=True)
-    h1.wait()
-    h2.wait()
-    both = torch.cat([g, allm]).cpu().tolist()
-    mins = both[1:]
-    prior = min(mins[:rank]) if rank > 0 else INF
-    return both[0], prior
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return float(t.item()), INF
+
+
+_BUFS = {}
+
+
+def _bufs(dist, world, nbytes):
+    """Per-process exchange buffers (device + pinned host), allocated once."""
+    import torch
+    dev = _dev(dist)
+    key = (str(dev), world, nbytes)
+    b = _BUFS.get(key)
+    if b is None:
+        pin = dev.type == "cuda"
+        b = {"min": torch.empty(1, dtype=torch.float64, device=dev),
+             "send_h": torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin),
+             "send_d": torch.empty(nbytes, dtype=torch.uint8, device=dev),
+             "recv_d": torch.empty(world * nbytes, dtype=torch.uint8, device=dev),
+             "recv_h": torch.empty(world * nbytes, dtype=torch.uint8, pin_memory=pin)}
+        _BUFS[key] = b
+    return b
+
+
+def pass1_allreduce(plan, begin, end, dist, world, stream=None):
+    """Pass 1 on this shard + the single all-reduce(min) over all shards.  Returns (global_min, local_min).
+
+    With NCCL the shard minimum never visits the host in between: the search kernel's reduction writes it to a
+    device double and the all-reduce is enqueued right behind the kernel (stream order), so the step costs one
+    host synchronisation."""
+    if dist is None:
+        lm = plan.pass1(begin, end, stream)
+        return lm, lm
+    import torch
+    if dist.get_backend() != "nccl":
+        lm = plan.pass1(begin, end, stream)
+        return exchange_minima(lm, dist, 0, world)[0], lm
+    cur = torch.cuda.current_stream()
+    if stream is not None and int(stream) != int(cur.cuda_stream):
+        raise ValueError("with NCCL the search must run on torch's current stream")
+    t = _bufs(dist, world, _GATHER_BYTES)["min"]
+    plan.pass1_begin(begin, end, t.data_ptr(), cur.cuda_stream)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)   # ordered behind the kernel on the current stream
+    lm = plan.pass1_end()
+    return float(t.item()), lm
 
 
 _GATHER_CAP = 256  # records per shard carried by the fixed-size exchange
+_GATHER_HEAD = 8 * 4  # int64 header: record count + up to three extras
 
 
 def gather_records(recs, dist, world, extra=None):
     """All shards' pass-2 records, concatenated in rank order (they are already sorted per shard).
 
     One fixed-size all-gather carries up to _GATHER_CAP records per shard plus the shard's record count
-    (and `extra`, a small int64 payload such as the solved-candidate count); only when a shard has more
+    (and `extra`, up to three int64 such as the solved-candidate count); only when a shard has more
     records is a second, variable-size exchange needed.  Returns records, or (records, extras) if extra is given.
     """
     if dist is None:
         return recs if extra is None else (recs, [list(extra)])
     import torch
     item = _lib.CAND_DTYPE.itemsize
-    dev = _dev(dist)
     nx = 0 if extra is None else len(extra)
-    head = np.zeros(1 + nx, dtype=np.int64)
+    assert nx <= 3
+    b = _bufs(dist, world, _GATHER_BYTES)
+    sh = b["send_h"].numpy()
+    head = sh[:_GATHER_HEAD].view(np.int64)
+    head[:] = 0
     head[0] = len(recs)
     if nx:
-        head[1:] = extra
+        head[1:1 + nx] = extra
     k = min(len(recs), _GATHER_CAP)
-    buf = np.zeros(head.nbytes + _GATHER_CAP * item, dtype=np.uint8)
-    buf[:head.nbytes] = np.frombuffer(head.tobytes(), dtype=np.uint8)
-    buf[head.nbytes:head.nbytes + k * item] = np.frombuffer(recs[:k].tobytes(), dtype=np.uint8)
-    t = torch.from_numpy(buf).to(dev)
-    out = torch.empty(world * buf.size, dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(out, t)
-    raw = out.cpu().numpy().reshape(world, buf.size)
-    heads = [np.frombuffer(raw[r, :head.nbytes].tobytes(), dtype=np.int64) for r in range(world)]
+    sh[_GATHER_HEAD:_GATHER_HEAD + k * item] = recs[:k].view(np.uint8).reshape(-1)
+    b["send_d"].copy_(b["send_h"], non_blocking=True)
+    dist.all_gather_into_tensor(b["recv_d"], b["send_d"])
+    b["recv_h"].copy_(b["recv_d"], non_blocking=True)
+    if b["recv_d"].is_cuda:
+        torch.cuda.current_stream().synchronize()
+    raw = b["recv_h"].numpy().reshape(world, _GATHER_BYTES)
+    heads = raw[:, :_GATHER_HEAD].copy().view(np.int64)
     ns = [int(h[0]) for h in heads]
     if max(ns) <= _GATHER_CAP:
-        parts = [np.frombuffer(raw[r, head.nbytes:head.nbytes + ns[r] * item].tobytes(), dtype=_lib.CAND_DTYPE)
-                 for r in range(world)]
+        parts = [raw[r, _GATHER_HEAD:_GATHER_HEAD + ns[r] * item].copy().view(_lib.CAND_DTYPE) for r in range(world)]
     else:
+        dev = _dev(dist)
         cap = max(ns)
         big = np.zeros(cap * item, dtype=np.uint8)
-        big[:len(recs) * item] = np.frombuffer(recs.tobytes(), dtype=np.uint8)
+        big[:len(recs) * item] = recs.view(np.uint8).reshape(-1)
         tb = torch.from_numpy(big).to(dev)
         outb = torch.empty(world * big.size, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(outb, tb)
         rawb = outb.cpu().numpy().reshape(world, big.size)
-        parts = [np.frombuffer(rawb[r, :ns[r] * item].tobytes(), dtype=_lib.CAND_DTYPE) for r in range(world)]
+        parts = [rawb[r, :ns[r] * item].copy().view(_lib.CAND_DTYPE) for r in range(world)]
     allrecs = np.concatenate(parts) if parts else recs
     if extra is None:
         return allrecs
-    return allrecs, [[int(v) for v in h[1:]] for h in heads]
+    return allrecs, [[int(v) for v in h[1:1 + nx]] for h in heads]
 
 
 class SearchResult(object):
@@ -153,10 +195,9 @@ def search_n2(plan, stream=None, rank_limit=None):
     if rank_limit is not None:
         total = min(total, int(rank_limit))
     begin, end = shard_range(total, rank, world)
-    local_min = plan.pass1(begin, end, stream)
+    g, _local = pass1_allreduce(plan, begin, end, dist, world, stream)
     stats = plan.stats()
-    g, prior = exchange_minima(local_min, dist, rank, world)
-    recs = plan.pass2(g, prior, stream)
+    recs = plan.pass2(g, INF, stream)
     stats.update({k: v for k, v in plan.stats().items() if k in ("n_rescanned", "ms_pass2")})
     allrecs, extras = gather_records(recs, dist, world, extra=[stats["n_solved"]])
     res = SearchResult()
@@ -204,6 +245,9 @@ def _finish_n2(plan, res, tau, sorted_index):
         best.append((_reverse_sort_rows(C, sorted_index), (mu0, 1 - mu0), np.float64(nll),
                      _reverse_sort_list(v, sorted_index)))
     return best
+
+
+_GATHER_BYTES = _GATHER_HEAD + _GATHER_CAP * _lib.CAND_DTYPE.itemsize
 
 
 _NO_PROFILES = ("Error: No valid Copy Number Profiles exist for these intervals within the bounds specified. "
