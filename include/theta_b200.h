@@ -85,6 +85,10 @@ typedef struct theta_search_stats {
     double newton_iters;   /* mean root-finder iterations per solved candidate */
     float ms_pass1;
     float ms_pass2;
+    uint64_t n_exact;            /* pass 1 (n=2): candidates whose NLL was evaluated in fp64 (the rest were proven
+                                    irrelevant by the fp32-log bound, theta_core.cuh::n2_l2_approx) */
+    uint64_t n_bound_violations; /* THETA_VERIFY_APPROX=1 only: candidates whose fp32-log NLL missed the fp64 one by
+                                    more than the stated bound (must be 0) */
 } theta_search_stats;
 
 typedef struct theta_plan theta_plan; /* opaque: device tables of one problem */

@@ -47,7 +47,8 @@ assert CAND_DTYPE.itemsize == C.sizeof(Cand)
 class SearchStats(C.Structure):
     _fields_ = [("n_candidates", C.c_uint64), ("n_solved", C.c_uint64), ("n_stripes", C.c_uint64),
                 ("n_rescanned", C.c_uint64), ("min_nll", C.c_double), ("newton_iters", C.c_double),
-                ("ms_pass1", C.c_float), ("ms_pass2", C.c_float)]
+                ("ms_pass1", C.c_float), ("ms_pass2", C.c_float),
+                ("n_exact", C.c_uint64), ("n_bound_violations", C.c_uint64)]
 
 
 # every symbol include/theta_b200.h declares: (restype, argtypes)

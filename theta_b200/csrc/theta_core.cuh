@@ -77,7 +77,18 @@ __device__ __forceinline__ double fast_log(double g, const double2* __restrict__
     return fma((double)e, 0.6931471805599453094, t.y + r);
 }
 
-// Evaluate f and f' at x over the non-empty groups (python/Optimizer.py:209-221 and its derivative).
+// 1/a to ~2^-44 relative: MUFU.RCP64H seed + one Newton-Raphson step.  Enough for the Newton iterates of the
+// root-finder (an error eps in every term of f moves the root by about eps * x), not used for results.
+__device__ __forceinline__ double fast_rcp1(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    const double e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
+
+// Evaluate f and f' at x in the open bracket (python/Optimizer.py:209-221 and its derivative).  Every
+// denominator v y + z is positive there (z = x S1 > 0), so empty groups (nv == 0) simply add zero and the
+// loop needs no guard.
 template <int KV>
 __device__ __forceinline__ void n2_f_df(const double (&nv)[KV], const double (&ev)[KV], double S1, double A, double x,
                                         double& f, double& fp) {
@@ -86,13 +97,11 @@ __device__ __forceinline__ void n2_f_df(const double (&nv)[KV], const double (&e
     double s = 0.0, sp = 0.0;
 #pragma unroll
     for (int v = 0; v < KV; ++v) {
-        if (nv[v] != 0.0) {
-            const double den = fma((double)v, y, z);
-            const double inv = fast_rcp(den);
-            const double t = nv[v] * inv;
-            s += t;
-            sp = fma(t * ev[v], inv, sp);
-        }
+        const double den = fma((double)v, y, z);
+        const double inv = fast_rcp1(den);
+        const double t = nv[v] * inv;
+        s += t;
+        sp = fma(t * ev[v], inv, sp);
     }
     f = -s;
     fp = sp;
@@ -115,9 +124,10 @@ __device__ __forceinline__ double n2_f(const double (&nv)[KV], double S1, double
 //   S1        : sum rN_i c_i
 //   zero_r_c0 : some interval with c_i == 0 has r_i == 0 (0/0 at x = lB = 0 -> NaN -> None)
 //   x0        : warm start for the root (<= 0: none)
+// n2_root: everything up to mu (brenth + M2); returns false when the reference returns None.
 template <int KV>
-__device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool zero_r_c0, const N2Const& k, double x0,
-                                         SolveOut& o, const double2* __restrict__ LT = nullptr) {
+__device__ __forceinline__ bool n2_root(const double (&R)[KV], double S1, bool zero_r_c0, const N2Const& k, double x0,
+                                        SolveOut& o) {
     o.x = 0.0;
     o.mu = 0.0;
     o.nll = 0.0;
@@ -126,7 +136,7 @@ __device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool 
     // NaN guard raises -> None.  Same for any rN_i == 0 (both normalised entries are 0).
     if (!(S1 > 0.0) || k.any_zero_rN || zero_r_c0) {
         o.status = THETA_ST_NONE_NAN;
-        return;
+        return false;
     }
     double ev[KV], nv[KV];
 #pragma unroll
@@ -161,7 +171,7 @@ __device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool 
     }
     if (f0 != f0 || fU != fU) {
         o.status = THETA_ST_NONE_NAN;
-        return;
+        return false;
     }
     double x;
     int status = THETA_ST_OK;
@@ -173,7 +183,7 @@ __device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool 
         status = THETA_ST_ROOT_UB;
     } else if ((f0 < 0.0) == (fU < 0.0)) {
         o.status = THETA_ST_NONE_SIGN;
-        return;
+        return false;
     } else {
         // f is increasing (f' = sum R_v e_v^2 / den^2 > 0): safeguarded Newton inside the bracket.
         double lo = 0.0, hi = uB;
@@ -204,15 +214,23 @@ __device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool 
         o.iters = it + 1;
         if (it >= THETA_NEWTON_MAXIT) {
             o.status = THETA_ST_NONE_NOCONV;
-            return;
+            return false;
         }
     }
     // M2 (Optimizer.py:223-226), same operation order
     const double numer = -x * S1;
     const double denom = (x - 1.0) * k.S0 + numer;
-    const double mu = numer / denom;
+    o.x = x;
+    o.mu = numer / denom;
+    o.status = status;
+    return true;
+}
+
+// L2 (Optimizer.py:187-196) on grouped statistics at mu.
+template <int KV>
+__device__ __forceinline__ double n2_l2(const double (&R)[KV], double S1, double mu, const N2Const& k,
+                                        const double2* __restrict__ LT) {
     const double mu1 = 1.0 - mu;
-    // L2 (Optimizer.py:187-196) on grouped statistics
     const double gbar = (mu * k.S0 + mu1 * S1) / k.A;
     const double lg = LT ? fast_log(gbar, LT) : log(gbar);
     double acc = 0.0;
@@ -223,10 +241,37 @@ __device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool 
             acc = fma(R[v], (LT ? fast_log(g, LT) : log(g)) - lg, acc);
         }
     }
-    o.x = x;
-    o.mu = mu;
-    o.nll = k.K0 - acc;
-    o.status = status;
+    return k.K0 - acc;
+}
+
+// The same NLL with fp32 MUFU logarithms: 7 special-function instructions instead of ~110 fp64 ones.
+// Valid when tau*mu >= 2^-7 (then every argument of log2 lies in [2^-7, 2^4) and |log2| < 8, so that
+// __log2f's 2-ulp bound is <= 2^-20): the absolute error of the result is below  THETA_APPROX_C * Rtot
+//   per logarithm: 2^-20 * ln2 (MUFU.LG2) + 3 * 2^-24 (fp32 argument)  <  8.5e-7,   total weight sum_v R_v + Rtot = 2 Rtot
+// and THETA_APPROX_C = 4e-6 leaves a factor 2.3 of slack.  The search uses it only to prove that a candidate
+// cannot matter (NLL far above the best seen); everything that can matter is evaluated by n2_l2.
+#define THETA_APPROX_C 4e-6
+#define THETA_APPROX_MIN_TM 0.0078125
+template <int KV>
+__device__ __forceinline__ double n2_l2_approx(const double (&R)[KV], double S1, double mu, const N2Const& k, double inv_A) {
+    const double mu1 = 1.0 - mu;
+    const double tm = k.tau * mu;
+    const float mu1f = (float)mu1, tmf = (float)tm;
+    const float lgb = __log2f((float)((mu * k.S0 + mu1 * S1) * inv_A));
+    double acc = 0.0;
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+        const float lg = __log2f(fmaf((float)v, mu1f, tmf));
+        acc = fma(R[v], (double)lg, acc);  // R[v] == 0 adds 0 (lg is finite: arguments >= 2^-7)
+    }
+    acc = fma(-k.Rtot, (double)lgb, acc);
+    return fma(-0.6931471805599453094, acc, k.K0);
+}
+
+template <int KV>
+__device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool zero_r_c0, const N2Const& k, double x0,
+                                         SolveOut& o, const double2* __restrict__ LT = nullptr) {
+    if (n2_root<KV>(R, S1, zero_r_c0, k, x0, o)) o.nll = n2_l2<KV>(R, S1, o.mu, k, LT);
 }
 
 }  // namespace theta

@@ -5,6 +5,7 @@
 // do_optimization_single / process_loop (python/RunTHetA.py:53-93,173-220).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -33,6 +34,7 @@ struct SearchParams {
     double near_thr;
     theta_cand* emit;
     unsigned long long emit_cap;
+    int verify;  // THETA_VERIFY_APPROX=1: evaluate every candidate exactly and count violations of the fp32 error bound
 };
 
 __device__ __forceinline__ double warp_min(double v) {
@@ -58,18 +60,26 @@ __device__ __forceinline__ void stage_tables(unsigned char* smem, const unsigned
 // its run once and then walks it with the odometer, warm-starting the root-finder from the roots of
 // the previous two columns.  Pass 1 (EMIT=false) writes one minimum per stripe; pass 2 (EMIT=true)
 // re-walks listed stripes in short runs and emits candidate records.
-template <int KT, bool EMIT>
-__global__ void __launch_bounds__(kBlock, 6) n2_search_kernel(const SearchParams p) {
+template <int KT, bool EMIT, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double2 s_logtab[THETA_LOGTAB_SIZE];
     for (int i = threadIdx.x; i < THETA_LOGTAB_SIZE; i += blockDim.x) s_logtab[i] = p.logtab[i];
     stage_tables(smem, p.tables, p.layout.bytes);
-    Tables T;
-    T.bind(smem, p.layout);
+    Tables T_;
+    T_.bind(smem, p.layout);
     const N2Const kc = p.kc;
     const int lane = threadIdx.x & 31;
-    unsigned long long solved = 0, iters = 0, nan_nll = 0;
+    unsigned long long solved = 0, iters = 0, nan_nll = 0, n_exact = 0, n_viol = 0;
     const unsigned long long n_units = (unsigned long long)p.n_items * p.units_per_item;
+    // Pass 1 proves most candidates irrelevant with the fp32-log NLL (n2_l2_approx): a candidate whose lower
+    // bound exceeds T + margin -- T = the best exact NLL this warp has seen in this or an earlier (lower-rank)
+    // stripe -- is neither the stripe minimum that matters (a strict prefix minimum of the stream is below
+    // everything before it, hence below T) nor within the tie window of the global minimum (<= T).
+    const double approx_E = THETA_APPROX_C * kc.Rtot;
+    const double approx_margin = 3.0 * THETA_TIE_MARGIN;
+    const double inv_A = 1.0 / kc.A;
+    double T = INFINITY;
 
     for (;;) {
         unsigned long long unit = 0;
@@ -87,12 +97,12 @@ __global__ void __launch_bounds__(kBlock, 6) n2_search_kernel(const SearchParams
         if (r0 < s_end) {
             const int cnt = (int)min((uint64_t)p.Lrun, s_end - r0);
             int q[KT];
-            n2_unrank<KT>(T, r0, q);
+            n2_unrank<KT>(T_, r0, q);
             double xprev = -1.0, xprev2 = -1.0;  // roots of the previous two columns (warm start)
             for (int t = 0; t < cnt; ++t) {
                 double R[KT + 1], S1;
                 bool z;
-                n2_groups<KT>(T, q, R, S1, z);
+                n2_groups<KT>(T_, q, R, S1, z);
                 SolveOut o;
                 // consecutive columns differ in one breakpoint, so the root moves smoothly: start Newton
                 // from the linear extrapolation of the last two roots (falls back to the last root)
@@ -101,57 +111,74 @@ __global__ void __launch_bounds__(kBlock, 6) n2_search_kernel(const SearchParams
                     const double xe = 2.0 * xprev - xprev2;
                     if (xe > 0.0 && xe < 1.0) x0 = xe;
                 }
-                n2_solve<KT + 1>(R, S1, z, kc, x0, o, s_logtab);
-                if (o.status < THETA_ST_NONE_SIGN) {
+                if (n2_root<KT + 1>(R, S1, z, kc, x0, o)) {
                     ++solved;
                     iters += o.iters;
                     xprev2 = xprev;
                     xprev = o.x;
-                    const double nll = o.nll;
-                    bool emit = false;
-                    if (nll != nll) {
-                        ++nan_nll;
-                        emit = true;  // isClose(nan, x) is True: a NaN NLL is always appended (Q6)
-                    } else {
-                        if (EMIT) emit = (nll <= p.near_thr) || (nll < prior && nll < tmin);
-                        tmin = fmin(tmin, nll);
+                    bool exact = true;
+                    double na = 0.0;
+                    if (!EMIT && kc.tau * o.mu >= THETA_APPROX_MIN_TM) {
+                        na = n2_l2_approx<KT + 1>(R, S1, o.mu, kc, inv_A);
+                        if (na - approx_E > T + approx_margin && !p.verify) exact = false;  // (NaN compares false)
                     }
-                    if (EMIT && emit) {
-                        // The record must not depend on the warm start (i.e. on how the rank range was cut into
-                        // shards / stripes / runs): solve the emitted candidate again from the cold start, so
-                        // that G GPUs return bit-identical (mu, NLL) to one GPU.
-                        SolveOut oc;
-                        n2_solve<KT + 1>(R, S1, z, kc, -1.0, oc, s_logtab);
-                        const unsigned long long slot = atomicAdd(&p.counters[3], 1ULL);
-                        if (slot < p.emit_cap) {
-                            theta_cand c;
-                            c.rank = r0 + t;
-                            c.nll = oc.nll;
-                            c.mu[0] = oc.mu;
-                            c.mu[1] = 1.0 - oc.mu;
-                            c.mu[2] = 0.0;
-                            c.status = oc.status;
-                            c.flags = oc.iters;
-                            p.emit[slot] = c;
+                    if (exact) {
+                        const double nll = n2_l2<KT + 1>(R, S1, o.mu, kc, s_logtab);
+                        if (!EMIT) {
+                            ++n_exact;
+                            if (p.verify && kc.tau * o.mu >= THETA_APPROX_MIN_TM && !(fabs(na - nll) <= approx_E)) ++n_viol;
+                        }
+                        bool emit = false;
+                        if (nll != nll) {
+                            ++nan_nll;
+                            emit = true;  // isClose(nan, x) is True: a NaN NLL is always appended (Q6)
+                        } else {
+                            if (EMIT) emit = (nll <= p.near_thr) || (nll < prior && nll < tmin);
+                            tmin = fmin(tmin, nll);
+                            T = fmin(T, nll);
+                        }
+                        if (EMIT && emit) {
+                            // The record must not depend on the warm start (i.e. on how the rank range was cut into
+                            // shards / stripes / runs): solve the emitted candidate again from the cold start, so
+                            // that G GPUs return bit-identical (mu, NLL) to one GPU.
+                            SolveOut oc;
+                            n2_solve<KT + 1>(R, S1, z, kc, -1.0, oc, s_logtab);
+                            const unsigned long long slot = atomicAdd(&p.counters[3], 1ULL);
+                            if (slot < p.emit_cap) {
+                                theta_cand c;
+                                c.rank = r0 + t;
+                                c.nll = oc.nll;
+                                c.mu[0] = oc.mu;
+                                c.mu[1] = 1.0 - oc.mu;
+                                c.mu[2] = 0.0;
+                                c.status = oc.status;
+                                c.flags = oc.iters;
+                                p.emit[slot] = c;
+                            }
                         }
                     }
                 }
-                if (t + 1 < cnt) n2_next<KT>(T, q);
+                if (t + 1 < cnt) n2_next<KT>(T_, q);
             }
         }
         if (!EMIT) {
             const double w = warp_min(tmin);
             if (lane == 0) p.stripe_min[stripe] = w;
+            T = fmin(warp_min(T), w);  // every lane continues with the warp's best
         }
     }
     if (!EMIT) {
         solved = warp_sum(solved);
         iters = warp_sum(iters);
         nan_nll = warp_sum(nan_nll);
+        n_exact = warp_sum(n_exact);
+        n_viol = warp_sum(n_viol);
         if (lane == 0) {
             if (solved) atomicAdd(&p.counters[1], solved);
             if (iters) atomicAdd(&p.counters[2], iters);
             if (nan_nll) atomicAdd(&p.counters[4], nan_nll);
+            if (n_exact) atomicAdd(&p.counters[5], n_exact);
+            if (n_viol) atomicAdd(&p.counters[6], n_viol);
         }
     }
 }
@@ -279,17 +306,34 @@ static int sm_count(int device) {
     return sms;
 }
 
-template <int KT, bool EMIT>
-static int launch_search(const theta_plan* plan, const SearchParams& sp, cudaStream_t st) {
+template <int KT, bool EMIT, int MINB>
+static int launch_search_v(const theta_plan* plan, const SearchParams& sp, cudaStream_t st) {
     int bps = 1;
-    int rc = config_kernel(n2_search_kernel<KT, EMIT>, plan->layout.bytes, &bps);
+    int rc = config_kernel(n2_search_kernel<KT, EMIT, MINB>, plan->layout.bytes, &bps);
     if (rc) return rc;
     const uint64_t units = (uint64_t)sp.n_items * sp.units_per_item;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((units + kBlock / 32 - 1) / (kBlock / 32), (uint64_t)sm_count(plan->device) * bps);
     if (grid == 0) return THETA_OK;
-    n2_search_kernel<KT, EMIT><<<grid, kBlock, plan->layout.bytes, st>>>(sp);
+    n2_search_kernel<KT, EMIT, MINB><<<grid, kBlock, plan->layout.bytes, st>>>(sp);
     THETA_CUDA(cudaGetLastError());
     return THETA_OK;
+}
+
+// THETA_SEARCH_MINB (tuning knob): resident CTAs per SM the pass-1 kernel is compiled for (6 -> 80 registers, 5 -> 96, 4 -> 128)
+static int g_search_minb = -1;
+
+template <int KT, bool EMIT>
+static int launch_search(const theta_plan* plan, const SearchParams& sp, cudaStream_t st) {
+    if (EMIT) return launch_search_v<KT, EMIT, 6>(plan, sp, st);
+    if (g_search_minb < 0) {
+        const char* e = getenv("THETA_SEARCH_MINB");
+        g_search_minb = e ? atoi(e) : 5;
+    }
+    switch (g_search_minb) {
+        case 4: return launch_search_v<KT, false, 4>(plan, sp, st);
+        case 5: return launch_search_v<KT, false, 5>(plan, sp, st);
+        default: return launch_search_v<KT, false, 6>(plan, sp, st);
+    }
 }
 
 }  // namespace theta
@@ -575,6 +619,10 @@ extern "C" int theta_search_n2_pass1_begin(theta_plan* pl, uint64_t rank_begin, 
         sp.begin = rank_begin; sp.end = rank_end; sp.L = (int)L; sp.Lrun = (int)L; sp.units_per_item = 1;
         sp.n_items = (uint32_t)stripes;
         sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters;
+        {
+            const char* ev = getenv("THETA_VERIFY_APPROX");
+            sp.verify = (ev && ev[0] == '1') ? 1 : 0;
+        }
         THETA_KT_DISPATCH(pl->KT, { int rc2 = launch_search<KT, false>(pl, sp, st); if (rc2) return rc2; });
     }
     THETA_CUDA(cudaEventRecord(pl->ev1, st));
@@ -599,6 +647,8 @@ extern "C" int theta_search_n2_pass1_end(theta_plan* pl, double* local_min) {
     pl->stats.newton_iters = ctr[1] ? (double)ctr[2] / (double)ctr[1] : 0.0;
     pl->stats.min_nll = g;
     pl->stats.n_rescanned = ctr[4];  // provisional: number of NaN-NLL candidates, consumed by pass 2
+    pl->stats.n_exact = ctr[5];
+    pl->stats.n_bound_violations = ctr[6];
     *local_min = g;
     return THETA_OK;
 }

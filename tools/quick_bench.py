@@ -20,5 +20,5 @@ for wl in sys.argv[1:] or ["cfg2", "m150k7"]:
         st = plan.stats(); p1.append(st["ms_pass1"]); p2.append(st["ms_pass2"]); wall.append((t1 - t0, t2 - t1))
     print(wl, "N=%d" % N, "pass1 ms %.3f" % min(p1), "pass2 ms %.3f" % min(p2), "cand/s kernel %.3e" % (N / min(p1) * 1e3),
           "iters %.3f" % st["newton_iters"], "host pass1 %.3f ms pass2 %.3f ms" % (1e3 * min(w[0] for w in wall), 1e3 * min(w[1] for w in wall)),
-          "rescanned", st["n_rescanned"], "recs", len(recs), "min", g)
+          "rescanned", st["n_rescanned"], "recs", len(recs), "exact", st["n_exact"], "minb", os.environ.get("THETA_SEARCH_MINB"), "min", g)
     plan.close()
