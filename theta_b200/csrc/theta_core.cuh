@@ -39,8 +39,8 @@ struct SolveOut {
 };
 
 #define THETA_NEWTON_MAXIT 100
-#define THETA_NEWTON_RTOL 1e-9    // a Newton step this small (relative) ends the iteration after it is applied
-#define THETA_NEWTON_PRED 2e-11   // ... or a predicted post-step error (quadratic model) this small
+#define THETA_NEWTON_PRED 2e-11   // stop when the error predicted after the step, |f''/(2f')| dN^2, is below this (relative)
+#define THETA_NEWTON_RTOL 1e-9    // a converged step that leaves the bracket by rounding is accepted if it is this small (relative)
 
 // 1/a for normal, non-zero a: MUFU.RCP64H seed (about 20 bits) + two Newton-Raphson steps (< 1 ulp
 // of error in practice).  The IEEE division it replaces costs ~2.5x as many instructions.
@@ -105,6 +105,30 @@ __device__ __forceinline__ void n2_f_df(const double (&nv)[KV], const double (&e
     }
     f = -s;
     fp = sp;
+}
+
+// f, f' and f''/2 at x in the open bracket:  f = -sum n_v/den_v,  f' = sum n_v e_v/den_v^2,  f''/2 = -sum n_v e_v^2/den_v^3
+// (den_v = v (1-x) A + x S1,  d den_v/dx = e_v).
+template <int KV>
+__device__ __forceinline__ void n2_f_df_d2(const double (&nv)[KV], const double (&ev)[KV], double S1, double A, double x,
+                                           double& f, double& fp, double& fpp2) {
+    const double z = x * S1;
+    const double y = (1.0 - x) * A;
+    double s = 0.0, sp = 0.0, spp = 0.0;
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+        const double den = fma((double)v, y, z);
+        const double inv = fast_rcp1(den);
+        const double t = nv[v] * inv;
+        const double ei = ev[v] * inv;
+        const double u = t * ei;
+        s += t;
+        sp += u;
+        spp = fma(u, ei, spp);
+    }
+    f = -s;
+    fp = sp;
+    fpp2 = -spp;
 }
 
 template <int KV>
@@ -185,30 +209,34 @@ __device__ __forceinline__ bool n2_root(const double (&R)[KV], double S1, bool z
         o.status = THETA_ST_NONE_SIGN;
         return false;
     } else {
-        // f is increasing (f' = sum R_v e_v^2 / den^2 > 0): safeguarded Newton inside the bracket.
+        // f is increasing (f' = sum R_v e_v^2 / den^2 > 0): safeguarded Halley iteration inside the bracket.
+        // With c2 = f''/(2f') the error left after a *Newton* step dN is |c2| dN^2 to leading order (and less
+        // after the Halley step actually taken), so the stopping test needs no history: stop once that bound is
+        // below THETA_NEWTON_PRED * |x|  (the reference's own brenth stops at 2e-12 absolute, Optimizer.py:118).
+        // Cubic convergence makes two evaluations enough from a warm start within ~1e-2, which keeps the lanes
+        // of a warp in step.
         double lo = 0.0, hi = uB;
         const bool rising = f0 < 0.0;
         x = (x0 > lo && x0 < hi) ? x0 : 0.5 * (lo + hi);
-        double dxp = INFINITY;  // previous step size
         int it = 0;
         for (; it < THETA_NEWTON_MAXIT; ++it) {
-            double f, fp;
-            n2_f_df<KV>(nv, ev, S1, k.A, x, f, fp);
+            double f, fp, fpp2;
+            n2_f_df_d2<KV>(nv, ev, S1, k.A, x, f, fp, fpp2);
             if (f == 0.0) break;
             if ((f < 0.0) == rising) lo = x; else hi = x;
-            const double dx = -f * fast_rcp(fp);
-            const double adx = fabs(dx);
+            const double rfp = fast_rcp(fp);
+            const double dN = -f * rfp;          // Newton step
+            const double c2 = fpp2 * rfp;         // f'' / (2 f')
+            const double den = fma(dN, c2, 1.0);  // Halley: dH = dN / (1 + dN c2)
+            const double dx = (den > 0.5 && den < 2.0) ? dN * fast_rcp(den) : dN;
             const double xn = x + dx;
             const bool inside = (xn > lo && xn < hi);
-            // Quadratic convergence: the error left after this step is about adx^3/dxp^2 once the steps
-            // contract fast; the reference's own brenth stops at 2e-12 absolute (Optimizer.py:118).
-            const bool small = adx <= THETA_NEWTON_RTOL * fabs(x);
-            const bool pred = inside && dxp < INFINITY && adx <= 1e-2 * dxp && adx * adx * adx <= THETA_NEWTON_PRED * fabs(x) * dxp * dxp;
-            if (small || pred) {
+            const bool conv = fabs(c2) * dN * dN <= THETA_NEWTON_PRED * fabs(x);
+            // (a converged step can round onto the bracket end it started from: then x itself is the root)
+            if (conv && (inside || fabs(dN) <= THETA_NEWTON_RTOL * fabs(x))) {
                 if (inside) x = xn;
                 break;
             }
-            dxp = inside ? adx : INFINITY;
             x = inside ? xn : 0.5 * (lo + hi);
         }
         o.iters = it + 1;
