@@ -160,6 +160,13 @@ int theta_nll_tiles_n2_dev(theta_plan* plan, const int8_t* cols_dev, int64_t pit
                            const double* mu_dev, double* nll_dev, void* stream);
 int theta_nll_tiles_n2(theta_plan* plan, const int8_t* cols_host, int64_t pitch, int64_t count, const double* mu_host,
                        double* nll_host);
+/* n=3 (Optimizer.L3, Optimizer.py:236-244; CalcAllC.L3, CalcAllC.py:63-76): one row-index byte per interval
+ * (index into theta_n3_rows(), the compact form of the m x 3 matrices of Enumerator._to_matrix), rows of
+ * `pitch` = theta_tile_pitch(m) bytes with zero padding; mu is [count][3].  Algorithmic bytes m + 24 + 8. */
+int theta_nll_rows_n3_dev(theta_plan* plan, const uint8_t* rows_dev, int64_t pitch, int64_t count, const double* mu_dev,
+                          double* nll_dev, void* stream);
+int theta_nll_rows_n3(theta_plan* plan, const uint8_t* rows_host, int64_t pitch, int64_t count, const double* mu_host,
+                      double* nll_host);
 
 /* ---- n = 3 (Enumerator._generate_next_C_3, Enumerator.py:172-298; Optimizer._solve_n3plus, Optimizer.py:128-165) ---- */
 /* Row table of the plan: rows[g] = (a_g, b_g) in the reference's order (first component fastest). */

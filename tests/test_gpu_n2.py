@@ -236,3 +236,78 @@ def test_fp32_bound_skip_is_sound(lib, monkeypatch):
         assert g0 == g1
         assert rec0.tobytes() == rec1.tobytes()
         plan.close()
+
+
+def test_config2_full_space_two_independent_paths(lib):
+    """BASELINE configs[1] at full size (25,251,156 candidates): the fused search (level-count enumeration, grouped
+    statistics, two passes) against the explicit pipeline (enumerate -> int8 tiles -> solve_tiles run-scan kernel)
+    over the WHOLE space on the device -- same solved count, same minimum, same arg-min, same tie list -- and the
+    winner re-evaluated by the CPU oracle."""
+    import torch
+    from theta_b200.search import search_n2, fold_replay
+    O = _oracle()
+    P = O.synthetic_problem_n2(150, 5, seed=1)
+    plan = lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"])
+    N = plan.count()
+    assert N == 25251156
+    res = search_n2(plan)
+    L = lib.load()
+    chunk = 1 << 22
+    pitch = plan.pitch
+    tiles = torch.empty(chunk * pitch, dtype=torch.int8, device="cuda")
+    mu = torch.empty(chunk, dtype=torch.float64, device="cuda")
+    nll = torch.empty(chunk, dtype=torch.float64, device="cuda")
+    st = torch.empty(chunk, dtype=torch.int32, device="cuda")
+    n_solved, best, near = 0, (float("inf"), -1), []
+    for b in range(0, N, chunk):
+        cnt = min(chunk, N - b)
+        lib.check(L.theta_enumerate_n2_dev(plan.handle, b, cnt, tiles.data_ptr(), pitch, None))
+        lib.check(L.theta_solve_tiles_n2_dev(plan.handle, tiles.data_ptr(), pitch, cnt, mu.data_ptr(), nll.data_ptr(),
+                                             st.data_ptr(), None))
+        ok = st[:cnt] < 8
+        n_solved += int(ok.sum())
+        v = torch.where(ok, nll[:cnt], torch.full_like(nll[:cnt], float("inf")))
+        m_, i_ = torch.min(v, dim=0)
+        if float(m_) < best[0]:
+            best = (float(m_), b + int(i_))
+        idx = torch.nonzero(v <= res.min_nll + 2.5e-3).flatten()
+        near += [(b + int(i), float(v[i])) for i in idx]
+    assert n_solved == res.n_solved
+    assert best[1] == res.best[0][0]
+    assert abs(best[0] - res.min_nll) <= 1e-13 * res.min_nll
+    assert sorted(r for r, _ in near) == sorted(set(int(r) for r, v in zip(res.records["rank"], res.records["nll"])
+                                                      if v <= res.min_nll + 2.5e-3))
+    col = plan.enumerate(best[1], 1)[0]
+    s = O.solve_n2(O.column_to_matrix(col), P["r"], P["rN"])
+    assert abs(s[0][0] - res.best[0][1]) <= MU_TOL
+    assert abs(s[1] - res.best[0][2]) <= NLL_RTOL * abs(s[1])
+    plan.close()
+
+
+def test_config3_rank_windows(lib):
+    """BASELINE configs[2] shape (m=300, k=7; 1.7e11 candidates): windows of the rank space searched by the fused
+    kernel == fold over every candidate of the window evaluated one by one; oracle spot checks."""
+    from theta_b200.search import fold_replay
+    O = _oracle()
+    P = O.synthetic_problem_n2(300, 7, seed=1)
+    plan = lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"])
+    N = plan.count()
+    assert N == O.count_n2(P["lower"], P["upper"]) and N > 10 ** 11
+    rng = np.random.default_rng(11)
+    for begin, cnt in ((0, 200000), (N // 3, 150001), (N - 77777, 77777)):
+        g = plan.pass1(begin, begin + cnt)
+        recs = plan.pass2(g)
+        cands, _ = plan.eval_ranks(np.arange(begin, begin + cnt, dtype=np.uint64), want_vals=False)
+        ok = cands["status"] < 8
+        full = fold_replay(cands["rank"][ok], cands["nll"][ok], dup_first=False)
+        sub = fold_replay(recs["rank"], recs["nll"], dup_first=False)
+        assert [int(cands["rank"][ok][i]) for i in full] == [int(recs["rank"][i]) for i in sub]
+        for i in rng.integers(0, cnt, 6):
+            col = plan.enumerate(begin + int(i), 1)[0]
+            s = O.solve_n2(O.column_to_matrix(col), P["r"], P["rN"])
+            if s is None:
+                assert cands["status"][i] >= 8
+            else:
+                assert abs(s[0][0] - cands["mu"][i][0]) <= MU_TOL
+                assert abs(s[1] - cands["nll"][i]) <= NLL_RTOL * abs(s[1])
+    plan.close()

@@ -159,3 +159,26 @@ def test_synthetic_configs_4_and_5(lib, golden):
         for q in recs[:n_chk]:
             assert list(first[q["index"]]) == q["path"], (name, q["index"])
         plan.close()
+
+
+def test_streaming_nll_kernel_n3(lib, golden):
+    """The streaming NLL kernel on row-index tiles (Optimizer.L3 at a given mu): against the live reference's
+    NLL at the reference's own mu for every regular candidate of the golden spaces, against the solver's own
+    NLL, and on a ragged batch (1, 31, 33 rows; sizes that end inside a TMA sub-tile)."""
+    for case in golden("n3_small_full.json.gz"):
+        plan = lib.Plan(3, case["r"], case["rN"], case["lower"], case["upper"])
+        gold = case["stream"][1:]
+        plan.prepare(4096)
+        paths = plan.enumerate_n3()
+        keep = [i for i, s in enumerate(gold) if s[2] is not None and not collinear(s[0])]
+        ref_mu = np.array([gold[i][1] for i in keep])
+        ref_nll = np.array([gold[i][2] for i in keep])
+        got = plan.nll_rows(paths[keep], ref_mu)
+        assert np.all(np.abs(got - ref_nll) <= 1e-10 * np.abs(ref_nll))
+        mu, mh, nll, st, _ = plan.solve_rows(paths[keep])
+        ok = (st < 8) & (st != lib.ST_DEGENERATE)
+        got2 = plan.nll_rows(paths[keep][ok], mu[ok])
+        assert np.allclose(got2, nll[ok], rtol=1e-13, atol=0)
+        for cnt in (1, 31, 33):
+            assert np.array_equal(plan.nll_rows(paths[keep][:cnt], ref_mu[:cnt]), got[:cnt])
+        plan.close()

@@ -87,6 +87,8 @@ SYMBOLS = {
     "theta_solve_tiles_n2": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP]),
     "theta_nll_tiles_n2_dev": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP]),
     "theta_nll_tiles_n2": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP]),
+    "theta_nll_rows_n3_dev": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP]),
+    "theta_nll_rows_n3": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP]),
     "theta_nll": (C.c_int, [C.c_int32, C.c_int32, _VP, _VP, _VP, C.POINTER(C.c_double), _VP, _VP]),
 }
 
@@ -266,6 +268,18 @@ class Plan(object):
             check(load().theta_solve_rows_n3(self._h, ptr(paths), cnt, ptr(mu), ptr(mh), ptr(nll), ptr(st),
                                              ptr(vals) if want_vals else None))
         return mu, mh, nll, st, vals
+
+    def nll_rows(self, paths, mu):
+        """Optimizer.L3 at given mu[count,3] on row-index strings [count, m] (streaming NLL kernel, n=3)."""
+        paths = np.asarray(paths, dtype=np.uint8)
+        cnt = paths.shape[0]
+        t = np.zeros((cnt, self.pitch), dtype=np.uint8)
+        t[:, :self.m] = paths
+        mu = np.ascontiguousarray(np.asarray(mu, dtype=np.float64).reshape(cnt, 3))
+        nll = np.zeros(cnt)
+        if cnt:
+            check(load().theta_nll_rows_n3(self._h, ptr(t), self.pitch, cnt, ptr(mu), ptr(nll)))
+        return nll
 
     def enumerate(self, rank_begin, count):
         """int8 [count, m] tumour columns of consecutive ranks (Enumerator.generate_next_C order)."""

@@ -118,6 +118,8 @@ __device__ __forceinline__ void n2_groups(const Tables& T, const int (&q)[KT], d
 struct theta_n3_state;  // theta_n3.cu
 int theta_n3_plan_init(theta_plan* pl);
 void theta_n3_plan_free(theta_plan* pl);
+// what the streaming NLL kernel needs from an n=3 plan: the row table and the problem constants
+int theta_n3_tile_info(const theta_plan* pl, uint8_t* ra, uint8_t* rb, int* n_rows, theta::N2Const* kc);
 
 // Host-side plan (opaque to C callers)
 struct theta_plan {

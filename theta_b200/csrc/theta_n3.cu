@@ -368,6 +368,32 @@ int theta_n3_plan_init(theta_plan* pl) {
     THETA_CUDA(cudaMemcpy(s->d_allow, s->allow.data(), sizeof(uint64_t) * m, cudaMemcpyHostToDevice));
     THETA_CUDA(cudaMemcpy(s->d_r, rd.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
     THETA_CUDA(cudaMemcpy(s->d_rN, rnd.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    {   // prefix sums of r / rN for the streaming NLL kernel (theta_tiles.cu), flat past m
+        const int64_t pitch = theta_tile_pitch(m);
+        pl->tile_pitch = pitch;
+        std::vector<double> P(2 * (pitch + 1), 0.0);
+        int64_t sr = 0, sn = 0;
+        for (int64_t i = 0; i < pitch; ++i) {
+            if (i < m) { sr += pl->r[i]; sn += pl->rN[i]; }
+            P[i + 1] = (double)sr; P[pitch + 1 + i + 1] = (double)sn;
+        }
+        THETA_CUDA(theta::dmalloc(&pl->d_arena, sizeof(double) * P.size()));
+        THETA_CUDA(cudaMemcpy(pl->d_arena, P.data(), sizeof(double) * P.size(), cudaMemcpyHostToDevice));
+        pl->d_PR = reinterpret_cast<double*>(pl->d_arena);
+        pl->d_PRN = pl->d_PR + (pitch + 1);
+        THETA_CUDA(theta::logtab_device(&pl->d_logtab));
+    }
+    return THETA_OK;
+}
+
+int theta_n3_tile_info(const theta_plan* pl, uint8_t* ra, uint8_t* rb, int* n_rows, theta::N2Const* kc) {
+    if (!pl || pl->n != 3 || !pl->n3) { set_error("plan is not n=3"); return THETA_ERR_INVALID; }
+    const theta_n3_state* s = pl->n3;
+    for (int g = 0; g < 64; ++g) { ra[g] = g < s->NR ? (uint8_t)s->ra[g] : 0; rb[g] = g < s->NR ? (uint8_t)s->rb[g] : 0; }
+    *n_rows = s->NR;
+    *kc = theta::N2Const{};
+    kc->A = s->kc.A; kc->S0 = s->kc.tau * s->kc.A; kc->Rtot = s->kc.Rtot; kc->K0 = s->kc.K0; kc->tau = s->kc.tau;
+    kc->max_normal = 1.0; kc->any_zero_rN = s->kc.any_zero_rN; kc->m = s->kc.m;
     return THETA_OK;
 }
 

@@ -63,6 +63,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 struct TileParams {
+    uint8_t ra[64], rb[64];  // n = 3 only: copy numbers (a, b) of row index g (Enumerator._create_graph order)
+    int n_rows;              // n = 3 only: number of valid row indices
     const double2* logtab;
     const int8_t* cols;
     int64_t pitch;
@@ -311,6 +313,7 @@ struct NllCfg {
         size_t o = sizeof(double2) * (size_t)(pitch + 1);
         o = (o + 127) & ~(size_t)127;
         o += sizeof(double2) * THETA_LOGTAB_SIZE;
+        o += sizeof(double2) * 64;  // (a, b) per row index (n = 3)
         o += (size_t)WARPS * STAGES * 32 * (size_t)pitch;
         return o + 32;  // slack: phase 1 of the last row may read up to 24 bytes past its end
     }
@@ -338,20 +341,34 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
 }
 
 // prp_s: shared-space address of the (PR, PRN) table (explicit ld.shared keeps the address arithmetic to one LEA)
-__device__ __forceinline__ double nll_row(const unsigned char* rp, int words, uint32_t prp_s,
-                                          const double2* __restrict__ LT, double mu, const N2Const& kc, double inv_A) {
+// N3 = false: byte = tumour copy number c_i, log argument tau mu + c (1 - mu)                (Optimizer.L2 / CalcAllC.L2)
+// N3 = true : byte = row index g_i -> (a, b), log argument tau mu0 + a mu1 + b mu2 with mu = (mu, mu1, mu2)
+//                                                                                (Optimizer.L3 / CalcAllC.L3)
+template <bool N3>
+__device__ __forceinline__ double nll_row(const unsigned char* rp, int words, uint32_t prp_s, uint32_t ab_s,
+                                          const double2* __restrict__ LT, double mu, double mu1, double mu2,
+                                          const N2Const& kc, double inv_A) {
     const uint2* rw = reinterpret_cast<const uint2*>(rp);
-    const double mu1 = 1.0 - mu;
     const double tm = kc.tau * mu;
-    double acc = 0.0, s1 = 0.0, pr_s = 0.0, prn_s = 0.0;
+    double acc = 0.0, s1 = 0.0, s2 = 0.0, pr_s = 0.0, prn_s = 0.0;
     uint32_t cur = rw[0].x & 0xffu;     // copy number of the open run
     uint32_t pat = cur * 0x01010101u;   // phase 1: last byte seen, replicated
     auto close_run = [&](uint32_t v, int e) {
         const double2 pp = lds_f64x2(prp_s + (uint32_t)e * 16u);
         const double wgt = pp.x - pr_s;
-        const double dv = (double)v;
-        s1 = fma(dv, pp.y - prn_s, s1);
-        if (wgt != 0.0) acc = fma(wgt, fast_log(fma(dv, mu1, tm), LT), acc);
+        double g;
+        if (N3) {
+            const double2 ab = lds_f64x2(ab_s + (v & 63u) * 16u);
+            const double dn = pp.y - prn_s;
+            s1 = fma(ab.x, dn, s1);
+            s2 = fma(ab.y, dn, s2);
+            g = fma(ab.x, mu1, fma(ab.y, mu2, tm));
+        } else {
+            const double dv = (double)v;
+            s1 = fma(dv, pp.y - prn_s, s1);
+            g = fma(dv, mu1, tm);
+        }
+        if (wgt != 0.0) acc = fma(wgt, fast_log(g, LT), acc);
         pr_s = pp.x;
         prn_s = pp.y;
     };
@@ -397,13 +414,13 @@ __device__ __forceinline__ double nll_row(const unsigned char* rp, int words, ui
         }
     }
     close_run(cur, kc.m);
-    const double gbar = (mu * kc.S0 + mu1 * s1) * inv_A;
+    const double gbar = (N3 ? fma(mu2, s2, fma(mu1, s1, mu * kc.S0)) : (mu * kc.S0 + mu1 * s1)) * inv_A;
     double nll = kc.K0 - (acc - kc.Rtot * fast_log(gbar, LT));
     if (kc.any_zero_rN) nll = INFINITY;
     return nll;
 }
 
-template <int WARPS, int STAGES, int MINB>
+template <int WARPS, int STAGES, int MINB, bool N3>
 __global__ void __launch_bounds__(WARPS * 32, MINB) nll_tiles_kernel(const TileParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[WARPS * STAGES];
@@ -412,12 +429,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nll_tiles_kernel(const TileP
     o = (o + 127) & ~(size_t)127;
     double2* LT = reinterpret_cast<double2*>(smem + o);
     o += sizeof(double2) * THETA_LOGTAB_SIZE;
+    double2* AB = reinterpret_cast<double2*>(smem + o);
+    o += sizeof(double2) * 64;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t slot_bytes = (size_t)32 * p.pitch;
     unsigned char* ring = smem + o + (size_t)warp * STAGES * slot_bytes;
     uint64_t* bar = bars + warp * STAGES;
     for (int i = tid; i <= p.pitch; i += WARPS * 32) PRP[i] = make_double2(p.PR[i], p.PRN[i]);
     for (int i = tid; i < THETA_LOGTAB_SIZE; i += WARPS * 32) LT[i] = p.logtab[i];
+    if (N3 && tid < 64)  // an invalid row index poisons the result instead of reading garbage
+        AB[tid] = tid < p.n_rows ? make_double2((double)p.ra[tid], (double)p.rb[tid]) : make_double2(NAN, NAN);
     if (tid == 0) {
         for (int s = 0; s < WARPS * STAGES; ++s) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -429,8 +450,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nll_tiles_kernel(const TileP
     const int64_t GW = (int64_t)gridDim.x * WARPS;
     const N2Const kc = p.kc;
     const double inv_A = 1.0 / kc.A;
-    uint32_t prp_s = smem_u32(PRP);
-    asm volatile("" : "+r"(prp_s));  // keep it in a register (the compiler otherwise re-derives it per run)
+    uint32_t prp_s = smem_u32(PRP), ab_s = smem_u32(AB);
+    asm volatile("" : "+r"(prp_s), "+r"(ab_s));  // keep them in registers (the compiler otherwise re-derives them per run)
     if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int s = 0; s < (STAGES > 1 ? STAGES - 1 : 1); ++s) {
@@ -444,7 +465,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nll_tiles_kernel(const TileP
         const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
         const int64_t row = t * 32 + lane;
         const bool live = row < p.count;
-        const double mu = live ? __ldg(p.mu_in + row) : 0.5;
+        double mu = 0.5, mu1 = 0.5, mu2 = 0.0;
+        if (live) {
+            if (N3) { mu = __ldg(p.mu_in + 3 * row); mu1 = __ldg(p.mu_in + 3 * row + 1); mu2 = __ldg(p.mu_in + 3 * row + 2); }
+            else { mu = __ldg(p.mu_in + row); mu1 = 1.0 - mu; }
+        }
         if (STAGES > 1) {
             __syncwarp();  // every lane is done with the slot about to be refilled
             if (lane == 0) {
@@ -458,7 +483,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nll_tiles_kernel(const TileP
         mbar_wait(&bar[slot], parity);
         __syncwarp();  // a hand-copied 8-byte tail (last sub-tile only) becomes visible to every lane
         double nll = 0.0;
-        if (live) nll = nll_row(ring + (size_t)slot * slot_bytes + (size_t)lane * p.pitch, words, prp_s, LT, mu, kc, inv_A);
+        if (live) nll = nll_row<N3>(ring + (size_t)slot * slot_bytes + (size_t)lane * p.pitch, words, prp_s, ab_s, LT, mu, mu1, mu2, kc, inv_A);
         if (STAGES == 1) {
             __syncwarp();
             if (lane == 0) {
@@ -475,11 +500,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nll_tiles_kernel(const TileP
 
 static int g_nll_variant = -1;  // THETA_NLL_VARIANT: 0 = 8 warps x 2 stages, 1 = 4 x 2, 2 = 8 x 1, 3 = 4 x 1, 4 = 16 x 1, 5/6 = 8 x 1 with a register cap
 
-template <int WARPS, int STAGES, int MINB>
+template <int WARPS, int STAGES, int MINB, bool N3 = false>
 static int launch_nll(const theta_plan* pl, const TileParams& tp, cudaStream_t st) {
     using Cfg = NllCfg<WARPS, STAGES>;
     const size_t smem = Cfg::smem_bytes(tp.pitch);
-    auto kern = nll_tiles_kernel<WARPS, STAGES, MINB>;
+    auto kern = nll_tiles_kernel<WARPS, STAGES, MINB, N3>;
     if (smem > 227 * 1024) { set_error("sub-tiles of 32 rows x %lld bytes do not fit shared memory", (long long)tp.pitch); return THETA_ERR_UNSUPPORTED; }
     THETA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = 1;
@@ -492,6 +517,11 @@ static int launch_nll(const theta_plan* pl, const TileParams& tp, cudaStream_t s
     kern<<<grid, Cfg::kThreads, smem, st>>>(tp);
     THETA_CUDA(cudaGetLastError());
     return THETA_OK;
+}
+
+int launch_nll_n3(const theta_plan* pl, const TileParams& tp, cudaStream_t st) {
+    if (NllCfg<16, 1>::smem_bytes(tp.pitch) > 227 * 1024) return launch_nll<4, 1, 8, true>(pl, tp, st);
+    return launch_nll<16, 1, 2, true>(pl, tp, st);
 }
 
 static int launch_nll_auto(const theta_plan* pl, const TileParams& tp, cudaStream_t st) {
@@ -559,6 +589,44 @@ extern "C" int theta_nll_tiles_n2_dev(theta_plan* pl, const int8_t* cols_dev, in
     tp.cols = cols_dev; tp.pitch = pitch; tp.count = count; tp.PR = pl->d_PR; tp.PRN = pl->d_PRN; tp.ZP = pl->d_ZP;
     tp.kc = pl->kc; tp.mu_in = mu_dev; tp.nll_out = nll_dev; tp.logtab = pl->d_logtab;
     return launch_nll_auto(pl, tp, st);  // asynchronous on `stream`
+}
+
+// n = 3: rows are row-index bytes (one per interval, pitch = theta_tile_pitch(m), padding 0), mu is [count][3]
+extern "C" int theta_nll_rows_n3_dev(theta_plan* pl, const uint8_t* rows_dev, int64_t pitch, int64_t count,
+                                     const double* mu_dev, double* nll_dev, void* stream) {
+    if (!pl || !rows_dev || !mu_dev || !nll_dev) { set_error("null argument"); return THETA_ERR_INVALID; }
+    TileParams tp{};
+    int rc = theta_n3_tile_info(pl, tp.ra, tp.rb, &tp.n_rows, &tp.kc);
+    if (rc) return rc;
+    if (count < 0) { set_error("negative count"); return THETA_ERR_INVALID; }
+    if (pl->m > 1023) { set_error("tile kernels support m <= 1023"); return THETA_ERR_UNSUPPORTED; }
+    if (pitch != pl->tile_pitch) {
+        set_error("pitch %lld invalid: tile kernels need theta_tile_pitch(m) = %lld", (long long)pitch, (long long)pl->tile_pitch);
+        return THETA_ERR_INVALID;
+    }
+    if (reinterpret_cast<uintptr_t>(rows_dev) & 15) { set_error("tile buffer must be 16-byte aligned"); return THETA_ERR_INVALID; }
+    if (count == 0) return THETA_OK;
+    tp.cols = reinterpret_cast<const int8_t*>(rows_dev); tp.pitch = pitch; tp.count = count;
+    tp.PR = pl->d_PR; tp.PRN = pl->d_PRN; tp.mu_in = mu_dev; tp.nll_out = nll_dev; tp.logtab = pl->d_logtab;
+    return launch_nll_n3(pl, tp, (cudaStream_t)stream);  // asynchronous on `stream`
+}
+
+extern "C" int theta_nll_rows_n3(theta_plan* pl, const uint8_t* rows_host, int64_t pitch, int64_t count,
+                                 const double* mu_host, double* nll_host) {
+    if (!pl || !rows_host || !mu_host || !nll_host) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (count <= 0) return THETA_OK;
+    uint8_t* d_c = nullptr; double *d_mu = nullptr, *d_nll = nullptr;
+    int rc = THETA_OK;
+    cudaError_t e = theta::dmalloc(&d_c, (size_t)count * pitch);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_mu, sizeof(double) * 3 * count);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_nll, sizeof(double) * count);
+    if (e == cudaSuccess) e = cudaMemcpy(d_c, rows_host, (size_t)count * pitch, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_mu, mu_host, sizeof(double) * 3 * count, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "nll_rows_n3 H2D", __FILE__, __LINE__);
+    if (rc == THETA_OK) rc = theta_nll_rows_n3_dev(pl, d_c, pitch, count, d_mu, d_nll, nullptr);
+    if (rc == THETA_OK) { e = cudaMemcpy(nll_host, d_nll, sizeof(double) * count, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = cuda_fail(e, "nll_rows_n3 D2H", __FILE__, __LINE__); }
+    theta::dfree(d_c); theta::dfree(d_mu); theta::dfree(d_nll);
+    return rc;
 }
 
 extern "C" int theta_solve_tiles_n2_dev(theta_plan* pl, const int8_t* cols_dev, int64_t pitch, int64_t count,
