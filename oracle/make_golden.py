@@ -265,6 +265,47 @@ def gen_config1_cli(R):
     print("wrote config1 CLI fixtures")
 
 
+def gen_cli_default_flow(R):
+    """The reference's own CLI beyond n=2 on the example data:
+      * -n 3 --RESULTS <config #1 n=2 files> --NUM_INTERVALS 8 (so that the reference's n=3 search finishes in
+        minutes), with and without --NO_MULTI_EVENT (CalcAllC.calc_all_c_3_multi_event / calc_all_c_3);
+      * ModelSelection on the n=2 / n=3 result files -> BEST.results;
+      * the default flow (no -n: n=2, n=3, ModelSelection in one call) with --NUM_INTERVALS 8 --FORCE."""
+    import shutil
+    src = os.path.join(GOLD, "Example.intervals")
+    out = "/tmp/theta_golden_flow"
+    shutil.rmtree(out, ignore_errors=True)
+    os.makedirs(out)
+    argv = sys.argv
+
+    def run(args):
+        sys.argv = ["RunTHetA.py"] + args
+        try:
+            with _quiet():
+                R.RunTHetA.main()
+        except SystemExit as e:
+            if e.code not in (0, None):
+                raise
+        finally:
+            sys.argv = argv
+    shutil.copy(os.path.join(GOLD, "config1_cli.n2.results"), os.path.join(out, "ex.n2.results"))
+    shutil.copy(os.path.join(GOLD, "config1_cli.n2.withBounds"), os.path.join(out, "ex.n2.withBounds"))
+    common = ["-n", "3", "-k", "3", "--NUM_INTERVALS", "8", "--NUM_PROCESSES", "1", "--RESULTS", os.path.join(out, "ex.n2.results"), "-d", out]
+    run([os.path.join(out, "ex.n2.withBounds")] + common + ["-p", "ex"])
+    run([os.path.join(out, "ex.n2.withBounds")] + common + ["--NO_MULTI_EVENT", "-p", "ex_nme"])
+    with _quiet():
+        R.ModelSelection.ModelSelection(src, os.path.join(out, "ex.n2.results"), os.path.join(out, "ex.n3.results"))
+    for f, g in (("ex.n3.results", "cli_n3.results"), ("ex.n3.withBounds", "cli_n3.withBounds"),
+                 ("ex_nme.n3.results", "cli_n3_nme.results"), ("ex_nme.n3.withBounds", "cli_n3_nme.withBounds"),
+                 ("ex.BEST.results", "cli_BEST.results")):
+        shutil.copy(os.path.join(out, f), os.path.join(GOLD, g))
+    print("wrote n=3 CLI fixtures")
+    run([src, "-k", "3", "--NUM_INTERVALS", "8", "--FORCE", "--NUM_PROCESSES", "1", "-d", out, "-p", "flow"])
+    for f in ("flow.n2.results", "flow.n2.withBounds", "flow.n3.results", "flow.n3.withBounds", "flow.BEST.results"):
+        shutil.copy(os.path.join(out, f), os.path.join(GOLD, "cli_" + f))
+    print("wrote default-flow CLI fixtures")
+
+
 def gen_edge(R):
     """Edge-case KATs from the live Optimizer.solve."""
     m = 7
@@ -319,6 +360,8 @@ def main():
         gen_config1(R)
     if "config1_cli" in todo:
         gen_config1_cli(R)
+    if "cli_flow" in todo:
+        gen_cli_default_flow(R)
 
 
 if __name__ == "__main__":

@@ -110,6 +110,8 @@ def modules():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         import Misc, Enumerator, Optimizer, CalcAllC, DataTools, TimeEstimate, SelectIntervals, FileIO, RunTHetA
+        import ModelSelection
     return types.SimpleNamespace(Misc=Misc, Enumerator=Enumerator, Optimizer=Optimizer,
                                  CalcAllC=CalcAllC, DataTools=DataTools, TimeEstimate=TimeEstimate,
-                                 SelectIntervals=SelectIntervals, FileIO=FileIO, RunTHetA=RunTHetA)
+                                 SelectIntervals=SelectIntervals, FileIO=FileIO, RunTHetA=RunTHetA,
+                                 ModelSelection=ModelSelection)

@@ -29,3 +29,32 @@ def test_find_mins_and_frac():
     assert pipeline.find_mins([a, b, c]) == c
     assert pipeline.find_mins([[], a]) == a
     assert abs(pipeline.determine_frac_copy_num([10, 10, 10, 10], [10, 10, 20, 10], [1, 1, 2, 1], 0.1) - 1.0) < 1e-12
+
+
+def test_model_selection_matches_reference(tmp_path):
+    """ModelSelection (python/ModelSelection.py:43-149) on the reference's own n=2 / n=3 result files of the example:
+    same choice, same BEST file."""
+    import os
+    import shutil
+    from theta_b200 import pipeline
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    shutil.copy(os.path.join(gold, "config1_cli.n2.results"), os.path.join(str(tmp_path), "ex.n2.results"))
+    shutil.copy(os.path.join(gold, "cli_n3.results"), os.path.join(str(tmp_path), "ex.n3.results"))
+    sel, path = pipeline.model_selection(os.path.join(gold, "Example.intervals"), os.path.join(str(tmp_path), "ex.n2.results"),
+                                         os.path.join(str(tmp_path), "ex.n3.results"))
+    with open(path) as f, open(os.path.join(gold, "cli_BEST.results")) as g:
+        assert f.read() == g.read()
+    assert path.endswith("ex.BEST.results")
+    # the criteria themselves
+    C = [[2, "2", "2"], [2, "3", "3"], [2, "1", "2"], [2, "X", "X"]]
+    assert pipeline.get_frac_breakdown(C, [10, 20, 30, 40]) == (0.1, 0.2, 0.3)
+    # a forced n=3 win: penalised NLL favours n=3 and the criteria hold
+    with open(os.path.join(str(tmp_path), "b.n2.results"), "w") as f:
+        f.write("#NLL\tmu\tC\tp*\n9e9\t0.5,0.5\t2:3\t0.5,0.5\n")
+    with open(os.path.join(str(tmp_path), "b.n3.results"), "w") as f:
+        f.write("#NLL\tmu\tC\tp*\n1e9\t0.4,0.3,0.3\t3,3:1,2\t0.5,0.5\n")
+    with open(os.path.join(str(tmp_path), "b.intervals"), "w") as f:
+        f.write("#ID\tchrm\tstart\tend\ttumorCount\tnormalCount\n1\t1\t0\t100\t10\t10\n2\t1\t100\t200\t10\t10\n")
+    sel, path = pipeline.model_selection(os.path.join(str(tmp_path), "b.intervals"), os.path.join(str(tmp_path), "b.n2.results"),
+                                         os.path.join(str(tmp_path), "b.n3.results"))
+    assert sel == 3 and open(path).read() == open(os.path.join(str(tmp_path), "b.n3.results")).read()

@@ -308,6 +308,127 @@ def calc_all_c_2(best, r, rN, all_tumor, all_normal, intervals_used):
     return out
 
 
+def _extend_setup(c, mu, r, rN, all_tumor, intervals_used):
+    """Common head of calc_all_c_3 / calc_all_c_3_multi_event (python/CalcAllC.py:149-167, 253-271)."""
+    m, n = c.shape
+    c_new = np.zeros((m + 1, n))
+    c_new[:m] = c
+    c_new = c_new * np.asarray(list(rN) + [0], dtype=np.float64)[:, None]  # weighted_C(c_new, rN + [0])
+    c_all = np.zeros((len(all_tumor), n))
+    for i, v in enumerate(intervals_used):
+        c_all[v] = c[i]
+    sum_all = sum([c_new[j][k] * mu[k] for j in range(m) for k in range(n)])
+    return m, n, c_new, c_all, sum_all, sum(r)
+
+
+def calc_all_c_3(best, r, rN, all_tumor, all_normal, intervals_used):
+    """python/CalcAllC.py:147-249 (--NO_MULTI_EVENT): for every interval left out of the n=3 search pick the row
+    among {(floor x, 2), (ceil x, 2), (2, floor y), (2, ceil y), (j, j) for j = 0, 1, ... until the NLL rises} with the
+    smallest L3 (ties resolved like the reference's list sort: by NLL, then by the row)."""
+    out = []
+    n_all = len(all_tumor)
+    used = set(intervals_used)
+    for c, mu, likelihood, vals in best:
+        m, n, c_new, c_all, sum_all, sum_r = _extend_setup(c, mu, r, rN, all_tumor, intervals_used)
+        for i in range(n_all):
+            if i in used:
+                continue
+            c_all[i][0] = 2
+            if all_normal[i] == 0:
+                c_all[i][1] = -1
+                c_all[i][2] = -1
+                continue
+            rr = list(r) + [all_tumor[i]]
+            cands = []
+            c_new[m][0] = 2 * all_normal[i]
+            c_new[m][2] = 2 * all_normal[i]
+            x = _calculate_x(all_tumor[i], all_normal[i], sum_r, sum_all, mu, n, [2, 0, 2], 1) / all_normal[i]
+            top, bot = int(max(0, math.ceil(x))), int(max(0, math.floor(x)))
+            c_new[m][1] = bot * all_normal[i]
+            x_bot = calc_all_c.L3(mu, c_new, m + 1, rr, n)[0]
+            c_new[m][1] = top * all_normal[i]
+            x_top = calc_all_c.L3(mu, c_new, m + 1, rr, n)[0]
+            cands.append((x_bot, [bot, 2]))
+            cands.append((x_top, [top, 2]))
+            y = _calculate_x(all_tumor[i], all_normal[i], sum_r, sum_all, mu, n, [2, 2, 0], 2) / all_normal[i]
+            top, bot = int(max(0, math.ceil(y))), int(max(0, math.floor(y)))
+            c_new[m][1] = 2 * all_normal[i]
+            c_new[m][2] = bot * all_normal[i]
+            y_bot = calc_all_c.L3(mu, c_new, m + 1, rr, n)[0]
+            c_new[m][2] = top * all_normal[i]
+            y_top = calc_all_c.L3(mu, c_new, m + 1, rr, n)[0]
+            cands.append((y_bot, [2, bot]))
+            cands.append((y_top, [2, top]))
+            prev = float("inf")
+            j = 0
+            while True:
+                c_new[m][1] = j * all_normal[i]
+                c_new[m][2] = j * all_normal[i]
+                l = calc_all_c.L3(mu, c_new, m + 1, rr, n)[0]
+                cands.append((l, [j, j]))
+                j += 1
+                if l > prev:
+                    break
+                prev = l
+            cands.sort()
+            c_all[i][1], c_all[i][2] = cands[0][1]
+        c_all_w = c_all * np.asarray(all_normal, dtype=np.float64)[:, None]
+        likelihood, vals = calc_all_c.L3(mu, c_all_w, n_all, all_tumor, n)
+        out.append([(c_all, mu, likelihood, vals)])
+    return out
+
+
+def calc_all_c_3_multi_event(best, r, rN, all_tumor, all_normal, intervals_used):
+    """python/CalcAllC.py:251-328 (default): for every interval left out of the n=3 search scan x = 0..ceil(x*) for the
+    first tumour population and floor/ceil of the conditional optimum for the second (kept on the same side of 2
+    as x), keeping the first strictly smaller L3."""
+    out = []
+    n_all = len(all_tumor)
+    used = set(intervals_used)
+    for c, mu, likelihood, vals in best:
+        m, n, c_new, c_all, sum_all, sum_r = _extend_setup(c, mu, r, rN, all_tumor, intervals_used)
+        for i in range(n_all):
+            if i in used:
+                continue
+            c_all[i][0] = 2
+            if all_normal[i] == 0:
+                c_all[i][1] = -1
+                c_all[i][2] = -1
+                continue
+            rr = list(r) + [all_tumor[i]]
+            w_x = _calculate_x(all_tumor[i], all_normal[i], sum_r, sum_all, mu, n, [2, 0, 0], 1)
+            max_x = math.ceil(w_x / all_normal[i])
+            c_new[m][0] = 2 * all_normal[i]
+            l_min = float("inf")
+            row_min = None
+            if max_x < 0:
+                max_x = 0
+            for x in range(int(max_x) + 1):
+                c_new[m][1] = x * all_normal[i]
+                y = _calculate_x(all_tumor[i], all_normal[i], sum_r, sum_all, mu, n, [2, x, 0], 2) / all_normal[i]
+                bot, top = int(max(0, math.floor(y))), int(max(0, math.ceil(y)))
+                if x < 2:
+                    bot, top = min(bot, 2), min(top, 2)
+                elif x > 2:
+                    bot, top = max(2, bot), max(2, top)
+                c_new[m][2] = bot * all_normal[i]
+                l_bot = calc_all_c.L3(mu, c_new, m + 1, rr, n)
+                if l_bot[0] < l_min:
+                    l_min = l_bot[0]
+                    row_min = [2, x, bot]
+                c_new[m][2] = top * all_normal[i]
+                l_top = calc_all_c.L3(mu, c_new, m + 1, rr, n)
+                if l_top[0] < l_min:
+                    l_min = l_top[0]
+                    row_min = [2, x, top]
+            c_all[i][1] = row_min[1]
+            c_all[i][2] = row_min[2]
+        c_all_w = c_all * np.asarray(all_normal, dtype=np.float64)[:, None]
+        likelihood, vals = calc_all_c.L3(mu, c_all_w, n_all, all_tumor, n)
+        out.append([(c_all, mu, likelihood, vals)])
+    return out
+
+
 def find_mins(best):
     """python/RunTHetA.py:107-122: merge per-solution lists, comparing only each list's first NLL (Misc.isClose)."""
     m_ = float("inf")
@@ -327,3 +448,96 @@ def find_mins(best):
 def best_near_max_contamination(best, max_normal):
     """python/RunTHetA.py:222-225."""
     return any(abs(max_normal - mu[0]) < .01 for _c, mu, _l, _v in best)
+
+
+# --------------------------------------------------------------------------- ModelSelection
+def load_results(filename, tau=2):
+    """python/FileIO.py:801-833: [(nll, C as lists of strings with tau prepended, mu)] of a .results file."""
+    with open(filename) as f:
+        lines = f.readlines()
+    if lines and lines[0].startswith("#"):
+        lines = lines[1:]
+    if len(lines) == 0:
+        sys.stderr.write("ERROR: The result file provided appears to be empty. Exiting...\n")
+        sys.exit(1)
+    results = []
+    for l in lines:
+        soln = l.strip().split("\t")
+        mu = [float(i) for i in soln[1].split(",")]
+        C = [[tau] + [i for i in row.split(",")] for row in soln[2].split(":")]
+        results.append((float(soln[0]), C, mu))
+    return results
+
+
+def get_frac_breakdown(C, lengths):
+    """python/ModelSelection.py:151-188: genome fractions with no aberration / clonal / subclonal aberrations."""
+    tot_len = tot_norm = tot_clonal = tot_subclonal = 0
+    for i, row in enumerate(C):
+        cur = lengths[i]
+        tot_len += cur
+        row_str = [str(x) for x in row[1:]]
+        if all(v == "X" for v in row_str):
+            continue
+        elif all(v == "2" for v in row_str):
+            tot_norm += cur
+        elif all(v == row_str[0] for v in row_str):
+            tot_clonal += cur
+        else:
+            tot_subclonal += cur
+    return float(tot_norm) / float(tot_len), float(tot_clonal) / float(tot_len), float(tot_subclonal) / float(tot_len)
+
+
+def additional_criteria(n2_result, n3_result, input_file, min_pop=0.05, min_clonal=0.0, max_ratio=5, min_ratio=0.05):
+    """python/ModelSelection.py:109-149: n=3 is kept only if one of its solutions has all tumour populations above
+    min_pop, some clonal aberration, and a subclonal/clonal length ratio within [min_ratio, max_ratio)."""
+    lengths = read_interval_file(input_file)[0]
+    is_valid = False
+    for _nll, C, mu in load_results(n3_result):
+        _no_cna, clonal, subclonal = get_frac_breakdown(C, lengths)
+        pop_is_big = all(i > min_pop for i in mu[1:])
+        clonal_is_big = clonal > min_clonal
+        small_enough, big_enough = False, True
+        if clonal > 0:
+            ratio = float(subclonal) / float(clonal)
+            small_enough = ratio < max_ratio
+            if ratio < min_ratio:
+                big_enough = False
+        if pop_is_big and clonal_is_big and small_enough and big_enough:
+            is_valid = True
+    return (3, n3_result) if is_valid else (2, n2_result)
+
+
+def _min_nll(path):
+    best = float("inf")
+    with open(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            best = min(best, float(line.strip().split("\t")[0]))
+    return best
+
+
+def model_selection(input_file, n2_result, n3_result):
+    """python/ModelSelection.py:43-107: penalised NLL  2 L + (m+1)(n-1) log(T+N)  decides between the n=2 and the n=3
+    result files; the winner is copied to <prefix>.BEST.results."""
+    num_tumor = num_normal = num_intervals = 0
+    with open(input_file) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            tumor, normal = line.strip().split("\t")[4:6]
+            if int(normal) > 0:
+                num_tumor += int(tumor)
+                num_normal += int(normal)
+                num_intervals += 1
+    p2 = 2 * _min_nll(n2_result) + (num_intervals + 1) * math.log(num_tumor + num_normal)
+    p3 = 2 * _min_nll(n3_result) + (num_intervals + 1) * 2 * math.log(num_tumor + num_normal)
+    selected_num, selected_res = 2, n2_result
+    if p3 <= p2:
+        selected_num, selected_res = additional_criteria(n2_result, n3_result, input_file)
+    filename = selected_res.replace(".n" + str(selected_num) + ".results", ".BEST.results")
+    print("Selected n=" + str(selected_num) + " solution.  Writing to", filename)
+    with open(filename, "w") as out, open(selected_res) as src:
+        for line in src:
+            out.write(line)
+    return selected_num, filename

@@ -5,7 +5,8 @@
            [--HEURISTIC_LB LB] [--HEURISTIC_UB UB] [--BOUNDS_ONLY] [--NO_MULTI_EVENT] [--RESULTS file] [--FORCE]
            [--GET_VALUES] [--NO_INTERVAL_SELECTION] [--RATIO_DEV x] [--MIN_FRAC x]
 
-Same flags, same <prefix>.n<N>.withBounds / <prefix>.n<N>.results / <prefix>.RunN3.bash outputs.  Differences,
+Same flags, same <prefix>.n<N>.withBounds / <prefix>.n<N>.results / <prefix>.RunN3.bash / <prefix>.BEST.results
+outputs; without -n the reference's default flow (n=2, n=3 seeded by the n=2 files, ModelSelection).  Differences,
 all outside the search path: K may be 0..7 (the reference's parser stops at 6 although it says 0-7, Q4);
 bounds read from the file are integers (Q11); floats print with Python-3 repr (Q12); the CPU timing loop of
 TimeEstimate is replaced by the exact candidate count; plotting, the BAF model and SNP clustering are not
@@ -145,8 +146,12 @@ def run_fixed_N(n, a, intervals, resultsfile=None, argv=None):
             best = pipeline.calc_all_c_2(best, r, rN, all_tumor, all_normal, order)
             best = pipeline.find_mins(best)
         else:
-            raise NotImplementedError("n=3 with automatic interval selection needs CalcAllC.calc_all_c_3* "
-                                      "(SURVEY 8f row f1, not built yet); run with --NO_INTERVAL_SELECTION")
+            # RunTHetA.py:470-474: --NO_MULTI_EVENT only selects which extension routine runs (Q3)
+            if a.NO_MULTI_EVENT:
+                best = pipeline.calc_all_c_3(best, r, rN, all_tumor, all_normal, order)
+            else:
+                best = pipeline.calc_all_c_3_multi_event(best, r, rN, all_tumor, all_normal, order)
+            best = pipeline.find_mins(best)
     resultsfile = pipeline.write_out_result(directory, prefix, best, n)
     if n == 2:
         pipeline.write_out_N3_script(directory, prefix, a.QUERY_FILE, argv)
@@ -159,10 +164,12 @@ def main(argv=None):
     intervals = pipeline.read_interval_file(a.QUERY_FILE)
     full_argv = ["RunTHetA.py"] + list(argv if argv is not None else sys.argv[1:])
     if a.N is None:
-        # RunTHetA.py:291-295 runs n=2, then n=3 from its outputs, then ModelSelection (out of scope here)
+        # RunTHetA.py:291-295: n=2, then n=3 seeded by the n=2 bounds / results files, then ModelSelection
         res2, bounds2 = run_fixed_N(2, a, intervals, argv=full_argv)
-        print("n=2 finished; run the generated RunN3.bash for n=3 (model selection is not part of this build)")
-        return res2, bounds2
+        intervals = pipeline.read_interval_file(bounds2)
+        res3, bounds3 = run_fixed_N(3, a, intervals, res2, argv=full_argv)
+        pipeline.model_selection(a.QUERY_FILE, res2, res3)
+        return res3, bounds3
     return run_fixed_N(a.N, a, intervals, a.RESULTS, argv=full_argv)
 
 
