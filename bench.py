@@ -234,9 +234,9 @@ def main():
     launches = [0]
 
     def step():
-        g, _lm = search.pass1_allreduce(plan, begin, end, D, world, stream)  # search kernel + min reduction [+ NCCL]
-        recs = plan.pass2(g, float("inf"), stream)
-        launches[0] += 2 + (1 if plan.stats()["n_rescanned"] else 0)
+        # search kernel, min reduction [, NCCL all-reduce], stripe scan, emit kernel -- one host synchronisation
+        recs, g = search.search_shard(plan, begin, end, D, world, stream)
+        launches[0] += 4
         return search.gather_records(recs, D, world), g
 
     def barrier():
@@ -363,8 +363,8 @@ def main():
         b7, e7 = search.shard_range(n7, rank, world)
 
         def step7():
-            g_, _ = search.pass1_allreduce(plan7, b7, e7, D, world, stream)
-            return search.gather_records(plan7.pass2(g_, float("inf"), stream), D, world), g_
+            r_, g_ = search.search_shard(plan7, b7, e7, D, world, stream)
+            return search.gather_records(r_, D, world), g_
         for _ in range(2):
             step7()
         barrier()

@@ -141,6 +141,12 @@ int theta_search_n2_pass1_end(theta_plan* plan, double* local_min);
  * every strict prefix minimum and every candidate with NLL <= global_min + 2*margin. */
 int theta_search_n2_pass2(theta_plan* plan, double global_min, double prior_min, theta_cand* out_host, uint64_t cap,
                           uint64_t* n_out, void* stream);
+/* The same with the global minimum read from DEVICE memory (NULL: this shard's own minimum), so that nothing
+ * returns to the host between pass 1, the all-reduce(min) and pass 2: the stripe list is built by a device-side
+ * prefix-min scan, the emit kernel is launched behind it and the host waits once.  Completes a pending
+ * theta_search_n2_pass1_begin (no _end needed); *global_min_host receives the value that was used. */
+int theta_search_n2_pass2_dev(theta_plan* plan, const double* global_min_dev, double prior_min, theta_cand* out_host,
+                              uint64_t cap, uint64_t* n_out, double* global_min_host, void* stream);
 int theta_search_stats_get(const theta_plan* plan, theta_search_stats* stats);
 /* Single-shard convenience: pass1 + pass2 with global_min = local_min, prior_min = +inf. */
 int theta_search_n2(theta_plan* plan, uint64_t rank_begin, uint64_t rank_end, theta_cand* out_host, uint64_t cap,

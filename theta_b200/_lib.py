@@ -80,6 +80,8 @@ SYMBOLS = {
     "theta_search_n2_pass1_begin": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, _VP]),
     "theta_search_n2_pass1_end": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "theta_search_n2_pass2": (C.c_int, [_VP, C.c_double, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP]),
+    "theta_search_n2_pass2_dev": (C.c_int, [_VP, _VP, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64),
+                                            C.POINTER(C.c_double), _VP]),
     "theta_search_stats_get": (C.c_int, [_VP, C.POINTER(SearchStats)]),
     "theta_search_n2": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
     "theta_eval_ranks_n2": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
@@ -312,6 +314,22 @@ class Plan(object):
                 continue
             check(rc)
             return buf[:int(n.value)]
+
+    def pass2_dev(self, global_min_dev=None, prior_min=float("inf"), stream=None):
+        """Pass 2 with the global minimum taken from device memory (None: this shard's own); also completes a
+        pending pass1_begin.  Returns (records, global_min)."""
+        cap = 1 << 10
+        while True:
+            buf = np.empty(cap, dtype=CAND_DTYPE)
+            n = C.c_uint64()
+            g = C.c_double()
+            rc = load().theta_search_n2_pass2_dev(self._h, global_min_dev, float(prior_min), ptr(buf), cap, C.byref(n),
+                                                  C.byref(g), stream)
+            if rc == ERR_OVERFLOW and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            check(rc)
+            return buf[:int(n.value)], float(g.value)
 
     def stats(self):
         s = SearchStats()

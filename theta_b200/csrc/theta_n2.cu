@@ -16,6 +16,10 @@ namespace theta {
 
 static constexpr int kBlock = 128;
 static constexpr int kCounters = 8;
+// device status block (u64 words): [0..7] pass-1 counters, [8..15] pass-2 counters, [16] listed stripes,
+// [17] shard minimum (double bits), [18] global minimum used by pass 2 (double bits)
+static constexpr int kStatusWords = 32;
+static constexpr int kStList = 16, kStLocalMin = 17, kStGlobalMin = 18;
 
 struct SearchParams {
     const double2* logtab;
@@ -26,12 +30,15 @@ struct SearchParams {
     int L;               // ranks per lane in one stripe (a stripe = 32 * L consecutive ranks, one warp)
     int Lrun;            // ranks per lane in one work unit (pass 1: L; pass 2: a few, for latency)
     int units_per_item;  // ceil(L / Lrun)
-    uint32_t n_items;    // stripes (pass 1) or listed stripes (pass 2)
+    uint32_t n_items;    // stripes (pass 1); pass 2 reads the number of listed stripes from n_items_dev
+    const unsigned long long* n_items_dev;
     double* stripe_min;
     unsigned long long* counters;
     const uint32_t* stripe_list;
     const double* stripe_prior;
     double near_thr;
+    const unsigned long long* near_thr_base;  // pass 2: global minimum (double bits) in device memory ...
+    double near_margin;                       // ... near_thr = that + near_margin
     theta_cand* emit;
     unsigned long long emit_cap;
     int verify;  // THETA_VERIFY_APPROX=1: evaluate every candidate exactly and count violations of the fp32 error bound
@@ -64,6 +71,10 @@ template <int KT, bool EMIT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double2 s_logtab[THETA_LOGTAB_SIZE];
+    // pass 2 is launched before the host knows how many stripes were listed (no host round trip between the
+    // passes): the count is read from device memory and surplus CTAs leave before staging anything
+    const unsigned long long n_units = (unsigned long long)(EMIT ? (uint32_t)*p.n_items_dev : p.n_items) * p.units_per_item;
+    if (EMIT && (unsigned long long)blockIdx.x * (kBlock / 32) >= n_units) return;
     for (int i = threadIdx.x; i < THETA_LOGTAB_SIZE; i += blockDim.x) s_logtab[i] = p.logtab[i];
     stage_tables(smem, p.tables, p.layout.bytes);
     Tables T_;
@@ -71,7 +82,6 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
     const N2Const kc = p.kc;
     const int lane = threadIdx.x & 31;
     unsigned long long solved = 0, iters = 0, nan_nll = 0, n_exact = 0, n_viol = 0;
-    const unsigned long long n_units = (unsigned long long)p.n_items * p.units_per_item;
     // Pass 1 proves most candidates irrelevant with the fp32-log NLL (n2_l2_approx): a candidate whose lower
     // bound exceeds T + margin -- T = the best exact NLL this warp has seen in this or an earlier (lower-rank)
     // stripe -- is neither the stripe minimum that matters (a strict prefix minimum of the stream is below
@@ -79,6 +89,7 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
     const double approx_E = THETA_APPROX_C * kc.Rtot;
     const double approx_margin = 3.0 * THETA_TIE_MARGIN;
     const double inv_A = 1.0 / kc.A;
+    const double near_thr = EMIT ? __longlong_as_double((long long)*p.near_thr_base) + p.near_margin : 0.0;
     double T = INFINITY;
 
     for (;;) {
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
                             ++nan_nll;
                             emit = true;  // isClose(nan, x) is True: a NaN NLL is always appended (Q6)
                         } else {
-                            if (EMIT) emit = (nll <= p.near_thr) || (nll < prior && nll < tmin);
+                            if (EMIT) emit = (nll <= near_thr) || (nll < prior && nll < tmin);
                             tmin = fmin(tmin, nll);
                             T = fmin(T, nll);
                         }
@@ -311,7 +322,7 @@ static int launch_search_v(const theta_plan* plan, const SearchParams& sp, cudaS
     int bps = 1;
     int rc = config_kernel(n2_search_kernel<KT, EMIT, MINB>, plan->layout.bytes, &bps);
     if (rc) return rc;
-    const uint64_t units = (uint64_t)sp.n_items * sp.units_per_item;
+    const uint64_t units = (uint64_t)sp.n_items * sp.units_per_item;  // pass 2: n_items = upper bound (all stripes)
     const uint32_t grid = (uint32_t)std::min<uint64_t>((units + kBlock / 32 - 1) / (kBlock / 32), (uint64_t)sm_count(plan->device) * bps);
     if (grid == 0) return THETA_OK;
     n2_search_kernel<KT, EMIT, MINB><<<grid, kBlock, plan->layout.bytes, st>>>(sp);
@@ -448,7 +459,7 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
     const size_t o_PR = o;  o = up256(o + sizeof(double) * (pitch + 1));
     const size_t o_PRN = o; o = up256(o + sizeof(double) * (pitch + 1));
     const size_t o_ZP = o;  o = up256(o + sizeof(int32_t) * (pitch + 1));
-    const size_t o_ctr = o; o = up256(o + sizeof(unsigned long long) * kCounters);
+    const size_t o_ctr = o; o = up256(o + sizeof(unsigned long long) * kStatusWords);
     const size_t arena_bytes = o;
     unsigned char* stage = nullptr;
     cudaError_t e = theta::hmalloc(&stage, arena_bytes);
@@ -498,8 +509,8 @@ extern "C" void theta_plan_destroy(theta_plan* pl) {
     theta::dfree(pl->d_arena);  // tables, r, rN, PR, PRN, ZP, counters (d_logtab is the per-device table: not owned)
     theta::dfree(pl->d_stripe_min); theta::dfree(pl->d_emit);
     theta::dfree(pl->d_list); theta::dfree(pl->d_prior);
-    theta::hfree(pl->h_stripe_min); theta::hfree(pl->h_emit); theta::hfree(pl->h_list); theta::hfree(pl->h_ctr);
-    if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
+    theta::hfree(pl->h_emit); theta::hfree(pl->h_ctr);
+    if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); cudaEventDestroy(pl->ev2); cudaEventDestroy(pl->ev3); }
     delete pl;
 }
 
@@ -558,8 +569,10 @@ extern "C" int theta_enumerate_n2(theta_plan* pl, uint64_t rank_begin, int64_t c
 
 // ======================================================================= search
 namespace theta {
-// min over the stripe minima -> one double in device memory (the operand of the NCCL all-reduce(min))
-__global__ void __launch_bounds__(1024) stripe_min_reduce_kernel(const double* __restrict__ v, uint64_t n, double* out0, double* out1) {
+// min over the stripe minima -> the shard minimum in the status block (and in the caller's device double: the
+// operand of the NCCL all-reduce(min))
+__global__ void __launch_bounds__(1024) stripe_min_reduce_kernel(const double* __restrict__ v, uint64_t n,
+                                                                 unsigned long long* status, double* out1) {
     __shared__ double s_w[32];
     double m = INFINITY;
     for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmin(m, v[i]);
@@ -568,18 +581,84 @@ __global__ void __launch_bounds__(1024) stripe_min_reduce_kernel(const double* _
     __syncthreads();
     if (threadIdx.x < 32) {
         m = warp_min(s_w[threadIdx.x]);
-        if (threadIdx.x == 0) { *out0 = m; if (out1) *out1 = m; }
+        if (threadIdx.x == 0) {
+            status[kStLocalMin] = (unsigned long long)__double_as_longlong(m);
+            if (out1) *out1 = m;
+        }
     }
+}
+
+// Which stripes can matter (RunTHetA.py:198-206): those that hold a strict prefix minimum of the NLL stream (every
+// reset of the reference fold is one) or a candidate within two margins of the global minimum (every member of
+// the final tie list is).  One block: exclusive prefix-min scan over the stripe minima, unordered append.
+__global__ void __launch_bounds__(1024) stripe_scan_kernel(const double* __restrict__ v, uint64_t n,
+                                                           const double* __restrict__ gmin_dev, double prior_min,
+                                                           double margin, unsigned long long* status,
+                                                           uint32_t* __restrict__ list, double* __restrict__ prior) {
+    __shared__ double s_w[32];
+    __shared__ double s_carry;
+    __shared__ unsigned int s_count;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double g = gmin_dev ? *gmin_dev : __longlong_as_double((long long)status[kStLocalMin]);
+    const double near_thr = g + margin;
+    const bool any_nan = status[4] != 0ULL;  // a NaN NLL is always appended (Q6): every stripe is re-walked
+    if (tid == 0) { s_carry = prior_min; s_count = 0u; }
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += 1024) {
+        const uint64_t i = base + tid;
+        const double x = i < n ? v[i] : INFINITY;
+        double incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl = fmin(incl, y);
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            double w = s_w[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w = fmin(w, y);
+            }
+            s_w[lane] = w;
+        }
+        __syncthreads();
+        const double carry = s_carry;
+        double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) prev = INFINITY;
+        const double P = fmin(carry, fmin(warp > 0 ? s_w[warp - 1] : INFINITY, prev));  // min of everything before stripe i
+        if (i < n) {
+            const bool rec = x < P, near = x <= near_thr;
+            if (rec || near || any_nan) {
+                const unsigned int slot = atomicAdd(&s_count, 1u);
+                list[slot] = (uint32_t)i;
+                prior[slot] = rec ? P : -INFINITY;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_carry = fmin(carry, s_w[31]);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        status[kStList] = s_count;
+        status[kStGlobalMin] = (unsigned long long)__double_as_longlong(g);
+    }
+    if (tid < kCounters) status[kCounters + tid] = 0ULL;  // pass-2 counters
 }
 }  // namespace theta
 
 static int plan_events(theta_plan* pl) {
-    if (!pl->ev0) { THETA_CUDA(cudaEventCreate(&pl->ev0)); THETA_CUDA(cudaEventCreate(&pl->ev1)); }
-    if (!pl->h_ctr) THETA_CUDA(theta::hmalloc(&pl->h_ctr, sizeof(unsigned long long) * 2 * kCounters + sizeof(double)));
+    if (!pl->ev0) {
+        THETA_CUDA(cudaEventCreate(&pl->ev0)); THETA_CUDA(cudaEventCreate(&pl->ev1));
+        THETA_CUDA(cudaEventCreate(&pl->ev2)); THETA_CUDA(cudaEventCreate(&pl->ev3));
+    }
+    if (!pl->h_ctr) THETA_CUDA(theta::hmalloc(&pl->h_ctr, sizeof(unsigned long long) * kStatusWords));
     return THETA_OK;
 }
 
-// Pass 1, asynchronous part: everything is enqueued on `stream` and nothing is waited for, so the caller can
+// Pass 1, asynchronous: everything is enqueued on `stream` and nothing is waited for, so the caller can
 // enqueue the NCCL all-reduce(min) on `local_min_dev` right behind it.
 extern "C" int theta_search_n2_pass1_begin(theta_plan* pl, uint64_t rank_begin, uint64_t rank_end, double* local_min_dev,
                                            void* stream) {
@@ -605,13 +684,14 @@ extern "C" int theta_search_n2_pass1_begin(theta_plan* pl, uint64_t rank_begin, 
     const uint64_t stripes = (N + L * 32 - 1) / (L * 32);
     pl->p1_stripes = stripes;
     if (stripes + 1 > pl->stripe_cap) {
-        theta::dfree(pl->d_stripe_min); theta::hfree(pl->h_stripe_min);
-        pl->d_stripe_min = nullptr; pl->h_stripe_min = nullptr; pl->stripe_cap = 0;
+        theta::dfree(pl->d_stripe_min); theta::dfree(pl->d_list); theta::dfree(pl->d_prior);
+        pl->d_stripe_min = nullptr; pl->d_list = nullptr; pl->d_prior = nullptr; pl->stripe_cap = 0;
         THETA_CUDA(theta::dmalloc(&pl->d_stripe_min, sizeof(double) * (stripes + 1)));
-        THETA_CUDA(theta::hmalloc(&pl->h_stripe_min, sizeof(double) * (stripes + 1)));
+        THETA_CUDA(theta::dmalloc(&pl->d_list, sizeof(uint32_t) * (stripes + 1)));
+        THETA_CUDA(theta::dmalloc(&pl->d_prior, sizeof(double) * (stripes + 1)));
         pl->stripe_cap = stripes + 1;
     }
-    THETA_CUDA(cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kCounters, st));
+    THETA_CUDA(cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kStatusWords, st));
     THETA_CUDA(cudaEventRecord(pl->ev0, st));
     if (N) {
         SearchParams sp{};
@@ -626,30 +706,33 @@ extern "C" int theta_search_n2_pass1_begin(theta_plan* pl, uint64_t rank_begin, 
         THETA_KT_DISPATCH(pl->KT, { int rc2 = launch_search<KT, false>(pl, sp, st); if (rc2) return rc2; });
     }
     THETA_CUDA(cudaEventRecord(pl->ev1, st));
-    // slot [stripes] of the stripe table receives the shard minimum (and so does the caller's device double)
-    stripe_min_reduce_kernel<<<1, 1024, 0, st>>>(pl->d_stripe_min, stripes, pl->d_stripe_min + stripes, local_min_dev);
+    stripe_min_reduce_kernel<<<1, 1024, 0, st>>>(pl->d_stripe_min, stripes, pl->d_counters, local_min_dev);
     THETA_CUDA(cudaGetLastError());
-    THETA_CUDA(cudaMemcpyAsync(pl->h_stripe_min, pl->d_stripe_min, sizeof(double) * (stripes + 1), cudaMemcpyDeviceToHost, st));
-    THETA_CUDA(cudaMemcpyAsync(pl->h_ctr, pl->d_counters, sizeof(unsigned long long) * kCounters, cudaMemcpyDeviceToHost, st));
     return THETA_OK;
+}
+
+static void read_pass1_stats(theta_plan* pl) {
+    const unsigned long long* ctr = pl->h_ctr;
+    cudaEventElapsedTime(&pl->stats.ms_pass1, pl->ev0, pl->ev1);
+    double g;
+    std::memcpy(&g, &ctr[kStLocalMin], sizeof(double));
+    pl->stats.n_solved = ctr[1];
+    pl->stats.n_stripes = pl->p1_stripes;
+    pl->stats.newton_iters = ctr[1] ? (double)ctr[2] / (double)ctr[1] : 0.0;
+    pl->stats.min_nll = g;
+    pl->stats.n_exact = ctr[5];
+    pl->stats.n_bound_violations = ctr[6];
 }
 
 extern "C" int theta_search_n2_pass1_end(theta_plan* pl, double* local_min) {
     if (!pl || !local_min) { set_error("null argument"); return THETA_ERR_INVALID; }
     if (!pl->p1_pending) { set_error("pass1_end without pass1_begin"); return THETA_ERR_INVALID; }
     pl->p1_pending = false;
-    THETA_CUDA(cudaStreamSynchronize((cudaStream_t)pl->p1_stream));
-    cudaEventElapsedTime(&pl->stats.ms_pass1, pl->ev0, pl->ev1);
-    const unsigned long long* ctr = pl->h_ctr;
-    const double g = pl->h_stripe_min[pl->p1_stripes];
-    pl->stats.n_solved = ctr[1];
-    pl->stats.n_stripes = pl->p1_stripes;
-    pl->stats.newton_iters = ctr[1] ? (double)ctr[2] / (double)ctr[1] : 0.0;
-    pl->stats.min_nll = g;
-    pl->stats.n_rescanned = ctr[4];  // provisional: number of NaN-NLL candidates, consumed by pass 2
-    pl->stats.n_exact = ctr[5];
-    pl->stats.n_bound_violations = ctr[6];
-    *local_min = g;
+    cudaStream_t st = (cudaStream_t)pl->p1_stream;
+    THETA_CUDA(cudaMemcpyAsync(pl->h_ctr, pl->d_counters, sizeof(unsigned long long) * kStatusWords, cudaMemcpyDeviceToHost, st));
+    THETA_CUDA(cudaStreamSynchronize(st));
+    read_pass1_stats(pl);
+    *local_min = pl->stats.min_nll;
     return THETA_OK;
 }
 
@@ -662,58 +745,22 @@ extern "C" int theta_search_n2_pass1(theta_plan* pl, uint64_t rank_begin, uint64
     return theta_search_n2_pass1_end(pl, local_min);
 }
 
-extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double prior_min, theta_cand* out_host,
-                                     uint64_t cap, uint64_t* n_out, void* stream) {
+// Pass 2 without a host round trip: the stripe list is built on the device from the stripe minima and the
+// global minimum in `global_min_dev` (NULL: this shard's own minimum), the emit kernel is launched behind it,
+// and the host waits once, at the end.  Also completes a pending pass1_begin.
+extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_min_dev, double prior_min, theta_cand* out_host,
+                                         uint64_t cap, uint64_t* n_out, double* global_min_host, void* stream) {
     if (!pl || !n_out) { set_error("null argument"); return THETA_ERR_INVALID; }
     *n_out = 0;
-    if (pl->p1_pending) { set_error("pass2 before pass1_end"); return THETA_ERR_INVALID; }
+    if (pl->n != 2 || !pl->ev0) { set_error("pass2 without pass1"); return THETA_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t stripes = pl->p1_stripes;
-    const bool any_nan = pl->stats.n_rescanned != 0;
-    pl->stats.n_rescanned = 0;
-    if (stripes == 0 || pl->p1_begin == pl->p1_end) return THETA_OK;
-    // A stripe matters if it holds a strict prefix minimum of the NLL stream (every reset of the
-    // reference fold is one, RunTHetA.py:203-206) or a candidate within two margins of the global minimum
-    // (every member of the final tie list is, RunTHetA.py:199-202).
-    const double near_thr = global_min + 2.5 * THETA_TIE_MARGIN;
-    size_t n_list = 0;
-    {
-        double P = prior_min;
-        for (uint64_t s = 0; s < stripes; ++s) {
-            const double v = pl->h_stripe_min[s];
-            if (v < P || v <= near_thr || any_nan) ++n_list;
-            if (v < P) P = v;
-        }
-    }
-    pl->stats.n_rescanned = n_list;
-    if (n_list == 0) return THETA_OK;
-    if (n_list > pl->list_cap) {
-        theta::dfree(pl->d_list); theta::dfree(pl->d_prior); theta::hfree(pl->h_list);
-        pl->d_list = nullptr; pl->d_prior = nullptr; pl->h_list = nullptr; pl->list_cap = 0;
-        const size_t want_l = std::max<size_t>(1024, n_list * 2);
-        THETA_CUDA(theta::dmalloc(&pl->d_list, sizeof(uint32_t) * want_l));
-        THETA_CUDA(theta::dmalloc(&pl->d_prior, sizeof(double) * want_l));
-        THETA_CUDA(theta::hmalloc(&pl->h_list, (sizeof(uint32_t) + sizeof(double)) * want_l));
-        pl->list_cap = want_l;
-    }
-    double* h_prior = reinterpret_cast<double*>(pl->h_list);
-    uint32_t* h_list = reinterpret_cast<uint32_t*>(pl->h_list + sizeof(double) * pl->list_cap);
-    {
-        double P = prior_min;
-        size_t w = 0;
-        for (uint64_t s = 0; s < stripes; ++s) {
-            const double v = pl->h_stripe_min[s];
-            const bool rec = v < P, near = v <= near_thr;
-            if (rec || near || any_nan) { h_list[w] = (uint32_t)s; h_prior[w] = rec ? P : -INFINITY; ++w; }
-            if (v < P) P = v;
-        }
-    }
-    THETA_CUDA(cudaMemcpyAsync(pl->d_list, h_list, sizeof(uint32_t) * n_list, cudaMemcpyHostToDevice, st));
-    THETA_CUDA(cudaMemcpyAsync(pl->d_prior, h_prior, sizeof(double) * n_list, cudaMemcpyHostToDevice, st));
+    const double margin = 2.5 * THETA_TIE_MARGIN;
     size_t want = std::max<size_t>(1 << 14, pl->emit_cap);
-    const size_t spec = 1024;  // records copied back speculatively together with the counters (one sync)
+    const size_t spec = 1024;  // records copied back speculatively together with the status block (one sync)
     theta_cand* host = nullptr;
     size_t n_host = 0;
+    double g = INFINITY;
     int rc = THETA_OK;
     for (int attempt = 0; attempt < 8; ++attempt) {
         if (want > pl->emit_cap) {
@@ -728,32 +775,41 @@ extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double p
             if (e != cudaSuccess) { rc = cuda_fail(e, "emit staging", __FILE__, __LINE__); break; }
             pl->h_emit_cap = std::max(spec, want);
         }
-        cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kCounters, st);
-        SearchParams sp{};
-        sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
-        sp.begin = pl->p1_begin; sp.end = pl->p1_end; sp.L = pl->p1_L; sp.n_items = (uint32_t)n_list;
-        sp.Lrun = std::min(pl->p1_L, 4); sp.units_per_item = (pl->p1_L + sp.Lrun - 1) / sp.Lrun;
-        sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters;
-        sp.stripe_list = pl->d_list; sp.stripe_prior = pl->d_prior; sp.near_thr = near_thr;
-        sp.emit = pl->d_emit; sp.emit_cap = pl->emit_cap;
-        cudaEventRecord(pl->ev0, st);
-        rc = THETA_OK;
-        switch (pl->KT) {
+        cudaEventRecord(pl->ev2, st);
+        // (re)builds the list and zeroes the pass-2 counters
+        stripe_scan_kernel<<<1, 1024, 0, st>>>(pl->d_stripe_min, stripes, global_min_dev, prior_min, margin, pl->d_counters,
+                                               pl->d_list, pl->d_prior);
+        if (stripes && pl->p1_begin != pl->p1_end) {
+            SearchParams sp{};
+            sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
+            sp.begin = pl->p1_begin; sp.end = pl->p1_end; sp.L = pl->p1_L; sp.n_items = (uint32_t)stripes;
+            sp.n_items_dev = pl->d_counters + kStList;
+            sp.Lrun = std::min(pl->p1_L, 4); sp.units_per_item = (pl->p1_L + sp.Lrun - 1) / sp.Lrun;
+            sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters + kCounters;
+            sp.stripe_list = pl->d_list; sp.stripe_prior = pl->d_prior;
+            sp.near_thr = 0.0; sp.near_thr_base = pl->d_counters + kStGlobalMin; sp.near_margin = margin;
+            sp.emit = pl->d_emit; sp.emit_cap = pl->emit_cap;
+            switch (pl->KT) {
 #define THETA_P2(KTV) case KTV: rc = launch_search<KTV, true>(pl, sp, st); break;
-            THETA_P2(2) THETA_P2(3) THETA_P2(4) THETA_P2(5) THETA_P2(6) THETA_P2(7) THETA_P2(8) THETA_P2(10) THETA_P2(12) THETA_P2(15)
+                THETA_P2(2) THETA_P2(3) THETA_P2(4) THETA_P2(5) THETA_P2(6) THETA_P2(7) THETA_P2(8) THETA_P2(10) THETA_P2(12) THETA_P2(15)
 #undef THETA_P2
-            default: set_error("unsupported level count"); rc = THETA_ERR_UNSUPPORTED;
+                default: set_error("unsupported level count"); rc = THETA_ERR_UNSUPPORTED;
+            }
+            if (rc) break;
         }
-        if (rc) break;
-        cudaEventRecord(pl->ev1, st);
-        unsigned long long* ctr = pl->h_ctr + kCounters;
-        cudaError_t e = cudaMemcpyAsync(ctr, pl->d_counters, sizeof(unsigned long long) * kCounters, cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(pl->ev3, st);
+        cudaError_t e = cudaMemcpyAsync(pl->h_ctr, pl->d_counters, sizeof(unsigned long long) * kStatusWords, cudaMemcpyDeviceToHost, st);
         const size_t n_spec = std::min(spec, pl->emit_cap);
         if (e == cudaSuccess) e = cudaMemcpyAsync(pl->h_emit, pl->d_emit, sizeof(theta_cand) * n_spec, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "pass2", __FILE__, __LINE__); break; }
-        cudaEventElapsedTime(&pl->stats.ms_pass2, pl->ev0, pl->ev1);
-        const unsigned long long emitted = ctr[3];
+        pl->p1_pending = false;
+        read_pass1_stats(pl);
+        cudaEventElapsedTime(&pl->stats.ms_pass2, pl->ev2, pl->ev3);
+        const unsigned long long* ctr = pl->h_ctr;
+        std::memcpy(&g, &ctr[kStGlobalMin], sizeof(double));
+        pl->stats.n_rescanned = ctr[kStList];
+        const unsigned long long emitted = ctr[kCounters + 3];
         if (emitted > pl->emit_cap) { want = (size_t)emitted + 1024; continue; }
         if (emitted > n_spec) {
             e = cudaMemcpyAsync(pl->h_emit + n_spec, pl->d_emit + n_spec, sizeof(theta_cand) * (emitted - n_spec), cudaMemcpyDeviceToHost, st);
@@ -765,6 +821,8 @@ extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double p
         break;
     }
     if (rc) return rc;
+    if (global_min_host) *global_min_host = g;
+    const double near_thr = g + margin;
     std::sort(host, host + n_host, [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; });
     {   // keep exactly: strict prefix minima of the whole stream (w.r.t. everything before this shard),
         // the near-minimum set, and NaN values -- the per-lane filter on the device emits a superset
@@ -785,6 +843,21 @@ extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double p
     }
     if (out_host && n_host) std::memcpy(out_host, host, sizeof(theta_cand) * n_host);
     return THETA_OK;
+}
+
+// Host-value form: global_min is written to the status block and picked up by the device-side list builder.
+extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double prior_min, theta_cand* out_host,
+                                     uint64_t cap, uint64_t* n_out, void* stream) {
+    if (!pl || !n_out) { set_error("null argument"); return THETA_ERR_INVALID; }
+    *n_out = 0;
+    if (pl->n != 2 || !pl->ev0) { set_error("pass2 without pass1"); return THETA_ERR_INVALID; }
+    if (pl->p1_pending) { set_error("pass2 before pass1_end"); return THETA_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    double* slot = reinterpret_cast<double*>(pl->d_counters + kStatusWords - 1);  // spare word of the status block
+    double* stage = reinterpret_cast<double*>(pl->h_ctr + kStatusWords - 1);
+    *stage = global_min;
+    THETA_CUDA(cudaMemcpyAsync(slot, stage, sizeof(double), cudaMemcpyHostToDevice, st));
+    return theta_search_n2_pass2_dev(pl, slot, prior_min, out_host, cap, n_out, nullptr, stream);
 }
 
 extern "C" int theta_search_stats_get(const theta_plan* pl, theta_search_stats* s) {

@@ -147,12 +147,10 @@ struct theta_plan {
     uint64_t p1_stripes = 0;
     double* d_stripe_min = nullptr;
     size_t stripe_cap = 0;
-    double* h_stripe_min = nullptr;  // pinned [stripe_cap]
     theta_cand* h_emit = nullptr;    // pinned [h_emit_cap]
     size_t h_emit_cap = 0;
-    unsigned char* h_list = nullptr;       // pinned staging of the pass-2 stripe list: prior f64[list_cap] | stripe u32[list_cap]
-    unsigned long long* h_ctr = nullptr;   // pinned [2 * kCounters]: pass-1 and pass-2 counter snapshots
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long* h_ctr = nullptr;   // pinned snapshot of the device status block (theta_n2.cu: kStatusWords)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     void* p1_stream = nullptr;
     bool p1_pending = false;
     unsigned long long* d_counters = nullptr;  // [0] stripe ticket, [1] solved, [2] newton iters, [3] emitted, [4] nan-nll

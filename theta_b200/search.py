@@ -101,26 +101,37 @@ def _bufs(dist, world, nbytes):
 
 
 def pass1_allreduce(plan, begin, end, dist, world, stream=None):
-    """Pass 1 on this shard + the single all-reduce(min) over all shards.  Returns (global_min, local_min).
-
-    With NCCL the shard minimum never visits the host in between: the search kernel's reduction writes it to a
-    device double and the all-reduce is enqueued right behind the kernel (stream order), so the step costs one
-    host synchronisation."""
+    """Pass 1 on this shard + the single all-reduce(min) over all shards (host values; the gloo / test path and
+    callers that want the two passes separately).  Returns (global_min, local_min)."""
+    lm = plan.pass1(begin, end, stream)
     if dist is None:
-        lm = plan.pass1(begin, end, stream)
         return lm, lm
-    import torch
+    return exchange_minima(lm, dist, 0, world)[0], lm
+
+
+def search_shard(plan, begin, end, dist, world, stream=None):
+    """Both passes on this shard with the one all-reduce(min) in between.  Returns (records, global_min).
+
+    On a GPU nothing returns to the host in between: pass 1 and its min reduction are enqueued, the NCCL
+    all-reduce(min) runs on the device double right behind them (stream order), the device-side stripe scan and
+    pass 2 follow, and the host waits once for the records."""
+    if not hasattr(plan, "pass1_begin"):  # host model of the plan (tests/test_dist_gloo.py)
+        g, _ = pass1_allreduce(plan, begin, end, dist, world, stream)
+        return plan.pass2(g, INF, stream), g
+    if dist is None:
+        plan.pass1_begin(begin, end, None, stream)
+        return plan.pass2_dev(None, INF, stream)
     if dist.get_backend() != "nccl":
-        lm = plan.pass1(begin, end, stream)
-        return exchange_minima(lm, dist, 0, world)[0], lm
+        g, _ = pass1_allreduce(plan, begin, end, dist, world, stream)
+        return plan.pass2(g, INF, stream), g
+    import torch
     cur = torch.cuda.current_stream()
     if stream is not None and int(stream) != int(cur.cuda_stream):
         raise ValueError("with NCCL the search must run on torch's current stream")
     t = _bufs(dist, world, _GATHER_BYTES)["min"]
     plan.pass1_begin(begin, end, t.data_ptr(), cur.cuda_stream)
-    dist.all_reduce(t, op=dist.ReduceOp.MIN)   # ordered behind the kernel on the current stream
-    lm = plan.pass1_end()
-    return float(t.item()), lm
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)   # ordered behind the kernel; the current stream then waits for it
+    return plan.pass2_dev(t.data_ptr(), INF, cur.cuda_stream)
 
 
 _GATHER_CAP = 256  # records per shard carried by the fixed-size exchange
@@ -195,10 +206,8 @@ def search_n2(plan, stream=None, rank_limit=None):
     if rank_limit is not None:
         total = min(total, int(rank_limit))
     begin, end = shard_range(total, rank, world)
-    g, _local = pass1_allreduce(plan, begin, end, dist, world, stream)
+    recs, g = search_shard(plan, begin, end, dist, world, stream)
     stats = plan.stats()
-    recs = plan.pass2(g, INF, stream)
-    stats.update({k: v for k, v in plan.stats().items() if k in ("n_rescanned", "ms_pass2")})
     allrecs, extras = gather_records(recs, dist, world, extra=[stats["n_solved"]])
     res = SearchResult()
     res.records = allrecs
