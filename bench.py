@@ -176,10 +176,16 @@ def run_reference(args):
     v = sum(vals) / len(vals)
     res["value"] = v
     P = problem(args.workload)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import theta_oracle as O
+    total = O.count_n2(P["lower"], P["upper"])
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "cfg2w":
+        total = min(total, PER_GPU * world)
     line = {"impl": "reference", "metric": "C-candidates/sec", "value": v, "unit": "candidates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": P["desc"], "n": 2, "m": P["m"], "k": P["k"]},
+            "config": {"workload": P["desc"], "n": 2, "m": P["m"], "k": P["k"], "candidates": int(total)},
             "cpu_baseline": res,
             "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -596,51 +596,50 @@ __global__ void __launch_bounds__(1024) stripe_scan_kernel(const double* __restr
                                                            double margin, unsigned long long* status,
                                                            uint32_t* __restrict__ list, double* __restrict__ prior) {
     __shared__ double s_w[32];
-    __shared__ double s_carry;
     __shared__ unsigned int s_count;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double g = gmin_dev ? *gmin_dev : __longlong_as_double((long long)status[kStLocalMin]);
     const double near_thr = g + margin;
     const bool any_nan = status[4] != 0ULL;  // a NaN NLL is always appended (Q6): every stripe is re-walked
-    if (tid == 0) { s_carry = prior_min; s_count = 0u; }
+    if (tid == 0) s_count = 0u;
+    // thread t owns the contiguous chunk [t*per, (t+1)*per): chunk minimum -> one block-wide exclusive scan ->
+    // a second walk over the chunk with the running prefix (two block barriers in total)
+    const uint64_t per = (n + 1023) / 1024;
+    const uint64_t lo = min(n, (uint64_t)tid * per), hi = min(n, lo + per);
+    double cm = INFINITY;
+    for (uint64_t i = lo; i < hi; ++i) cm = fmin(cm, v[i]);
+    double incl = cm;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = fmin(incl, y);
+    }
+    if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    for (uint64_t base = 0; base < n; base += 1024) {
-        const uint64_t i = base + tid;
-        const double x = i < n ? v[i] : INFINITY;
-        double incl = x;
+    if (warp == 0) {
+        double w = s_w[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const double y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl = fmin(incl, y);
+            const double y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w = fmin(w, y);
         }
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            double w = s_w[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w = fmin(w, y);
-            }
-            s_w[lane] = w;
-        }
-        __syncthreads();
-        const double carry = s_carry;
-        double prev = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) prev = INFINITY;
-        const double P = fmin(carry, fmin(warp > 0 ? s_w[warp - 1] : INFINITY, prev));  // min of everything before stripe i
-        if (i < n) {
-            const bool rec = x < P, near = x <= near_thr;
-            if (rec || near || any_nan) {
-                const unsigned int slot = atomicAdd(&s_count, 1u);
-                list[slot] = (uint32_t)i;
-                prior[slot] = rec ? P : -INFINITY;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) s_carry = fmin(carry, s_w[31]);
-        __syncthreads();
+        s_w[lane] = w;
     }
+    __syncthreads();
+    double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) prev = INFINITY;
+    double P = fmin(prior_min, fmin(warp > 0 ? s_w[warp - 1] : INFINITY, prev));  // min of everything before the chunk
+    for (uint64_t i = lo; i < hi; ++i) {
+        const double x = v[i];
+        const bool rec = x < P, near = x <= near_thr;
+        if (rec || near || any_nan) {
+            const unsigned int slot = atomicAdd(&s_count, 1u);
+            list[slot] = (uint32_t)i;
+            prior[slot] = rec ? P : -INFINITY;
+        }
+        P = fmin(P, x);
+    }
+    __syncthreads();
     if (tid == 0) {
         status[kStList] = s_count;
         status[kStGlobalMin] = (unsigned long long)__double_as_longlong(g);
