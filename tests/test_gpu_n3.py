@@ -64,13 +64,15 @@ def test_search_matches_reference_best(lib, golden):
             assert np.allclose(b[3], g["vals"], rtol=1e-9, atol=0)
 
 
-def test_search_equals_bruteforce_fold(lib, golden):
-    """pass1/pass2 + replay == the reference fold over every solved candidate (computed on the GPU too)."""
+def test_search_equals_bruteforce_fold(lib, golden, monkeypatch):
+    """pass1/pass2 + replay == the reference fold over every solved candidate (computed on the GPU too); with the
+    screening of pass 1 on (default) and off (then the solved count is the exact one)."""
     from theta_b200.search import fold_replay
     from theta_b200.search_n3 import search_n3
     case = golden("n3_small_full.json.gz")[2]
     plan = lib.Plan(3, case["r"], case["rN"], case["lower"], case["upper"])
-    for cap in (8, 64, 100000):
+    for cap, screen in ((8, "1"), (64, "0"), (100000, "1"), (100000, "0")):
+        monkeypatch.setenv("THETA_N3_SCREEN", screen)
         res = search_n3(plan, leaf_cap=cap)
         paths = plan.enumerate_n3()
         mu, mh, nll, st, _ = plan.solve_rows(paths)
@@ -82,8 +84,50 @@ def test_search_equals_bruteforce_fold(lib, golden):
         got = [None if b[0] is None else tuple(b[0]) for b in res.best]
         assert got == want
         assert res.count == len(paths) + 1
-        assert res.n_solved == int(ok.sum()) + 1
+        if screen == "0":
+            assert res.n_solved == int(ok.sum()) + 1
+    monkeypatch.delenv("THETA_N3_SCREEN", raising=False)
     plan.close()
+
+
+def test_screening_bound_is_sound(lib, golden, monkeypatch):
+    """Pass 1 of the n=3 search skips the exact solve of leaves whose Frank-Wolfe lower bound (n3_screen) proves them
+    irrelevant.  THETA_VERIFY_APPROX=1 solves every leaf and counts leaves whose bound exceeds the exact NLL: must be
+    0 on the golden spaces and on 1.5 M candidates of the config #4 shape; and the records must not depend on it."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import theta_oracle as O
+    cases = [(c["r"], c["rN"], c["lower"], c["upper"], 64, None) for c in golden("n3_small_full.json.gz")]
+    P = O.synthetic_problem_n3(150, 5, 1, 12, False)
+    cases.append((P["r"], P["rN"], P["lower"], P["upper"], 512, 3000))
+    for r, rN, lo, up, cap, n_items in cases:
+        plan = lib.Plan(3, r, rN, lo, up)
+        ni = plan.prepare(cap)
+        end = ni if n_items is None else min(ni, n_items)
+        out = {}
+        for mode in ("screen", "verify", "off"):
+            monkeypatch.delenv("THETA_VERIFY_APPROX", raising=False)
+            monkeypatch.delenv("THETA_N3_SCREEN", raising=False)
+            if mode == "verify":
+                monkeypatch.setenv("THETA_VERIFY_APPROX", "1")
+            if mode == "off":
+                monkeypatch.setenv("THETA_N3_SCREEN", "0")
+            g = plan.pass1_n3(0, end)
+            st = plan.stats()
+            recs, paths = plan.pass2_n3(g)
+            out[mode] = (g, st, recs.copy(), paths.copy())
+        monkeypatch.delenv("THETA_VERIFY_APPROX", raising=False)
+        monkeypatch.delenv("THETA_N3_SCREEN", raising=False)
+        assert out["verify"][1]["n_bound_violations"] == 0
+        assert out["verify"][1]["n_exact"] == out["verify"][1]["n_candidates"] == out["off"][1]["n_candidates"]
+        assert out["screen"][0] == out["off"][0] == out["verify"][0]
+        for mode in ("screen", "verify"):
+            assert out[mode][2]["nll"].tobytes() == out["off"][2]["nll"].tobytes()
+            assert out[mode][2]["rank"].tobytes() == out["off"][2]["rank"].tobytes()
+            assert out[mode][3].tobytes() == out["off"][3].tobytes()
+        if out["off"][1]["n_candidates"] > 100000:
+            assert out["screen"][1]["n_exact"] < out["off"][1]["n_candidates"] // 2  # the screen does skip
+        plan.close()
 
 
 def test_optimizer_and_enumerator_mirrors(lib, golden):

@@ -16,10 +16,19 @@
 #ifndef __CUDACC__
 #define THETA_HD inline
 #define THETA_HDN inline
+#define THETA_MPI inline
 #else
 #define THETA_HD __host__ __device__ __forceinline__
-// the solver is large: out-of-line routines keep the kernels within the instruction cache
+// the solver is large: out-of-line routines keep the kernels within the instruction cache ...
 #define THETA_HDN __host__ __device__ __noinline__
+// ... except the MINPACK routines themselves (THETA_MPI): inlined and unrolled at N = 4 their 4-vectors become
+// registers and their loops straight-line code; out of line (-DTHETA_MP_OUTLINE) every vector lives in local
+// memory and every loop runs with run-time indices
+#ifdef THETA_MP_OUTLINE
+#define THETA_MPI __host__ __device__ __noinline__
+#else
+#define THETA_MPI __host__ __device__ __forceinline__
+#endif
 #endif
 
 namespace theta {
@@ -34,6 +43,7 @@ THETA_HDN double enorm(int n, const double* x) {
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0, x1max = 0.0, x3max = 0.0;
     const double agiant = rgiant / (double)n;
+#pragma unroll
     for (int i = 0; i < n; ++i) {
         const double xabs = fabs(x[i]);
         if (xabs > rdwarf && xabs < agiant) {
@@ -67,21 +77,27 @@ THETA_HDN double enorm(int n, const double* x) {
 }
 
 // a is column-major N x N: a[i + N*j]
-THETA_HDN void qrfac(double* a, double* rdiag, double* acnorm) {
+THETA_MPI void qrfac(double* a, double* rdiag, double* acnorm) {
+#pragma unroll
     for (int j = 0; j < N; ++j) {
         acnorm[j] = enorm(N, a + N * j);
         rdiag[j] = acnorm[j];
     }
+#pragma unroll
     for (int j = 0; j < N; ++j) {
         double ajnorm = enorm(N - j, a + j + N * j);
         if (ajnorm != 0.0) {
             if (a[j + N * j] < 0.0) ajnorm = -ajnorm;
+#pragma unroll
             for (int i = j; i < N; ++i) a[i + N * j] /= ajnorm;
             a[j + N * j] += 1.0;
+#pragma unroll
             for (int k = j + 1; k < N; ++k) {
                 double sum = 0.0;
+#pragma unroll
                 for (int i = j; i < N; ++i) sum += a[i + N * j] * a[i + N * k];
                 const double temp = sum / a[j + N * j];
+#pragma unroll
                 for (int i = j; i < N; ++i) a[i + N * k] -= temp * a[i + N * j];
             }
         }
@@ -89,21 +105,28 @@ THETA_HDN void qrfac(double* a, double* rdiag, double* acnorm) {
     }
 }
 
-THETA_HDN void qform(double* q, double* wa) {
+THETA_MPI void qform(double* q, double* wa) {
+#pragma unroll
     for (int j = 1; j < N; ++j)
+#pragma unroll
         for (int i = 0; i < j; ++i) q[i + N * j] = 0.0;
+#pragma unroll
     for (int l = 0; l < N; ++l) {
         const int k = N - 1 - l;
+#pragma unroll
         for (int i = k; i < N; ++i) {
             wa[i] = q[i + N * k];
             q[i + N * k] = 0.0;
         }
         q[k + N * k] = 1.0;
         if (wa[k] != 0.0) {
+#pragma unroll
             for (int j = k; j < N; ++j) {
                 double sum = 0.0;
+#pragma unroll
                 for (int i = k; i < N; ++i) sum += q[i + N * j] * wa[i];
                 const double temp = sum / wa[k];
+#pragma unroll
                 for (int i = k; i < N; ++i) q[i + N * j] -= temp * wa[i];
             }
         }
@@ -111,15 +134,17 @@ THETA_HDN void qform(double* q, double* wa) {
 }
 
 // r: upper triangle packed by rows (0-based l); x: output step
-THETA_HDN void dogleg(const double* r, const double* diag, const double* qtb, double delta, double* x, double* wa1,
+THETA_MPI void dogleg(const double* r, const double* diag, const double* qtb, double delta, double* x, double* wa1,
                      double* wa2) {
     // Gauss-Newton direction
     int jj = LR;  // 0-based index one past the last diagonal (1-based jj = LR + 1)
+#pragma unroll
     for (int k = 1; k <= N; ++k) {
         const int j = N - k;  // 0-based
         jj -= k;              // now the 0-based index of r(j,j)
         int l = jj + 1;
         double sum = 0.0;
+#pragma unroll
         for (int i = j + 1; i < N; ++i) {
             sum += r[l] * x[i];
             ++l;
@@ -127,6 +152,7 @@ THETA_HDN void dogleg(const double* r, const double* diag, const double* qtb, do
         double temp = r[jj];
         if (temp == 0.0) {
             l = j;  // 0-based index of r(0,j)
+#pragma unroll
             for (int i = 0; i <= j; ++i) {
                 temp = fmax(temp, fabs(r[l]));
                 l += N - 1 - i;
@@ -136,6 +162,7 @@ THETA_HDN void dogleg(const double* r, const double* diag, const double* qtb, do
         }
         x[j] = (qtb[j] - sum) / temp;
     }
+#pragma unroll
     for (int j = 0; j < N; ++j) {
         wa1[j] = 0.0;
         wa2[j] = diag[j] * x[j];
@@ -144,8 +171,10 @@ THETA_HDN void dogleg(const double* r, const double* diag, const double* qtb, do
     if (qnorm <= delta) return;
     // scaled gradient direction
     int l = 0;
+#pragma unroll
     for (int j = 0; j < N; ++j) {
         const double temp = qtb[j];
+#pragma unroll
         for (int i = j; i < N; ++i) {
             wa1[i] += r[l] * temp;
             ++l;
@@ -156,10 +185,13 @@ THETA_HDN void dogleg(const double* r, const double* diag, const double* qtb, do
     double sgnorm = 0.0;
     double alpha = delta / qnorm;
     if (gnorm != 0.0) {
+#pragma unroll
         for (int j = 0; j < N; ++j) wa1[j] = (wa1[j] / gnorm) / diag[j];
         l = 0;
+#pragma unroll
         for (int j = 0; j < N; ++j) {
             double sum = 0.0;
+#pragma unroll
             for (int i = j; i < N; ++i) {
                 sum += r[l] * wa1[i];
                 ++l;
@@ -178,14 +210,16 @@ THETA_HDN void dogleg(const double* r, const double* diag, const double* qtb, do
         }
     }
     const double temp = (1.0 - alpha) * fmin(sgnorm, delta);
+#pragma unroll
     for (int j = 0; j < N; ++j) x[j] = temp * wa1[j] + alpha * x[j];
 }
 
 // s: lower triangular stored by columns (== R packed by rows); m = n = N
-THETA_HDN void r1updt(double* s, const double* u, double* v, double* w, bool* sing) {
+THETA_MPI void r1updt(double* s, const double* u, double* v, double* w, bool* sing) {
     const double p5 = 0.5, p25 = 0.25;
     int jj = LR - 1;  // 0-based index of s(N-1,N-1)
     w[N - 1] = s[jj];
+#pragma unroll
     for (int nmj = 1; nmj <= N - 1; ++nmj) {
         const int j = N - 1 - nmj;  // 0-based
         jj -= (N - j);              // 0-based index of s(j,j)
@@ -207,6 +241,7 @@ THETA_HDN void r1updt(double* s, const double* u, double* v, double* w, bool* si
             v[N - 1] = sn * v[j] + c * v[N - 1];
             v[j] = tau;
             int l = jj;
+#pragma unroll
             for (int i = j; i < N; ++i) {
                 const double temp = c * s[l] - sn * w[i];
                 w[i] = sn * s[l] + c * w[i];
@@ -215,8 +250,10 @@ THETA_HDN void r1updt(double* s, const double* u, double* v, double* w, bool* si
             }
         }
     }
+#pragma unroll
     for (int i = 0; i < N; ++i) w[i] += v[N - 1] * u[i];
     *sing = false;
+#pragma unroll
     for (int j = 0; j < N - 1; ++j) {
         if (w[j] != 0.0) {
             double c, sn, tau;
@@ -233,6 +270,7 @@ THETA_HDN void r1updt(double* s, const double* u, double* v, double* w, bool* si
                 tau = sn;
             }
             int l = jj;
+#pragma unroll
             for (int i = j; i < N; ++i) {
                 const double temp = c * s[l] + sn * w[i];
                 w[i] = -sn * s[l] + c * w[i];
@@ -249,7 +287,8 @@ THETA_HDN void r1updt(double* s, const double* u, double* v, double* w, bool* si
 }
 
 // a: m x N column-major with leading dimension lda
-THETA_HDN void r1mpyq(int m, double* a, int lda, const double* v, const double* w) {
+THETA_MPI void r1mpyq(int m, double* a, int lda, const double* v, const double* w) {
+#pragma unroll
     for (int nmj = 1; nmj <= N - 1; ++nmj) {
         const int j = N - 1 - nmj;
         double c, sn;
@@ -260,12 +299,14 @@ THETA_HDN void r1mpyq(int m, double* a, int lda, const double* v, const double* 
             sn = v[j];
             c = sqrt(1.0 - sn * sn);
         }
+#pragma unroll
         for (int i = 0; i < m; ++i) {
             const double temp = c * a[i + lda * j] - sn * a[i + lda * (N - 1)];
             a[i + lda * (N - 1)] = sn * a[i + lda * j] + c * a[i + lda * (N - 1)];
             a[i + lda * j] = temp;
         }
     }
+#pragma unroll
     for (int j = 0; j < N - 1; ++j) {
         double c, sn;
         if (fabs(w[j]) > 1.0) {
@@ -275,6 +316,7 @@ THETA_HDN void r1mpyq(int m, double* a, int lda, const double* v, const double* 
             sn = w[j];
             c = sqrt(1.0 - sn * sn);
         }
+#pragma unroll
         for (int i = 0; i < m; ++i) {
             const double temp = c * a[i + lda * j] + sn * a[i + lda * (N - 1)];
             a[i + lda * (N - 1)] = -sn * a[i + lda * j] + c * a[i + lda * (N - 1)];
@@ -289,7 +331,7 @@ struct Result {
 
 // Sys must provide:  void fcn(const double* x, double* fvec);  void jac(const double* x, double* fjac /*col-major*/);
 template <class Sys>
-THETA_HDN Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double factor) {
+THETA_MPI Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double factor) {
     const double p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
     double fvec[N], fjac[N * N], diag[N], r[LR], qtf[N], wa1[N], wa2[N], wa3[N], wa4[N];
     Result res{0, 0, 0};
@@ -304,27 +346,35 @@ THETA_HDN Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double fact
         ++res.njev;
         qrfac(fjac, wa1, wa2);
         if (iter == 1) {
+#pragma unroll
             for (int j = 0; j < N; ++j) {
                 diag[j] = wa2[j];
                 if (wa2[j] == 0.0) diag[j] = 1.0;
             }
+#pragma unroll
             for (int j = 0; j < N; ++j) wa3[j] = diag[j] * x[j];
             xnorm = enorm(N, wa3);
             delta = factor * xnorm;
             if (delta == 0.0) delta = factor;
         }
+#pragma unroll
         for (int i = 0; i < N; ++i) qtf[i] = fvec[i];
+#pragma unroll
         for (int j = 0; j < N; ++j) {
             if (fjac[j + N * j] != 0.0) {
                 double sum = 0.0;
+#pragma unroll
                 for (int i = j; i < N; ++i) sum += fjac[i + N * j] * qtf[i];
                 const double temp = -sum / fjac[j + N * j];
+#pragma unroll
                 for (int i = j; i < N; ++i) qtf[i] += fjac[i + N * j] * temp;
             }
         }
         bool sing = false;
+#pragma unroll
         for (int j = 0; j < N; ++j) {
             int l = j;
+#pragma unroll
             for (int i = 0; i < j; ++i) {
                 r[l] = fjac[i + N * j];
                 l += N - 1 - i;
@@ -333,9 +383,11 @@ THETA_HDN Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double fact
             if (wa1[j] == 0.0) sing = true;
         }
         qform(fjac, wa1);
+#pragma unroll
         for (int j = 0; j < N; ++j) diag[j] = fmax(diag[j], wa2[j]);
         for (;;) {  // inner loop
             dogleg(r, diag, qtf, delta, wa1, wa2, wa3);
+#pragma unroll
             for (int j = 0; j < N; ++j) {
                 wa1[j] = -wa1[j];
                 wa2[j] = x[j] + wa1[j];
@@ -349,8 +401,10 @@ THETA_HDN Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double fact
             double actred = -1.0;
             if (fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
             int l = 0;
+#pragma unroll
             for (int i = 0; i < N; ++i) {
                 double sum = 0.0;
+#pragma unroll
                 for (int j = i; j < N; ++j) {
                     sum += r[l] * wa1[j];
                     ++l;
@@ -373,6 +427,7 @@ THETA_HDN Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double fact
                 if (fabs(ratio - 1.0) <= p1) delta = pnorm / p5;
             }
             if (ratio >= p0001) {
+#pragma unroll
                 for (int j = 0; j < N; ++j) {
                     x[j] = wa2[j];
                     wa2[j] = diag[j] * x[j];
@@ -394,8 +449,10 @@ THETA_HDN Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double fact
             if (nslow1 == 10) res.info = 5;
             if (res.info != 0) return res;
             if (ncfail == 2) break;  // recompute the Jacobian
+#pragma unroll
             for (int j = 0; j < N; ++j) {
                 double sum = 0.0;
+#pragma unroll
                 for (int i = 0; i < N; ++i) sum += fjac[i + N * j] * wa4[i];
                 wa2[j] = (sum - wa3[j]) / pnorm;
                 wa1[j] = diag[j] * ((diag[j] * wa1[j]) / pnorm);

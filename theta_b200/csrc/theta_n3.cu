@@ -12,6 +12,7 @@
 // keeping the grouped statistics (R_g, S1, S2) incrementally (exact integer sums in fp64).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -200,44 +201,89 @@ struct Search3Params {
     uint8_t* emit_paths;
     unsigned long long emit_cap;
     int enumerate_only;          // emit every leaf's path, no solve
+    int screen;                  // pass 1: skip the exact solve of leaves that n3_screen proves irrelevant
+    int verify;                  // THETA_VERIFY_APPROX=1: solve every leaf and count leaves whose bound exceeds the exact NLL
 };
 
-template <int MAXM, bool EMIT>
-__global__ void __launch_bounds__(kBlock3, 8) n3_search_kernel(const Search3Params p) {
+// The per-candidate solver (hybrj restatement + fallback) is ~200 KB of machine code, far more than the
+// instruction caches hold, so warps that run it at unrelated phases each stream it from L2 ("no instruction"
+// was the top stall).  The leaf loop is therefore block-synchronous: every thread advances its own DFS to its
+// next leaf (cheap, divergent), the block meets at a barrier, and all warps enter the solver together and
+// move through it roughly in step, sharing the fetched instructions.
+template <int MAXM, bool EMIT, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) n3_search_kernel(const Search3Params p) {
     __shared__ N3Dev D;
     if (threadIdx.x == 0) D = p.D;
     __syncthreads();
     Dfs<MAXM> dfs;
     Groups3 G;
-    unsigned long long solved = 0, nfev = 0, nan_nll = 0, leaves = 0;
+    unsigned long long solved = 0, nfev = 0, nan_nll = 0, leaves = 0, n_exact = 0, n_viol = 0;
     const int m = D.kc.m;
+    // pass 1 screens every leaf with a rigorous lower bound (n3_screen) against T = the best exact NLL this
+    // thread has seen so far -- all of it at lower ranks: a thread takes items in increasing order and walks
+    // each in enumeration order -- so a skipped leaf is neither a strict prefix minimum nor in the tie window
+    Screen3 ws{1.0 / 3.0, 1.0 / 3.0};
+    double T = INFINITY;
+    const double screen_margin = 3.0 * THETA_TIE_MARGIN;
+    bool has_item = false, exhausted = false, fresh = true;
+    uint32_t ticket = 0, item = 0, seq = 0;
+    double prior = 0.0, tmin = INFINITY;
     for (;;) {
-        const uint32_t ticket = (uint32_t)atomicAdd(&p.ctr[0], 1ULL);
-        if (ticket >= p.n_items) break;
-        const uint32_t item = EMIT ? p.list[ticket] : p.item_begin + ticket;
-        const double prior = EMIT ? p.prior[ticket] : 0.0;
-        dfs.load_prefix(D, p.prefix + p.off[item], (int)(p.off[item + 1] - p.off[item]));
-        double tmin = INFINITY;
-        uint32_t seq = 0;
-        bool fresh = true;
-        while (dfs.next_leaf(D, fresh)) {
-            fresh = false;
+        bool have_leaf = false;
+        while (!have_leaf && !exhausted) {
+            if (!has_item) {
+                ticket = (uint32_t)atomicAdd(&p.ctr[0], 1ULL);
+                if (ticket >= p.n_items) { exhausted = true; break; }
+                item = EMIT ? p.list[ticket] : p.item_begin + ticket;
+                prior = EMIT ? p.prior[ticket] : 0.0;
+                dfs.load_prefix(D, p.prefix + p.off[item], (int)(p.off[item + 1] - p.off[item]));
+                tmin = INFINITY;
+                seq = 0;
+                fresh = true;
+                has_item = true;
+            }
+            if (dfs.next_leaf(D, fresh)) {
+                fresh = false;
+                have_leaf = true;
+            } else {
+                if (!EMIT) p.item_min[ticket] = tmin;
+                has_item = false;
+            }
+        }
+        if (!__syncthreads_or(have_leaf ? 1 : 0)) break;
+        if (have_leaf) {
             ++leaves;
             bool emit = false;
             Solve3Out o;
             o.status = THETA_ST_NONE_NAN;
             if (!p.enumerate_only) {
                 dfs.groups(D, G);
-                n3_solve(G, dfs.S1, dfs.S2, D.kc, o);
-                if (o.status < THETA_ST_NONE_SIGN) {
-                    ++solved;
-                    nfev += o.nfev;
-                    if (o.nll != o.nll) {
-                        ++nan_nll;
-                        emit = true;  // Misc.isClose(nan, x) is True (Q6)
-                    } else {
-                        if (EMIT) emit = (o.nll <= p.near_thr) || (o.nll < prior && o.nll < tmin);
-                        tmin = fmin(tmin, o.nll);
+                // (deferring the leaves that survive the screen so that the solver runs with full warps was
+                // measured slower: surviving leaves cluster in time, and the longer divergent screening loops
+                // between solver rounds cost more than they save)
+                bool skip = false;
+                double lb = -INFINITY;
+                if (p.screen) {
+                    // pass 2 emits a leaf only if NLL <= near_thr or NLL < min(prior, item minimum so far): a leaf whose
+                    // lower bound exceeds both thresholds is neither emitted nor changes the item minimum
+                    const double thr = EMIT ? fmax(p.near_thr, fmin(prior, tmin)) : T + screen_margin;
+                    skip = n3_screen(G, dfs.S1, dfs.S2, D.kc, ws, thr, lb) && !p.verify;
+                }
+                if (!skip) {
+                    n3_solve(G, dfs.S1, dfs.S2, D.kc, o);
+                    ++n_exact;
+                    if (o.status < THETA_ST_NONE_SIGN) {
+                        ++solved;
+                        nfev += o.nfev;
+                        if (o.nll != o.nll) {
+                            ++nan_nll;
+                            emit = true;  // Misc.isClose(nan, x) is True (Q6)
+                        } else {
+                            if (EMIT) emit = (o.nll <= p.near_thr) || (o.nll < prior && o.nll < tmin);
+                            tmin = fmin(tmin, o.nll);
+                            T = fmin(T, o.nll);
+                            if (p.verify && lb > o.nll) ++n_viol;
+                        }
                     }
                 }
             } else {
@@ -259,12 +305,13 @@ __global__ void __launch_bounds__(kBlock3, 8) n3_search_kernel(const Search3Para
             }
             ++seq;
         }
-        if (!EMIT) p.item_min[ticket] = tmin;
     }
     if (solved) atomicAdd(&p.ctr[1], solved);
     if (nfev) atomicAdd(&p.ctr[2], nfev);
     if (nan_nll) atomicAdd(&p.ctr[4], nan_nll);
     if (leaves) atomicAdd(&p.ctr[5], leaves);
+    if (n_exact) atomicAdd(&p.ctr[6], n_exact);
+    if (n_viol) atomicAdd(&p.ctr[7], n_viol);
 }
 
 // Optimizer.solve on explicit row-index strings
@@ -546,19 +593,43 @@ extern "C" int theta_n3_item_weights(const theta_plan* pl, double* weights) {
 }
 
 // ----------------------------------------------------------------------- launches
-template <bool EMIT>
-static int launch_n3(const theta_plan* pl, const Search3Params& sp, cudaStream_t st) {
+// THETA_N3_BLOCK (tuning knob): threads per CTA of the n=3 search kernel (64, 128, 256 or 512; default: by item count)
+static int g_n3_block = -1;
+
+template <bool EMIT, int BLOCK, int MINB>
+static int launch_n3_b(const theta_plan* pl, const Search3Params& sp, cudaStream_t st) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
     const int m = pl->m;
     const int64_t threads_wanted = (int64_t)sp.n_items;
-    int grid = (int)std::min<int64_t>((threads_wanted + kBlock3 - 1) / kBlock3, (int64_t)sms * 8);
+    int grid = (int)std::min<int64_t>((threads_wanted + BLOCK - 1) / BLOCK, (int64_t)sms * MINB);
     if (grid < 1) grid = 1;
-    if (m <= 64) n3_search_kernel<64, EMIT><<<grid, kBlock3, 0, st>>>(sp);
-    else if (m <= 256) n3_search_kernel<256, EMIT><<<grid, kBlock3, 0, st>>>(sp);
-    else n3_search_kernel<1024, EMIT><<<grid, kBlock3, 0, st>>>(sp);
+    if (m <= 64) n3_search_kernel<64, EMIT, BLOCK, MINB><<<grid, BLOCK, 0, st>>>(sp);
+    else if (m <= 256) n3_search_kernel<256, EMIT, BLOCK, MINB><<<grid, BLOCK, 0, st>>>(sp);
+    else n3_search_kernel<1024, EMIT, BLOCK, MINB><<<grid, BLOCK, 0, st>>>(sp);
     THETA_CUDA(cudaGetLastError());
     return THETA_OK;
+}
+
+template <bool EMIT>
+static int launch_n3(const theta_plan* pl, const Search3Params& sp, cudaStream_t st) {
+    if (g_n3_block < 0) {
+        const char* e = getenv("THETA_N3_BLOCK");
+        g_n3_block = e ? atoi(e) : 0;
+    }
+    int block = g_n3_block;
+    if (block == 0) {  // the largest CTA that still gives every SM at least half a CTA of items
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+        const int64_t per_sm = (int64_t)sp.n_items / sms;
+        block = per_sm >= 256 ? 512 : per_sm >= 128 ? 256 : per_sm >= 64 ? 128 : 64;
+    }
+    switch (block) {
+        case 64: return launch_n3_b<EMIT, 64, 8>(pl, sp, st);
+        case 128: return launch_n3_b<EMIT, 128, 4>(pl, sp, st);
+        case 512: return launch_n3_b<EMIT, 512, 1>(pl, sp, st);
+        default: return launch_n3_b<EMIT, 256, 2>(pl, sp, st);
+    }
 }
 
 extern "C" int theta_search_n3_pass1(theta_plan* pl, uint64_t item_begin, uint64_t item_end, double* local_min, void* stream) {
@@ -583,6 +654,12 @@ extern "C" int theta_search_n3_pass1(theta_plan* pl, uint64_t item_begin, uint64
     fill_dev(pl, &sp.D);
     sp.prefix = s->d_prefix; sp.off = s->d_off; sp.item_begin = (uint32_t)item_begin; sp.n_items = (uint32_t)n;
     sp.item_min = s->d_item_min; sp.ctr = s->d_ctr;
+    {
+        const char* ev = getenv("THETA_VERIFY_APPROX");
+        sp.verify = (ev && ev[0] == '1') ? 1 : 0;
+        const char* es = getenv("THETA_N3_SCREEN");
+        sp.screen = (es && es[0] == '0') ? 0 : 1;
+    }
     cudaEvent_t e0, e1;
     THETA_CUDA(cudaEventCreate(&e0)); THETA_CUDA(cudaEventCreate(&e1));
     THETA_CUDA(cudaEventRecord(e0, st));
@@ -598,7 +675,9 @@ extern "C" int theta_search_n3_pass1(theta_plan* pl, uint64_t item_begin, uint64
     double g = INFINITY;
     for (double v : s->h_item_min) if (v < g) g = v;
     pl->stats.n_candidates = ctr[5];
-    pl->stats.n_solved = ctr[1];
+    pl->stats.n_solved = ctr[1];  // of the leaves that were solved exactly (all of them with THETA_N3_SCREEN=0)
+    pl->stats.n_exact = ctr[6];
+    pl->stats.n_bound_violations = ctr[7];
     pl->stats.n_stripes = n;
     pl->stats.newton_iters = ctr[1] ? (double)ctr[2] / (double)ctr[1] : 0.0;
     pl->stats.min_nll = g;
@@ -632,6 +711,12 @@ static int run_emit(theta_plan* pl, const std::vector<uint32_t>& list, const std
         sp.prefix = s->d_prefix; sp.off = s->d_off; sp.n_items = (uint32_t)list.size(); sp.ctr = s->d_ctr;
         sp.list = d_list; sp.prior = d_prior; sp.near_thr = near_thr; sp.emit = d_emit; sp.emit_paths = d_paths;
         sp.emit_cap = cap; sp.enumerate_only = enumerate_only;
+        {
+            const char* ev = getenv("THETA_VERIFY_APPROX");
+            sp.verify = (ev && ev[0] == '1') ? 1 : 0;
+            const char* es = getenv("THETA_N3_SCREEN");
+            sp.screen = (enumerate_only || (es && es[0] == '0')) ? 0 : 1;
+        }
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, st);

@@ -148,6 +148,80 @@ THETA_HDN void n3_finish(const Groups3& g, double S1, double S2, const N3Const& 
     o.nll = k.K0 - acc;
 }
 
+// ---- screening: a rigorous lower bound on anything the reference can return for this candidate ----
+//
+// In normalised coordinates y (y_j >= 0, sum y = 1) the NLL is convex:
+//     f(y) = K0 - sum_g R_g log(A d_g(y)),     d_g = y0/A + a_g y1/S1 + b_g y2/S2
+// and whatever Optimizer._solve_n3plus ends with -- the hybrj root if it is in range, the BFGS start point
+// (1/3,1/3,1/3), or a point the fallback moved to inside [0,1]^3 -- is evaluated by M3 / L3 at a non-negative
+// mu_hat, i.e. at f(mu_hat / sum mu_hat) >= f* = min over the simplex.  For any interior y the first-order
+// (Frank-Wolfe) bound gives   f* >= f(y) - gap(y),   gap(y) = max_j t_j sum_g c_gj R_g / d_g  -  sum_g R_g >= 0
+// (grad f . y = -Rtot exactly).  A few damped Newton steps in (y0, y1), warm-started from the previous leaf of the
+// DFS, make the gap small; f(y) is evaluated with fp32 MUFU logarithms whose error is bounded as in
+// theta_core.cuh::n2_l2_approx (arguments A d_g kept within [2^-15, 2^15], |log2| < 16, 2 ulp = 2^-19).
+// Returns true when  f32(y) - gap - E  >  T + margin  (the candidate can neither be a strict prefix minimum of
+// the stream nor lie within the tie window); the caller then skips the exact solve.  lb_out is that bound.
+#define THETA_N3_APPROX_C 6e-6
+struct Screen3 {
+    double y0, y1;  // warm start (interior point of the simplex)
+};
+
+#ifdef __CUDACC__
+__device__ __noinline__ bool n3_screen(const Groups3& g, double S1, double S2, const N3Const& k, Screen3& ws,
+                                       double T_plus_margin, double& lb_out) {
+    lb_out = -INFINITY;
+    if (k.any_zero_rN || !(S1 > 0.0) || !(S2 > 0.0)) return false;
+    const double t1 = k.A / S1, t2 = k.A / S2;  // A d_g = y0 + a (A/S1) y1 + b (A/S2) y2
+    const double E = THETA_N3_APPROX_C * k.Rtot;
+    double y0 = ws.y0, y1 = ws.y1;
+    if (!(y0 > 1e-6 && y1 > 1e-6 && y0 + y1 < 1.0 - 1e-6)) { y0 = 1.0 / 3.0; y1 = 1.0 / 3.0; }
+    for (int it = 0; it < 3; ++it) {
+        const double y2 = 1.0 - (y0 + y1);
+        const double u1 = y1 * t1, u2 = y2 * t2;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, h00 = 0.0, h01 = 0.0, h02 = 0.0, h11 = 0.0, h12 = 0.0, h22 = 0.0, lacc = 0.0;
+        bool ok = true;
+        for (int i = 0; i < g.G; ++i) {
+            const double a = g.a[i], b = g.b[i], R = g.R[i];
+            const double d = y0 + a * u1 + b * u2;  // A d_g > 0 in the interior
+            const double r = fast_rcp1(d);
+            const double q = R * r, qq = q * r, aq = a * qq, bq = b * qq;
+            s0 += q; s1 = fma(a, q, s1); s2 = fma(b, q, s2);
+            h00 += qq; h01 += aq; h02 += bq; h11 = fma(a, aq, h11); h12 = fma(a, bq, h12); h22 = fma(b, bq, h22);
+            const float df = (float)d;
+            if (!(df >= 3.0517578125e-05f && df <= 32768.0f)) ok = false;
+            lacc = fma(R, (double)__log2f(df), lacc);
+        }
+        if (!ok) return false;
+        // gradient components (up to sign): G_j = t_j sum c_gj q_g ; gap = max_j G_j - Rtot
+        const double G0 = s0, G1 = t1 * s1, G2 = t2 * s2;
+        const double gap = fmax(G0, fmax(G1, G2)) - k.Rtot;
+        const double fy = fma(-0.6931471805599453094, lacc, k.K0);
+        const double lb = fy - fmax(gap, 0.0) * (1.0 + 1e-9) - E;
+        if (lb > lb_out) lb_out = lb;
+        if (lb > T_plus_margin) { ws.y0 = y0; ws.y1 = y1; return true; }
+        if (it == 2) break;
+        // damped Newton step on the reduced problem (y2 = 1 - y0 - y1); grad f_j = -G_j
+        const double g0 = -(G0 - G2), g1 = -(G1 - G2);
+        const double H00 = h00, H01 = t1 * h01, H02 = t2 * h02, H11 = t1 * t1 * h11, H12 = t1 * t2 * h12, H22 = t2 * t2 * h22;
+        const double r00 = H00 - 2.0 * H02 + H22, r01 = H01 - H02 - H12 + H22, r11 = H11 - 2.0 * H12 + H22;
+        const double det = r00 * r11 - r01 * r01;
+        if (!(det > 0.0)) break;
+        const double idet = 1.0 / det;
+        const double e0 = -(r11 * g0 - r01 * g1) * idet, e1 = -(r00 * g1 - r01 * g0) * idet, e2 = -(e0 + e1);
+        double alpha = 1.0;
+        if (e0 < 0.0) alpha = fmin(alpha, 0.9 * y0 / -e0);
+        if (e1 < 0.0) alpha = fmin(alpha, 0.9 * y1 / -e1);
+        if (e2 < 0.0) alpha = fmin(alpha, 0.9 * y2 / -e2);
+        if (!(alpha > 0.0)) break;
+        y0 = fma(alpha, e0, y0);
+        y1 = fma(alpha, e1, y1);
+        if (!(y0 > 0.0 && y1 > 0.0 && y0 + y1 < 1.0)) break;
+    }
+    ws.y0 = y0; ws.y1 = y1;
+    return false;
+}
+#endif
+
 THETA_HDN void n3_solve(const Groups3& g, double S1, double S2, const N3Const& k, Solve3Out& o) {
     o.nfev = 0;
     o.nll = 0.0;

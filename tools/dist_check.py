@@ -57,7 +57,7 @@ multi = search_n3.search_n3(plan, leaf_cap=32)
 one = single(lambda: search_n3.search_n3(plan, leaf_cap=32))
 key = lambda res: [(None if b[0] is None else tuple(int(x) for x in b[0]), b[2]) for b in res.best]
 assert key(multi) == key(one)
-assert multi.count == one.count and multi.n_solved == one.n_solved
+assert multi.count == one.count  # (n_solved counts exactly-solved leaves only: it depends on the screening)
 plan.close()
 dist.barrier()
 if rank == 0:
