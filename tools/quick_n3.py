@@ -7,7 +7,8 @@ import theta_oracle as O
 from theta_b200 import _lib
 from theta_b200.search_n3 import search_n3
 _lib.init(0)
-for (m, k, F, tb, cap, maxit) in [(150, 5, 12, False, 512, 1 << 22), (500, 7, 12, True, 4096, 200000)]:
+CAPS = [int(x) for x in os.environ.get("LEAF_CAPS", "512").split(",")]
+for (m, k, F, tb, cap, maxit) in [(150, 5, 12, False, c, 1 << 22) for c in CAPS] + ([(500, 7, 12, True, 4096, 200000)] if "SKIP500" not in os.environ else []):
     P = O.synthetic_problem_n3(m, k, 1, F, tb)
     plan = _lib.Plan(3, P["r"], P["rN"], P["lower"], P["upper"])
     t0 = time.perf_counter(); ni = plan.prepare(cap, maxit); t1 = time.perf_counter()
