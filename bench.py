@@ -36,6 +36,7 @@ WORKLOADS = {
                   desc="synthetic m=150 n=2 k=5 seed=1 (BASELINE configs[1] data), upper bounds +2 copies (4.196e8 "
                        "candidates), first n_gpus x 25,251,156 ranks"),
     "m150k7": dict(m=150, k=7, seed=1, desc="synthetic m=150 n=2 k=7 seed=1 (>=100x target shape), full space"),
+    "cfg3": dict(m=300, k=7, seed=1, desc="synthetic m=300 n=2 k=7 seed=1 (BASELINE configs[2]), full space (1.698e11 candidates)"),
     "cfg3win": dict(m=300, k=7, seed=1, window=1 << 33,
                     desc="synthetic m=300 n=2 k=7 seed=1 (BASELINE configs[2]), first 2^33 ranks"),
 }
@@ -381,6 +382,21 @@ def main():
         extra["m150_k7_full_space"] = {"candidates": n7, "seconds": dt7, "cand_per_s": n7 / dt7, "min_nll": g7,
                                        "ms_pass1_rank0": plan7.stats()["ms_pass1"], "n_gpus": world}
         plan7.close()
+        # (a2) BASELINE configs[2]: m=300, k=7, the whole 1.698e11-candidate space (SURVEY 8d allowed a rank budget;
+        # at this rate the full space takes seconds)
+        P3f = problem("cfg3")
+        plan3f = _lib.Plan(2, P3f["r"], P3f["rN"], P3f["lower"], P3f["upper"])
+        n3f = plan3f.count()
+        b3f, e3f = search.shard_range(n3f, rank, world)
+        barrier()
+        t0 = time.perf_counter()
+        r3f, g3f = search.search_shard(plan3f, b3f, e3f, D, world, stream)
+        r3f = search.gather_records(r3f, D, world)
+        barrier()
+        dt3f = time.perf_counter() - t0
+        extra["m300_k7_full_space"] = {"candidates": n3f, "seconds": dt3f, "cand_per_s": n3f / dt3f, "min_nll": g3f,
+                                       "ms_pass1_rank0": plan3f.stats()["ms_pass1"], "n_records": int(len(r3f)), "n_gpus": world}
+        plan3f.close()
         # (b) n = 3: BASELINE configs[3] shape (m=150, k=5, explicit bounds, F=12), whole space, sharded by items
         import theta_oracle as O
         from theta_b200 import search_n3
@@ -411,7 +427,8 @@ def main():
                                        % ((total + world - 1) // world),
                            "l2_policy": "search kernel streams nothing from HBM (tables in shared memory); the "
                                         "roofline kernel uses tiles of %d MiB > L2" % (roof["tile_bytes"] >> 20 if roof else 0)},
-                "e2e": e2e, "gpu_launches": launches[0], "clocks": clocks, "roofline": roof,
+                "e2e": e2e, "time_to_best_nll_ms": e2e["ms_per_step"], "gpu_launches": launches[0], "clocks": clocks,
+                "roofline": roof,
                 "search_kernel": search_kernel, "cpu_baseline": cpu, "extra": extra,
                 "result": {"min_nll": g, "n_records": int(len(recs)), "n_solved": int(st["n_solved"])}}
         print(json.dumps(line))

@@ -311,3 +311,31 @@ def test_config3_rank_windows(lib):
                 assert abs(s[0][0] - cands["mu"][i][0]) <= MU_TOL
                 assert abs(s[1] - cands["nll"][i]) <= NLL_RTOL * abs(s[1])
     plan.close()
+
+
+def test_sharded_on_one_gpu_equals_unsharded(lib, golden):
+    """The multi-GPU decomposition exercised on one device: cut the rank space into 1, 2, 3 and 8 contiguous shards,
+    run pass 1 per shard, take the minimum of the shard minima (what the all-reduce(min) returns), run pass 2 per
+    shard with prior = +inf, concatenate the records in shard order and replay the fold -- the result must be the
+    unsharded one bit for bit (config #1 and the m=150 / k=5 space)."""
+    from theta_b200.search import fold_replay, search_n2, shard_range
+    O = _oracle()
+    g1 = golden("config1_search.json")["inputs"]
+    for P in (dict(r=g1["r"], rN=g1["rN"], lower=g1["lower"], upper=g1["upper"]), O.synthetic_problem_n2(150, 5, seed=1)):
+        plan = lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"])
+        N = plan.count()
+        one = search_n2(plan)
+        for world in (2, 3, 8):
+            mins, ranges = [], [shard_range(N, r_, world) for r_ in range(world)]
+            shard_plans = [lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"]) for _ in range(world)]
+            for sp, (b, e) in zip(shard_plans, ranges):
+                mins.append(sp.pass1(b, e))
+            g = min(mins)
+            recs = np.concatenate([sp.pass2(g) for sp in shard_plans])
+            idx = fold_replay(recs["rank"], recs["nll"], dup_first=True)
+            got = [(int(recs["rank"][i]), float(recs["mu"][i][0]), float(recs["nll"][i]), int(recs["status"][i])) for i in idx]
+            assert g == one.min_nll
+            assert got == one.best, (world, got, one.best)
+            for sp in shard_plans:
+                sp.close()
+        plan.close()
