@@ -242,9 +242,9 @@ def main():
 
     def step():
         # search kernel, min reduction [, NCCL all-reduce], stripe scan, emit kernel -- one host synchronisation
-        recs, g = search.search_shard(plan, begin, end, D, world, stream)
+        recs, g, _ = search.search_sharded(plan, begin, end, D, world, stream)
         launches[0] += 4
-        return search.gather_records(recs, D, world), g
+        return recs, g
 
     def barrier():
         torch.cuda.synchronize()
@@ -370,8 +370,8 @@ def main():
         b7, e7 = search.shard_range(n7, rank, world)
 
         def step7():
-            r_, g_ = search.search_shard(plan7, b7, e7, D, world, stream)
-            return search.gather_records(r_, D, world), g_
+            r_, g_, _ = search.search_sharded(plan7, b7, e7, D, world, stream)
+            return r_, g_
         for _ in range(2):
             step7()
         barrier()
@@ -390,8 +390,7 @@ def main():
         b3f, e3f = search.shard_range(n3f, rank, world)
         barrier()
         t0 = time.perf_counter()
-        r3f, g3f = search.search_shard(plan3f, b3f, e3f, D, world, stream)
-        r3f = search.gather_records(r3f, D, world)
+        r3f, g3f, _ = search.search_sharded(plan3f, b3f, e3f, D, world, stream)
         barrier()
         dt3f = time.perf_counter() - t0
         extra["m300_k7_full_space"] = {"candidates": n3f, "seconds": dt3f, "cand_per_s": n3f / dt3f, "min_nll": g3f,

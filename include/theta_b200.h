@@ -147,6 +147,16 @@ int theta_search_n2_pass2(theta_plan* plan, double global_min, double prior_min,
  * theta_search_n2_pass1_begin (no _end needed); *global_min_host receives the value that was used. */
 int theta_search_n2_pass2_dev(theta_plan* plan, const double* global_min_dev, double prior_min, theta_cand* out_host,
                               uint64_t cap, uint64_t* n_out, double* global_min_host, void* stream);
+/* Fully asynchronous form for the multi-GPU exchange (replaces returnQueue / find_mins, RunTHetA.py:141,162-171):
+ * pass 2 is enqueued and its status block + first `cap` raw records land in the caller's DEVICE buffer
+ * [uint64 status[32] | theta_cand records[cap]] -- the operand of ncclAllGather -- with no host synchronisation.
+ * status[11] (records emitted) > cap means the shard overflowed the buffer (fall back to theta_search_n2_pass2_dev).
+ * After synchronising, the caller passes its own status words to _async_done (statistics) and the union of all
+ * shards' raw records to theta_filter_records (sort by rank + the exact superset filter of the fold replay). */
+int theta_search_n2_pass2_enqueue(theta_plan* plan, const double* global_min_dev, double prior_min, void* out_dev,
+                                  uint64_t cap, void* stream);
+int theta_search_n2_async_done(theta_plan* plan, const unsigned long long* status_host);
+int theta_filter_records(theta_cand* recs, uint64_t n, double prior_min, double near_thr, uint64_t* n_out);
 int theta_search_stats_get(const theta_plan* plan, theta_search_stats* stats);
 /* Single-shard convenience: pass1 + pass2 with global_min = local_min, prior_min = +inf. */
 int theta_search_n2(theta_plan* plan, uint64_t rank_begin, uint64_t rank_end, theta_cand* out_host, uint64_t cap,

@@ -82,6 +82,9 @@ SYMBOLS = {
     "theta_search_n2_pass2": (C.c_int, [_VP, C.c_double, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP]),
     "theta_search_n2_pass2_dev": (C.c_int, [_VP, _VP, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64),
                                             C.POINTER(C.c_double), _VP]),
+    "theta_search_n2_pass2_enqueue": (C.c_int, [_VP, _VP, C.c_double, _VP, C.c_uint64, _VP]),
+    "theta_search_n2_async_done": (C.c_int, [_VP, _VP]),
+    "theta_filter_records": (C.c_int, [_VP, C.c_uint64, C.c_double, C.c_double, C.POINTER(C.c_uint64)]),
     "theta_search_stats_get": (C.c_int, [_VP, C.POINTER(SearchStats)]),
     "theta_search_n2": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
     "theta_eval_ranks_n2": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
@@ -331,6 +334,14 @@ class Plan(object):
             check(rc)
             return buf[:int(n.value)], float(g.value)
 
+    def pass2_enqueue(self, global_min_dev, out_dev, cap, prior_min=float("inf"), stream=None):
+        """Asynchronous pass 2 into a device buffer [u64 status[32] | records[cap]] (see include/theta_b200.h)."""
+        check(load().theta_search_n2_pass2_enqueue(self._h, global_min_dev, float(prior_min), out_dev, int(cap), stream))
+
+    def async_done(self, status_words):
+        st = np.ascontiguousarray(status_words, dtype=np.uint64)
+        check(load().theta_search_n2_async_done(self._h, ptr(st)))
+
     def stats(self):
         s = SearchStats()
         check(load().theta_search_stats_get(self._h, C.byref(s)))
@@ -371,6 +382,18 @@ class Plan(object):
         if cnt:
             check(load().theta_nll_tiles_n2(self._h, ptr(t), self.pitch, cnt, ptr(mu), ptr(nll)))
         return nll
+
+
+STATUS_WORDS = 32          # uint64 words of the device status block (theta_n2.cu)
+ST_SOLVED, ST_EMITTED, ST_LIST, ST_LOCAL_MIN, ST_GLOBAL_MIN = 1, 8 + 3, 16, 17, 18
+
+
+def filter_records(recs, near_thr, prior_min=float("inf")):
+    """theta_filter_records: sort raw pass-2 records by rank, keep NaN / strict prefix minima / near-minimum ones."""
+    recs = np.ascontiguousarray(recs)
+    n = C.c_uint64()
+    check(load().theta_filter_records(ptr(recs), len(recs), float(prior_min), float(near_thr), C.byref(n)))
+    return recs[:int(n.value)]
 
 
 def nll_single(mu, Cw, r):

@@ -844,6 +844,83 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
     return THETA_OK;
 }
 
+// Fully asynchronous pass 2 for the multi-GPU exchange: list scan + emit kernel are enqueued, then the status
+// block and the first `cap` raw (unsorted, unfiltered) records are copied device-to-device into the caller's
+// buffer  [ u64 status[32] | theta_cand records[cap] ]  -- the operand of the all-gather.  Nothing is waited for.
+// The caller fetches the gathered buffers, then hands its own status words to theta_search_n2_async_done and
+// all raw records to theta_filter_records.  status[8+3] > cap means this shard overflowed the exchange buffer.
+extern "C" int theta_search_n2_pass2_enqueue(theta_plan* pl, const double* global_min_dev, double prior_min,
+                                             void* out_dev, uint64_t cap, void* stream) {
+    if (!pl || !out_dev || cap == 0) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (pl->n != 2 || !pl->ev0) { set_error("pass2 without pass1"); return THETA_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t stripes = pl->p1_stripes;
+    const double margin = 2.5 * THETA_TIE_MARGIN;
+    const size_t want = std::max<size_t>(std::max<size_t>(1 << 14, pl->emit_cap), cap);
+    if (want > pl->emit_cap) {
+        theta::dfree(pl->d_emit); pl->d_emit = nullptr; pl->emit_cap = 0;
+        THETA_CUDA(theta::dmalloc(&pl->d_emit, sizeof(theta_cand) * want));
+        pl->emit_cap = want;
+    }
+    THETA_CUDA(cudaEventRecord(pl->ev2, st));
+    stripe_scan_kernel<<<1, 1024, 0, st>>>(pl->d_stripe_min, stripes, global_min_dev, prior_min, margin, pl->d_counters,
+                                           pl->d_list, pl->d_prior);
+    int rc = THETA_OK;
+    if (stripes && pl->p1_begin != pl->p1_end) {
+        SearchParams sp{};
+        sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
+        sp.begin = pl->p1_begin; sp.end = pl->p1_end; sp.L = pl->p1_L; sp.n_items = (uint32_t)stripes;
+        sp.n_items_dev = pl->d_counters + kStList;
+        sp.Lrun = std::min(pl->p1_L, 4); sp.units_per_item = (pl->p1_L + sp.Lrun - 1) / sp.Lrun;
+        sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters + kCounters;
+        sp.stripe_list = pl->d_list; sp.stripe_prior = pl->d_prior;
+        sp.near_thr = 0.0; sp.near_thr_base = pl->d_counters + kStGlobalMin; sp.near_margin = margin;
+        sp.emit = pl->d_emit; sp.emit_cap = pl->emit_cap;
+        switch (pl->KT) {
+#define THETA_P2(KTV) case KTV: rc = launch_search<KTV, true>(pl, sp, st); break;
+            THETA_P2(2) THETA_P2(3) THETA_P2(4) THETA_P2(5) THETA_P2(6) THETA_P2(7) THETA_P2(8) THETA_P2(10) THETA_P2(12) THETA_P2(15)
+#undef THETA_P2
+            default: set_error("unsupported level count"); rc = THETA_ERR_UNSUPPORTED;
+        }
+        if (rc) return rc;
+    }
+    THETA_CUDA(cudaEventRecord(pl->ev3, st));
+    unsigned char* out = static_cast<unsigned char*>(out_dev);
+    THETA_CUDA(cudaMemcpyAsync(out, pl->d_counters, sizeof(unsigned long long) * kStatusWords, cudaMemcpyDeviceToDevice, st));
+    THETA_CUDA(cudaMemcpyAsync(out + sizeof(unsigned long long) * kStatusWords, pl->d_emit, sizeof(theta_cand) * cap,
+                               cudaMemcpyDeviceToDevice, st));
+    return THETA_OK;
+}
+
+// After the caller has synchronised: record the statistics of the asynchronous search from this shard's status words.
+extern "C" int theta_search_n2_async_done(theta_plan* pl, const unsigned long long* status_host) {
+    if (!pl || !status_host) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (!pl->h_ctr) { set_error("no search in flight"); return THETA_ERR_INVALID; }
+    std::memcpy(pl->h_ctr, status_host, sizeof(unsigned long long) * kStatusWords);
+    pl->p1_pending = false;
+    read_pass1_stats(pl);
+    cudaEventElapsedTime(&pl->stats.ms_pass2, pl->ev2, pl->ev3);
+    pl->stats.n_rescanned = status_host[kStList];
+    return THETA_OK;
+}
+
+// Sort raw pass-2 records by rank and keep exactly what the fold replay needs: NaN values, strict prefix minima
+// of the sequence (starting from prior_min) and everything within near_thr.  In place; returns the new count.
+extern "C" int theta_filter_records(theta_cand* recs, uint64_t n, double prior_min, double near_thr, uint64_t* n_out) {
+    if ((!recs && n) || !n_out) { set_error("null argument"); return THETA_ERR_INVALID; }
+    std::sort(recs, recs + n, [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; });
+    size_t w = 0;
+    double run = prior_min;
+    for (size_t i = 0; i < n; ++i) {
+        const double v = recs[i].nll;
+        const bool keep = (v != v) || v < run || v <= near_thr;
+        if (v < run) run = v;
+        if (keep) recs[w++] = recs[i];
+    }
+    *n_out = w;
+    return THETA_OK;
+}
+
 // Host-value form: global_min is written to the status block and picked up by the device-side list builder.
 extern "C" int theta_search_n2_pass2(theta_plan* pl, double global_min, double prior_min, theta_cand* out_host,
                                      uint64_t cap, uint64_t* n_out, void* stream) {

@@ -9,6 +9,7 @@ the GPU through the C ABI (theta_b200/_lib.py); this module only
   * replays the reference's order-dependent tie fold (RunTHetA.py:198-206,
     Misc.isClose python/Misc.py:36-47) over the few records pass 2 returns.
 """
+import os
 import sys
 
 import numpy as np
@@ -134,6 +135,53 @@ def search_shard(plan, begin, end, dist, world, stream=None):
     return plan.pass2_dev(t.data_ptr(), INF, cur.cuda_stream)
 
 
+_XCAP = 1024  # raw records per shard carried by the stream-ordered exchange
+
+
+def search_sharded(plan, begin, end, dist, world, stream=None):
+    """The whole sharded search of one step.  Returns (records, global_min, n_solved): the records of all shards
+    sorted by rank (a superset of what the fold replay needs), identical on every rank.
+
+    Default: search_shard (pass 1 -> all-reduce(min) on the device double -> stripe scan + pass 2, one host wait)
+    followed by the fixed-size record all-gather (a second wait).  With THETA_ASYNC_EXCHANGE=1 everything is
+    enqueued in stream order and the host waits once: ... -> device-to-device copy of the status block and the
+    raw records into the exchange buffer -> all-gather -> one D2H copy."""
+    # The fully stream-ordered exchange below (one host wait per step) measured SLOWER than pass 2 + a separate
+    # record gather on 2 x B200 (1.39 vs 1.24 ms per step: the raw-record all-gather is 4x larger and the second
+    # wait is cheap), so it is opt-in (THETA_ASYNC_EXCHANGE=1) until it is tuned at 8 GPUs.
+    if (dist is None or not hasattr(plan, "pass2_enqueue") or dist.get_backend() != "nccl"
+            or os.environ.get("THETA_ASYNC_EXCHANGE") != "1"):
+        recs, g = search_shard(plan, begin, end, dist, world, stream)
+        allrecs, extras = gather_records(recs, dist, world, extra=[plan.stats()["n_solved"]])
+        return allrecs, g, sum(e[0] for e in extras)
+    import torch
+    cur = torch.cuda.current_stream()
+    if stream is not None and int(stream) != int(cur.cuda_stream):
+        raise ValueError("with NCCL the search must run on torch's current stream")
+    item = _lib.CAND_DTYPE.itemsize
+    head = 8 * _lib.STATUS_WORDS
+    nbytes = head + _XCAP * item
+    b = _bufs(dist, world, nbytes)
+    plan.pass1_begin(begin, end, b["min"].data_ptr(), cur.cuda_stream)
+    dist.all_reduce(b["min"], op=dist.ReduceOp.MIN)
+    plan.pass2_enqueue(b["min"].data_ptr(), b["send_d"].data_ptr(), _XCAP, INF, cur.cuda_stream)
+    dist.all_gather_into_tensor(b["recv_d"], b["send_d"])
+    b["recv_h"].copy_(b["recv_d"], non_blocking=True)
+    cur.synchronize()
+    raw = b["recv_h"].numpy().reshape(world, nbytes)
+    status = raw[:, :head].copy().view(np.uint64)  # [world, STATUS_WORDS]
+    plan.async_done(status[dist.get_rank()])
+    g = float(status[0, _lib.ST_GLOBAL_MIN:_lib.ST_GLOBAL_MIN + 1].view(np.float64)[0])
+    n_solved = int(status[:, _lib.ST_SOLVED].sum())
+    emitted = [int(v) for v in status[:, _lib.ST_EMITTED]]
+    if max(emitted) > _XCAP:  # a shard overflowed the exchange buffer (every rank sees it): synchronous path
+        recs, _ = plan.pass2_dev(b["min"].data_ptr(), INF, cur.cuda_stream)
+        return gather_records(recs, dist, world), g, n_solved
+    parts = [raw[r, head:head + emitted[r] * item].copy().view(_lib.CAND_DTYPE) for r in range(world)]
+    allraw = np.concatenate(parts) if parts else np.zeros(0, dtype=_lib.CAND_DTYPE)
+    return _lib.filter_records(allraw, g + 2.5 * TIE_MARGIN), g, n_solved
+
+
 _GATHER_CAP = 256  # records per shard carried by the fixed-size exchange
 _GATHER_HEAD = 8 * 4  # int64 header: record count + up to three extras
 
@@ -206,15 +254,14 @@ def search_n2(plan, stream=None, rank_limit=None):
     if rank_limit is not None:
         total = min(total, int(rank_limit))
     begin, end = shard_range(total, rank, world)
-    recs, g = search_shard(plan, begin, end, dist, world, stream)
+    allrecs, g, n_solved = search_sharded(plan, begin, end, dist, world, stream)
     stats = plan.stats()
-    allrecs, extras = gather_records(recs, dist, world, extra=[stats["n_solved"]])
     res = SearchResult()
     res.records = allrecs
     res.count = total
     res.min_nll = g
     res.stats = stats
-    res.n_solved = sum(e[0] for e in extras)
+    res.n_solved = n_solved
     idx = fold_replay(allrecs["rank"], allrecs["nll"], dup_first=True)
     res.best = [(int(allrecs["rank"][i]), float(allrecs["mu"][i][0]), float(allrecs["nll"][i]), int(allrecs["status"][i]))
                 for i in idx]
