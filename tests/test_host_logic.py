@@ -112,3 +112,30 @@ def test_shard_range_partitions():
             edges = [shard_range(total, r, world) for r in range(world)]
             assert edges[0][0] == 0 and edges[-1][1] == total
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+
+
+def test_filter_records_host_function():
+    """theta_filter_records (pure host code in the library): sort by rank, keep NaN / strict prefix minima / near ones."""
+    import numpy as np
+    from theta_b200 import _lib
+    rng = np.random.default_rng(7)
+    for trial in range(50):
+        n = int(rng.integers(0, 400))
+        recs = np.zeros(n, dtype=_lib.CAND_DTYPE)
+        recs["rank"] = rng.permutation(n).astype(np.uint64) * 3
+        recs["nll"] = 1e9 + rng.choice([0.0, 1e-4, 5e-4, 2e-3, 1.0, 50.0], size=n) * rng.integers(0, 40, size=n)
+        if n > 5:
+            recs["nll"][rng.integers(0, n, 2)] = np.nan
+        g = float(np.nanmin(recs["nll"])) if n and not np.all(np.isnan(recs["nll"])) else float("inf")
+        near = g + 2.5e-3
+        prior = float(rng.choice([np.inf, g + 10.0]))
+        want = []
+        run = prior
+        for i in np.argsort(recs["rank"], kind="stable"):
+            v = float(recs["nll"][i])
+            if v != v or v < run or v <= near:
+                want.append(int(recs["rank"][i]))
+            if v < run:
+                run = v
+        got = _lib.filter_records(recs.copy(), near, prior)
+        assert [int(x) for x in got["rank"]] == want

@@ -39,6 +39,7 @@ struct theta_n3_state {
     double* d_item_min = nullptr;
     unsigned long long* d_ctr = nullptr;
     std::vector<double> h_item_min;
+    std::vector<std::vector<double>> est;  // est[i][g*2+sw]: completions of a prefix ending in row g at interval i (no mu-bounds)
     uint64_t p1_begin = 0, p1_end = 0;
     unsigned long long nan_nll = 0;
     bool truncated = false;
@@ -194,8 +195,9 @@ struct Search3Params {
     uint32_t n_items;            // pass 1: number of items from item_begin; pass 2: listed items
     double* item_min;            // [n_items] (pass 1, indexed from item_begin)
     unsigned long long* ctr;     // [0] ticket [1] solved [2] nfev [3] emitted [4] nan [5] leaves
-    const uint32_t* list;        // pass 2
+    const uint32_t* list;        // pass 2 (NULL: item = ticket)
     const double* prior;         // pass 2
+    const uint64_t* rank_base;   // pass 2 over sub-items: (parent item << 32) | (sub-item << 12); NULL: item << 32
     double near_thr;
     theta_cand* emit;
     uint8_t* emit_paths;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) n3_search_kernel(const Search3Par
             if (!has_item) {
                 ticket = (uint32_t)atomicAdd(&p.ctr[0], 1ULL);
                 if (ticket >= p.n_items) { exhausted = true; break; }
-                item = EMIT ? p.list[ticket] : p.item_begin + ticket;
+                item = EMIT ? (p.list ? p.list[ticket] : ticket) : p.item_begin + ticket;
                 prior = EMIT ? p.prior[ticket] : 0.0;
                 dfs.load_prefix(D, p.prefix + p.off[item], (int)(p.off[item + 1] - p.off[item]));
                 tmin = INFINITY;
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) n3_search_kernel(const Search3Par
                 const unsigned long long slot = atomicAdd(&p.ctr[3], 1ULL);
                 if (slot < p.emit_cap) {
                     theta_cand c;
-                    c.rank = ((uint64_t)item << 32) | seq;
+                    c.rank = (p.rank_base ? p.rank_base[ticket] : ((uint64_t)item << 32)) + seq;
                     c.nll = o.nll;
                     c.mu[0] = o.mu[0]; c.mu[1] = o.mu[1]; c.mu[2] = o.mu[2];
                     c.status = o.status;
@@ -487,14 +489,18 @@ namespace {
 struct Expander {
     const theta_plan* pl;
     theta_n3_state* s;
-    std::vector<std::vector<double>> est;  // est[i][g*2+sw]
     double cap;
     size_t max_items;
     bool overflow = false;
     std::vector<uint8_t> path;
+    // where the items go (theta_n3_prepare: the plan's item list; pass 2: a temporary list of sub-items)
+    std::vector<uint8_t>* o_prefix = nullptr;
+    std::vector<uint32_t>* o_off = nullptr;
+    std::vector<double>* o_weight = nullptr;
 
     void build_est() {
         const int m = pl->m, NR = s->NR;
+        std::vector<std::vector<double>>& est = s->est;
         est.assign(m, std::vector<double>(NR * 2, 0.0));
         for (int g = 0; g < NR; ++g) est[m - 1][g * 2] = est[m - 1][g * 2 + 1] = 1.0;
         for (int i = m - 2; i >= 0; --i)
@@ -512,15 +518,15 @@ struct Expander {
                 }
     }
     void emit(int depth, double w) {
-        if (s->off.size() - 1 >= max_items) { overflow = true; return; }
-        s->prefix.insert(s->prefix.end(), path.begin(), path.begin() + depth + 1);
-        s->off.push_back((uint32_t)s->prefix.size());
-        s->weight.push_back(w);
+        if (o_off->size() - 1 >= max_items) { overflow = true; return; }
+        o_prefix->insert(o_prefix->end(), path.begin(), path.begin() + depth + 1);
+        o_off->push_back((uint32_t)o_prefix->size());
+        o_weight->push_back(w);
     }
     void rec(int depth, uint8_t mn, uint8_t mx, int sw) {
         if (overflow) return;
         const int g = path[depth];
-        const double w = est[depth][g * 2 + sw];
+        const double w = s->est[depth][g * 2 + sw];
         if (w <= 0.0) return;  // no completion even without the mu-bounds
         if (depth == pl->m - 1 || w <= cap) { emit(depth, w); return; }
         uint64_t c = s->edges[g] & s->allow[depth + 1];
@@ -534,9 +540,25 @@ struct Expander {
             rec(depth + 1, mn2, mx2, (sw && (s->eqmask >> w2 & 1)) ? 1 : 0);
         }
     }
+    // the sub-trees of one item (given by its prefix), each with at most `cap` leaves, in enumeration order
+    void run_from_prefix(const uint8_t* pre, int len) {
+        path.assign(pl->m, 0);
+        uint8_t mn = 0, mx = 255;
+        int sw = 0;
+        for (int i = 0; i < len; ++i) {
+            path[i] = pre[i];
+            if (i == 0) sw = (s->eqmask >> pre[0] & 1) ? 1 : 0;
+            else {
+                theta::step_bounds(s->ra[pre[i - 1]], s->rb[pre[i - 1]], s->ra[pre[i]], s->rb[pre[i]], mn, mx);
+                sw = (sw && (s->eqmask >> pre[i] & 1)) ? 1 : 0;
+            }
+        }
+        rec(len - 1, mn, mx, sw);
+    }
     void run() {
         build_est();
         path.assign(pl->m, 0);
+        o_prefix = &s->prefix; o_off = &s->off; o_weight = &s->weight;
         s->prefix.clear(); s->off.assign(1, 0); s->weight.clear();
         // Enumerator._generate_next_C_3 (Enumerator.py:172-187): first rows with a <= b, within bounds
         uint64_t c = s->allow[0] & s->symmask;
@@ -692,12 +714,60 @@ static int run_emit(theta_plan* pl, const std::vector<uint32_t>& list, const std
     const int m = pl->m;
     recs->clear(); paths->clear();
     if (list.empty()) return THETA_OK;
+    // Pass 2 walks only a handful of items, one thread each: cut every listed item into sub-trees of at most
+    // kSubCap leaves (same expander, started from the item's prefix) so that the walk is spread over many threads.
+    // Records keep the enumeration order through rank = (parent item << 32) | (sub-item << 12) | leaf-in-sub-item.
+    constexpr double kSubCap = 16.0;
+    std::vector<uint8_t> sub_prefix;
+    std::vector<uint32_t> sub_off(1, 0);
+    std::vector<double> sub_weight, sub_prior;
+    std::vector<uint64_t> sub_rank;
+    const bool split = !enumerate_only && !s->est.empty();
+    if (split) {
+        Expander ex{pl, s};
+        ex.cap = kSubCap;
+        ex.max_items = (size_t)1 << 30;
+        ex.o_prefix = &sub_prefix; ex.o_off = &sub_off; ex.o_weight = &sub_weight;
+        for (size_t k = 0; k < list.size(); ++k) {
+            const uint32_t it = list[k];
+            const uint8_t* pre = s->prefix.data() + s->off[it];
+            const int len = (int)(s->off[it + 1] - s->off[it]);
+            const size_t first = sub_off.size() - 1;
+            if (s->weight[it] <= kSubCap * 1048576.0) ex.run_from_prefix(pre, len);
+            size_t n_sub = sub_off.size() - 1 - first;
+            if (n_sub == 0 || n_sub >= ((size_t)1 << 20)) {  // not split (huge item, or nothing survived): the item itself
+                sub_prefix.resize(sub_off[first]); sub_off.resize(first + 1); sub_weight.resize(first);
+                sub_prefix.insert(sub_prefix.end(), pre, pre + len);
+                sub_off.push_back((uint32_t)sub_prefix.size());
+                sub_weight.push_back(s->weight[it]);
+                n_sub = 1;
+            }
+            for (size_t j = 0; j < n_sub; ++j) {
+                sub_rank.push_back(((uint64_t)it << 32) | ((uint64_t)j << 12));
+                sub_prior.push_back(prior[k]);
+            }
+        }
+    }
+    const size_t n_work = split ? sub_rank.size() : list.size();
     uint32_t* d_list = nullptr; double* d_prior = nullptr; theta_cand* d_emit = nullptr; uint8_t* d_paths = nullptr;
+    uint8_t* d_sub_prefix = nullptr; uint32_t* d_sub_off = nullptr; uint64_t* d_sub_rank = nullptr;
     int rc = THETA_OK;
-    cudaError_t e = theta::dmalloc(&d_list, sizeof(uint32_t) * list.size());
-    if (e == cudaSuccess) e = theta::dmalloc(&d_prior, sizeof(double) * list.size());
-    if (e == cudaSuccess) e = cudaMemcpy(d_list, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_prior, prior.data(), sizeof(double) * list.size(), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaSuccess;
+    if (split) {
+        e = theta::dmalloc(&d_sub_prefix, std::max<size_t>(1, sub_prefix.size()));
+        if (e == cudaSuccess) e = theta::dmalloc(&d_sub_off, sizeof(uint32_t) * sub_off.size());
+        if (e == cudaSuccess) e = theta::dmalloc(&d_sub_rank, sizeof(uint64_t) * n_work);
+        if (e == cudaSuccess) e = theta::dmalloc(&d_prior, sizeof(double) * n_work);
+        if (e == cudaSuccess) e = cudaMemcpy(d_sub_prefix, sub_prefix.data(), sub_prefix.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_sub_off, sub_off.data(), sizeof(uint32_t) * sub_off.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_sub_rank, sub_rank.data(), sizeof(uint64_t) * n_work, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_prior, sub_prior.data(), sizeof(double) * n_work, cudaMemcpyHostToDevice);
+    } else {
+        e = theta::dmalloc(&d_list, sizeof(uint32_t) * list.size());
+        if (e == cudaSuccess) e = theta::dmalloc(&d_prior, sizeof(double) * list.size());
+        if (e == cudaSuccess) e = cudaMemcpy(d_list, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_prior, prior.data(), sizeof(double) * list.size(), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) rc = cuda_fail(e, "n3 emit setup", __FILE__, __LINE__);
     size_t cap = 1 << 14;
     for (int attempt = 0; rc == THETA_OK && attempt < 8; ++attempt) {
@@ -708,8 +778,10 @@ static int run_emit(theta_plan* pl, const std::vector<uint32_t>& list, const std
         if (e != cudaSuccess) { rc = cuda_fail(e, "n3 emit buffers", __FILE__, __LINE__); break; }
         Search3Params sp{};
         fill_dev(pl, &sp.D);
-        sp.prefix = s->d_prefix; sp.off = s->d_off; sp.n_items = (uint32_t)list.size(); sp.ctr = s->d_ctr;
-        sp.list = d_list; sp.prior = d_prior; sp.near_thr = near_thr; sp.emit = d_emit; sp.emit_paths = d_paths;
+        sp.prefix = split ? d_sub_prefix : s->d_prefix; sp.off = split ? d_sub_off : s->d_off;
+        sp.n_items = (uint32_t)n_work; sp.ctr = s->d_ctr;
+        sp.list = split ? nullptr : d_list; sp.rank_base = split ? d_sub_rank : nullptr;
+        sp.prior = d_prior; sp.near_thr = near_thr; sp.emit = d_emit; sp.emit_paths = d_paths;
         sp.emit_cap = cap; sp.enumerate_only = enumerate_only;
         {
             const char* ev = getenv("THETA_VERIFY_APPROX");
@@ -742,6 +814,7 @@ static int run_emit(theta_plan* pl, const std::vector<uint32_t>& list, const std
         break;
     }
     theta::dfree(d_list); theta::dfree(d_prior); theta::dfree(d_emit); theta::dfree(d_paths);
+    theta::dfree(d_sub_prefix); theta::dfree(d_sub_off); theta::dfree(d_sub_rank);
     if (rc) return rc;
     // sort by enumeration order, carrying the paths along
     std::vector<uint32_t> idx(recs->size());
@@ -784,6 +857,24 @@ extern "C" int theta_search_n3_pass2(theta_plan* pl, double global_min, double p
     std::vector<uint8_t> paths;
     rc = run_emit(pl, list, prior, near_thr, 0, &recs, &paths, (cudaStream_t)stream);
     if (rc) return rc;
+    {   // the device emits a superset (every sub-item restarts its running minimum): keep exactly the NaN values,
+        // the strict prefix minima w.r.t. everything before this shard, and the near-minimum set
+        const size_t m = (size_t)pl->m;
+        size_t w = 0;
+        double run = prior_min;
+        for (size_t i = 0; i < recs.size(); ++i) {
+            const double v = recs[i].nll;
+            const bool keep = (v != v) || v < run || v <= near_thr;
+            if (v < run) run = v;
+            if (keep) {
+                if (w != i) { recs[w] = recs[i]; std::memmove(paths.data() + w * m, paths.data() + i * m, m); }
+                recs[w].flags = (int32_t)w;
+                ++w;
+            }
+        }
+        recs.resize(w);
+        paths.resize(w * m);
+    }
     *n_out = recs.size();
     if (recs.size() > cap) { set_error("pass2 produced %zu records, buffer holds %llu", recs.size(), (unsigned long long)cap); return THETA_ERR_OVERFLOW; }
     if (out_host && !recs.empty()) std::memcpy(out_host, recs.data(), sizeof(theta_cand) * recs.size());
