@@ -167,12 +167,14 @@ struct Screen3 {
 };
 
 #ifdef __CUDACC__
+// LT: the fast_log table in shared memory.  With it f(y) is evaluated in fp64 (E shrinks from 6e-6 Rtot to the
+// rounding noise of the sums) at ~20 more instructions per group; LT == nullptr keeps the fp32 MUFU logarithms.
 __device__ __noinline__ bool n3_screen(const Groups3& g, double S1, double S2, const N3Const& k, Screen3& ws,
-                                       double T_plus_margin, double& lb_out) {
+                                       double T_plus_margin, double& lb_out, const double2* LT = nullptr) {
     lb_out = -INFINITY;
     if (k.any_zero_rN || !(S1 > 0.0) || !(S2 > 0.0)) return false;
     const double t1 = k.A / S1, t2 = k.A / S2;  // A d_g = y0 + a (A/S1) y1 + b (A/S2) y2
-    const double E = THETA_N3_APPROX_C * k.Rtot;
+    const double E = (LT ? 1e-11 : THETA_N3_APPROX_C) * k.Rtot;
     double y0 = ws.y0, y1 = ws.y1;
     if (!(y0 > 1e-6 && y1 > 1e-6 && y0 + y1 < 1.0 - 1e-6)) { y0 = 1.0 / 3.0; y1 = 1.0 / 3.0; }
     for (int it = 0; it < 3; ++it) {
@@ -187,15 +189,19 @@ __device__ __noinline__ bool n3_screen(const Groups3& g, double S1, double S2, c
             const double q = R * r, qq = q * r, aq = a * qq, bq = b * qq;
             s0 += q; s1 = fma(a, q, s1); s2 = fma(b, q, s2);
             h00 += qq; h01 += aq; h02 += bq; h11 = fma(a, aq, h11); h12 = fma(a, bq, h12); h22 = fma(b, bq, h22);
-            const float df = (float)d;
-            if (!(df >= 3.0517578125e-05f && df <= 32768.0f)) ok = false;
-            lacc = fma(R, (double)__log2f(df), lacc);
+            if (LT) {
+                lacc = fma(R, fast_log(d, LT), lacc);  // natural log, |error| ~ 1e-16
+            } else {
+                const float df = (float)d;
+                if (!(df >= 3.0517578125e-05f && df <= 32768.0f)) ok = false;
+                lacc = fma(R, (double)__log2f(df), lacc);
+            }
         }
         if (!ok) return false;
         // gradient components (up to sign): G_j = t_j sum c_gj q_g ; gap = max_j G_j - Rtot
         const double G0 = s0, G1 = t1 * s1, G2 = t2 * s2;
         const double gap = fmax(G0, fmax(G1, G2)) - k.Rtot;
-        const double fy = fma(-0.6931471805599453094, lacc, k.K0);
+        const double fy = LT ? k.K0 - lacc : fma(-0.6931471805599453094, lacc, k.K0);
         const double lb = fy - fmax(gap, 0.0) * (1.0 + 1e-9) - E;
         if (lb > lb_out) lb_out = lb;
         if (lb > T_plus_margin) { ws.y0 = y0; ws.y1 = y1; return true; }
