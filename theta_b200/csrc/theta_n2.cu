@@ -105,12 +105,17 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
         const uint64_t s_end = min(p.end, (uint64_t)(s_begin + (uint64_t)32 * (uint64_t)p.L));
         const uint64_t r0 = s_begin + ((uint64_t)sub * 32u + lane) * (uint64_t)p.Lrun;
         double tmin = INFINITY;
-        if (r0 < s_end) {
-            const int cnt = (int)min((uint64_t)p.Lrun, s_end - r0);
+        {
+            const int cnt = r0 < s_end ? (int)min((uint64_t)p.Lrun, s_end - r0) : 0;
             int q[KT];
-            n2_unrank<KT>(T_, r0, q);
+            if (cnt) n2_unrank<KT>(T_, r0, q);
             double xprev = -1.0, xprev2 = -1.0;  // roots of the previous two columns (warm start)
-            for (int t = 0; t < cnt; ++t) {
+            // pass 1 runs the same trip count in every lane so that the warp can pool its thresholds every 8
+            // columns (candidates of the same stripe: the stripe is re-walked by pass 2 whenever it matters)
+            const int trips = EMIT ? cnt : p.Lrun;
+            for (int t = 0; t < trips; ++t) {
+                if (!EMIT && (t & 7) == 0 && t) T = warp_min(T);
+                if (t >= cnt) continue;
                 double R[KT + 1], S1;
                 bool z;
                 n2_groups<KT>(T_, q, R, S1, z);
