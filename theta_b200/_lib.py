@@ -142,6 +142,17 @@ def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _int_array(v, dtype):
+    """int(x) for every element (the reference's lists hold Python ints; strings / floats are converted the same way)."""
+    try:
+        a = np.asarray(v)
+        if a.dtype.kind in "iu":
+            return np.ascontiguousarray(a, dtype=dtype)
+    except (TypeError, ValueError):
+        pass
+    return np.ascontiguousarray(np.asarray([int(x) for x in v], dtype=dtype))
+
+
 class Plan(object):
     """Owns a theta_plan: device tables of one problem at the do_optimization* boundary."""
 
@@ -151,10 +162,10 @@ class Plan(object):
         self.m = len(r)
         self.tau = int(tau)
         self.max_normal = float(max_normal)
-        self._r = np.ascontiguousarray(np.asarray([int(v) for v in r], dtype=np.int64))
-        self._rN = np.ascontiguousarray(np.asarray([int(v) for v in rN], dtype=np.int64))
-        self._lo = np.ascontiguousarray(np.asarray([int(v) for v in lower], dtype=np.int32))
-        self._up = np.ascontiguousarray(np.asarray([int(v) for v in upper], dtype=np.int32))
+        self._r = _int_array(r, np.int64)
+        self._rN = _int_array(rN, np.int64)
+        self._lo = _int_array(lower, np.int32)
+        self._up = _int_array(upper, np.int32)
         if not (len(self._rN) == len(self._lo) == len(self._up) == self.m):
             raise ValueError("r, rN, lower, upper must have the same length")
         prob = Problem(self.n, self.m, self.tau, 0,

@@ -32,11 +32,12 @@ def fold_replay(ranks, nlls, dup_first=True):
     twice: the drivers evaluate the first matrix twice, RunTHetA.py:148,188 -- Q1).
     """
     best, m_ = [], INF
-    for i in range(len(ranks)):
-        reps = 2 if (dup_first and int(ranks[i]) == 0) else 1
+    ranks = ranks.tolist() if hasattr(ranks, "tolist") else list(ranks)
+    nlls = nlls.tolist() if hasattr(nlls, "tolist") else list(nlls)
+    for i, nll in enumerate(nlls):
+        reps = 2 if (dup_first and ranks[i] == 0) else 1
         for _ in range(reps):
-            nll = float(nlls[i])
-            if is_close(nll, m_):
+            if not (abs(nll - m_) > TIE_MARGIN):  # Misc.isClose: NaN counts as close (Q6)
                 best.append(i)
             elif nll < m_:
                 best = [i]
@@ -329,9 +330,8 @@ def do_optimization_single(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_
     try:
         # Enumerator._check_bound_order edits the caller's lists in place (Q16)
         lo, up = plan.bounds()
-        for i in range(len(lower_bounds)):
-            lower_bounds[i] = int(lo[i])
-            upper_bounds[i] = int(up[i])
+        lower_bounds[:] = lo.tolist()
+        upper_bounds[:] = up.tolist()
         try:
             res = search_n2(plan, rank_limit=rank_limit)
         except _lib.EmptySpaceError:
