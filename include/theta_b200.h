@@ -161,6 +161,13 @@ int theta_search_stats_get(const theta_plan* plan, theta_search_stats* stats);
 /* Single-shard convenience: pass1 + pass2 with global_min = local_min, prior_min = +inf. */
 int theta_search_n2(theta_plan* plan, uint64_t rank_begin, uint64_t rank_end, theta_cand* out_host, uint64_t cap,
                     uint64_t* n_out);
+/* do_optimization_single (RunTHetA.py:173-220) for n=2 in one call, host buffers in and out: plan creation, both
+ * passes, the reference's running-min fold over the emitted records, and for each surviving solution (fold order,
+ * up to cap_best) its record, its tumour column cols[k][m] (sorted interval order) and Optimizer.solve's vals[k][m].
+ * rank_limit = 0 searches the whole space.  lower_out / upper_out receive the monotonised bounds (Q16). */
+int theta_optimize_n2(const theta_problem* p, uint64_t rank_limit, int32_t* lower_out, int32_t* upper_out,
+                      uint64_t cap_best, uint64_t* n_best, theta_cand* best, int8_t* cols, double* vals,
+                      theta_search_stats* stats, uint64_t* n_candidates);
 /* (mu, NLL, status, vals[m]) of given ranks -- Optimizer.solve's return for the winners (Optimizer.py:123-126). */
 int theta_eval_ranks_n2(theta_plan* plan, const uint64_t* ranks_host, int64_t count, theta_cand* out_host,
                         double* vals_host /* [count][m] or NULL */);

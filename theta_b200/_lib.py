@@ -87,6 +87,8 @@ SYMBOLS = {
     "theta_filter_records": (C.c_int, [_VP, C.c_uint64, C.c_double, C.c_double, C.POINTER(C.c_uint64)]),
     "theta_search_stats_get": (C.c_int, [_VP, C.POINTER(SearchStats)]),
     "theta_search_n2": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "theta_optimize_n2": (C.c_int, [C.POINTER(Problem), C.c_uint64, _VP, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP, _VP, _VP,
+                                    C.POINTER(SearchStats), C.POINTER(C.c_uint64)]),
     "theta_eval_ranks_n2": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
     "theta_solve_tiles_n2_dev": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP, _VP]),
     "theta_solve_tiles_n2": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP]),
@@ -393,6 +395,37 @@ class Plan(object):
         if cnt:
             check(load().theta_nll_tiles_n2(self._h, ptr(t), self.pitch, cnt, ptr(mu), ptr(nll)))
         return nll
+
+
+def optimize_n2(r, rN, lower, upper, tau=2, max_normal=1.0, rank_limit=None, cap_best=64):
+    """theta_optimize_n2: the whole single-GPU n=2 search in one C call.
+    Returns (lower, upper, best records [fold order], cols [n_best, m] int8, vals [n_best, m], stats dict, n_candidates)."""
+    init()
+    ra, rNa = _int_array(r, np.int64), _int_array(rN, np.int64)
+    lo, up = _int_array(lower, np.int32), _int_array(upper, np.int32)
+    m = len(ra)
+    if not (len(rNa) == len(lo) == len(up) == m):
+        raise ValueError("r, rN, lower, upper must have the same length")
+    prob = Problem(2, m, int(tau), 0, ra.ctypes.data_as(C.POINTER(C.c_int64)), rNa.ctypes.data_as(C.POINTER(C.c_int64)),
+                   lo.ctypes.data_as(C.POINTER(C.c_int32)), up.ctypes.data_as(C.POINTER(C.c_int32)), float(max_normal))
+    lo_out = np.empty(m, dtype=np.int32)
+    up_out = np.empty(m, dtype=np.int32)
+    while True:
+        best = np.empty(cap_best, dtype=CAND_DTYPE)
+        cols = np.empty((cap_best, m), dtype=np.int8)
+        vals = np.empty((cap_best, m), dtype=np.float64)
+        n = C.c_uint64()
+        nc = C.c_uint64()
+        st = SearchStats()
+        rc = load().theta_optimize_n2(C.byref(prob), int(rank_limit or 0), ptr(lo_out), ptr(up_out), cap_best, C.byref(n),
+                                      ptr(best), ptr(cols), ptr(vals), C.byref(st), C.byref(nc))
+        if rc == ERR_OVERFLOW and n.value > cap_best:
+            cap_best = int(n.value) + 8
+            continue
+        check(rc)
+        k = int(n.value)
+        return (lo_out, up_out, best[:k], cols[:k], vals[:k], {f: getattr(st, f) for f, _ in SearchStats._fields_},
+                int(nc.value))
 
 
 STATUS_WORDS = 32          # uint64 words of the device status block (theta_n2.cu)

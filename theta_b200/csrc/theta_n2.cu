@@ -955,6 +955,70 @@ extern "C" int theta_search_n2(theta_plan* pl, uint64_t rank_begin, uint64_t ran
     return theta_search_n2_pass2(pl, g, INFINITY, out_host, cap, n_out, nullptr);
 }
 
+// do_optimization_single (python/RunTHetA.py:173-220) for n=2 in ONE call: plan, both passes, the reference's
+// running-min fold (RunTHetA.py:198-206 with Misc.isClose, the first matrix evaluated twice -- Q1, NaN counts as
+// close -- Q6) over the emitted records, and for each survivor its tumour column and Optimizer.solve's `vals`.
+// The winners come back in fold order (a rank can appear twice).  *n_best may exceed cap_best (THETA_ERR_OVERFLOW).
+extern "C" int theta_optimize_n2(const theta_problem* prob, uint64_t rank_limit, int32_t* lower_out, int32_t* upper_out,
+                                 uint64_t cap_best, uint64_t* n_best, theta_cand* best, int8_t* cols, double* vals,
+                                 theta_search_stats* stats, uint64_t* n_candidates) {
+    if (!prob || !n_best || (cap_best && (!best || !cols || !vals))) { set_error("null argument"); return THETA_ERR_INVALID; }
+    *n_best = 0;
+    if (prob->n != 2) { set_error("theta_optimize_n2 needs n == 2"); return THETA_ERR_INVALID; }
+    theta_plan* pl = nullptr;
+    int rc = theta_plan_create(prob, &pl);
+    if (rc) return rc;
+    const int m = pl->m;
+    if (lower_out) std::memcpy(lower_out, pl->lower.data(), sizeof(int32_t) * m);
+    if (upper_out) std::memcpy(upper_out, pl->upper.data(), sizeof(int32_t) * m);
+    const uint64_t total = rank_limit ? std::min<uint64_t>(pl->count, rank_limit) : pl->count;
+    if (n_candidates) *n_candidates = total;
+    std::vector<theta_cand> recs(1024);
+    uint64_t n = 0;
+    rc = theta_search_n2_pass1_begin(pl, 0, total, nullptr, nullptr);
+    if (rc == THETA_OK) {
+        rc = theta_search_n2_pass2_dev(pl, nullptr, INFINITY, recs.data(), recs.size(), &n, nullptr, nullptr);
+        if (rc == THETA_ERR_OVERFLOW && n > recs.size()) {
+            recs.resize(n + 16);
+            rc = theta_search_n2_pass2_dev(pl, nullptr, INFINITY, recs.data(), recs.size(), &n, nullptr, nullptr);
+        }
+    }
+    if (rc) { theta_plan_destroy(pl); return rc; }
+    if (stats) *stats = pl->stats;
+    // the fold, verbatim
+    std::vector<uint32_t> keep;
+    double M = INFINITY;
+    for (uint64_t i = 0; i < n; ++i) {
+        const int reps = recs[i].rank == 0 ? 2 : 1;
+        for (int k = 0; k < reps; ++k) {
+            const double L = recs[i].nll;
+            if (!(fabs(L - M) > THETA_TIE_MARGIN)) keep.push_back((uint32_t)i);
+            else if (L < M) { keep.assign(1, (uint32_t)i); M = L; }
+        }
+    }
+    *n_best = keep.size();
+    if (keep.size() > cap_best) {
+        set_error("%zu solutions tie, the caller's buffers hold %llu", keep.size(), (unsigned long long)cap_best);
+        theta_plan_destroy(pl);
+        return THETA_ERR_OVERFLOW;
+    }
+    if (!keep.empty()) {
+        std::vector<uint64_t> ranks(keep.size());
+        for (size_t k = 0; k < keep.size(); ++k) { ranks[k] = recs[keep[k]].rank; best[k] = recs[keep[k]]; }
+        std::vector<theta_cand> ev(keep.size());
+        rc = theta_eval_ranks_n2(pl, ranks.data(), (int64_t)ranks.size(), ev.data(), vals);
+        const int64_t pitch = pl->tile_pitch;
+        std::vector<int8_t> tile((size_t)pitch);
+        for (size_t k = 0; rc == THETA_OK && k < keep.size(); ++k) {
+            if (k && ranks[k] == ranks[k - 1]) { std::memcpy(cols + k * (size_t)m, cols + (k - 1) * (size_t)m, m); continue; }
+            rc = theta_enumerate_n2(pl, ranks[k], 1, tile.data(), pitch);
+            if (rc == THETA_OK) std::memcpy(cols + k * (size_t)m, tile.data(), m);
+        }
+    }
+    theta_plan_destroy(pl);
+    return rc;
+}
+
 extern "C" int theta_eval_ranks_n2(theta_plan* pl, const uint64_t* ranks_host, int64_t count, theta_cand* out_host,
                                    double* vals_host) {
     if (!pl || !ranks_host || !out_host) { set_error("null argument"); return THETA_ERR_INVALID; }

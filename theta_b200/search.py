@@ -326,6 +326,28 @@ def do_optimization_single(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_
         return do_optimization_n3(m, k, tau, lower_bounds, upper_bounds, r, rN, sorted_index, get_values, prefix)
     if n != 2:
         raise ValueError("n must be 2 or 3 (FileIO.py:42)")
+    if _dist_state()[2] is None and not get_values:
+        # single GPU: the whole search is one C call (theta_optimize_n2: plan, both passes, fold, winners)
+        try:
+            lo, up, recs, cols, vals, _st, _nc = _lib.optimize_n2(r, rN, lower_bounds, upper_bounds, tau, max_normal, rank_limit)
+        except _lib.EmptySpaceError:
+            # Enumerator._check_bound_order edits the caller's lists before the reference notices (Q16)
+            print(_NO_PROFILES)
+            sys.exit(1)
+        lower_bounds[:] = lo.tolist()
+        upper_bounds[:] = up.tolist()
+        best = []
+        si = np.asarray(sorted_index, dtype=np.int64)
+        for k in range(len(recs)):
+            C = np.zeros((m, 2))
+            C[si, 0] = tau
+            C[si, 1] = cols[k]
+            mu0 = np.float64(recs["mu"][k][0])
+            v = [0] * m
+            for i, x in zip(sorted_index, vals[k].tolist()):
+                v[i] = np.float64(x)
+            best.append((C, (mu0, 1 - mu0), np.float64(recs["nll"][k]), v))
+        return best
     plan = Plan(2, r, rN, lower_bounds, upper_bounds, tau=tau, max_normal=max_normal)
     try:
         # Enumerator._check_bound_order edits the caller's lists in place (Q16)
