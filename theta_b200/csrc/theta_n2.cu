@@ -407,7 +407,8 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
     pl->kc.tau = (double)p->tau; pl->kc.max_normal = p->max_normal; pl->kc.any_zero_rN = zero_rN; pl->kc.m = m;
     // tables
     pl->layout = TableLayout(m, KT);
-    std::vector<unsigned char> blob(pl->layout.bytes, 0);
+    pl->h_tables.assign(pl->layout.bytes, 0);
+    std::vector<unsigned char>& blob = pl->h_tables;
     double* SR = reinterpret_cast<double*>(blob.data() + pl->layout.off_SR);
     double* SRN = reinterpret_cast<double*>(blob.data() + pl->layout.off_SRN);
     uint64_t* SW = reinterpret_cast<uint64_t*>(blob.data() + pl->layout.off_SW);
@@ -955,6 +956,31 @@ extern "C" int theta_search_n2(theta_plan* pl, uint64_t rank_begin, uint64_t ran
     return theta_search_n2_pass2(pl, g, INFINITY, out_host, cap, n_out, nullptr);
 }
 
+// Host mirror of n2_unrank (theta_n2.cuh): tumour column of `rank` from the plan's count tables.
+static void host_column_of_rank(const theta_plan* pl, uint64_t rank, int8_t* col) {
+    const TableLayout& L = pl->layout;
+    const int m = pl->m, KT = pl->KT;
+    const uint64_t* SW = reinterpret_cast<const uint64_t*>(pl->h_tables.data() + L.off_SW);
+    const int32_t* qlo = reinterpret_cast<const int32_t*>(pl->h_tables.data() + L.off_qlo);
+    const int32_t* qhi = reinterpret_cast<const int32_t*>(pl->h_tables.data() + L.off_qhi);
+    std::memset(col, 0, (size_t)m);
+    uint64_t rem = rank;
+    int prev = 0;
+    for (int v = KT; v >= 1; --v) {
+        const uint64_t* sw = SW + (size_t)(v - 1) * (m + 2);
+        int lo = std::max(prev, (int)qlo[v - 1]), hi = qhi[v - 1];
+        const uint64_t base = sw[lo];
+        int l = lo;
+        while (l < hi) {
+            const int mid = (l + hi) >> 1;
+            if (base - sw[mid + 1] > rem) hi = mid; else l = mid + 1;
+        }
+        rem -= base - sw[l];
+        prev = l;
+        for (int i = m - l; i < m; ++i) col[i] += 1;  // q_v = l intervals (the last l in sorted order) have c_i >= v
+    }
+}
+
 // do_optimization_single (python/RunTHetA.py:173-220) for n=2 in ONE call: plan, both passes, the reference's
 // running-min fold (RunTHetA.py:198-206 with Misc.isClose, the first matrix evaluated twice -- Q1, NaN counts as
 // close -- Q6) over the emitted records, and for each survivor its tumour column and Optimizer.solve's `vals`.
@@ -1002,18 +1028,23 @@ extern "C" int theta_optimize_n2(const theta_problem* prob, uint64_t rank_limit,
         theta_plan_destroy(pl);
         return THETA_ERR_OVERFLOW;
     }
-    if (!keep.empty()) {
-        std::vector<uint64_t> ranks(keep.size());
-        for (size_t k = 0; k < keep.size(); ++k) { ranks[k] = recs[keep[k]].rank; best[k] = recs[keep[k]]; }
-        std::vector<theta_cand> ev(keep.size());
-        rc = theta_eval_ranks_n2(pl, ranks.data(), (int64_t)ranks.size(), ev.data(), vals);
-        const int64_t pitch = pl->tile_pitch;
-        std::vector<int8_t> tile((size_t)pitch);
-        for (size_t k = 0; rc == THETA_OK && k < keep.size(); ++k) {
-            if (k && ranks[k] == ranks[k - 1]) { std::memcpy(cols + k * (size_t)m, cols + (k - 1) * (size_t)m, m); continue; }
-            rc = theta_enumerate_n2(pl, ranks[k], 1, tile.data(), pitch);
-            if (rc == THETA_OK) std::memcpy(cols + k * (size_t)m, tile.data(), m);
+    // columns by host-side unranking, vals_i = numer_i / denom of Optimizer.L2 (Optimizer.py:187-196) at the
+    // record's mu: no further kernel launch after pass 2
+    for (size_t k = 0; k < keep.size(); ++k) {
+        best[k] = recs[keep[k]];
+        int8_t* col = cols + k * (size_t)m;
+        double* vk = vals + k * (size_t)m;
+        if (k && best[k].rank == best[k - 1].rank) {
+            std::memcpy(col, col - m, (size_t)m);
+            std::memcpy(vk, vk - m, sizeof(double) * (size_t)m);
+            continue;
         }
+        host_column_of_rank(pl, best[k].rank, col);
+        const double mu = best[k].mu[0], mu1 = 1.0 - mu;
+        double S1 = 0.0;
+        for (int i = 0; i < m; ++i) S1 += (double)pl->rN[i] * (double)col[i];  // exact (< 2^53)
+        const double D = mu * pl->kc.S0 + mu1 * S1;
+        for (int i = 0; i < m; ++i) vk[i] = (double)pl->rN[i] * (pl->kc.tau * mu + (double)col[i] * mu1) / D;
     }
     theta_plan_destroy(pl);
     return rc;

@@ -129,6 +129,7 @@ struct theta_plan {
     double max_normal = 1.0;
     std::vector<int32_t> lower, upper;  // monotonised (Enumerator.py:90-113)
     std::vector<int64_t> r, rN;
+    std::vector<unsigned char> h_tables;  // host copy of the table blob (host-side unranking of the winners)
     uint64_t count = 0;
     theta::N2Const kc;
     theta::TableLayout layout;
