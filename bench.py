@@ -275,8 +275,8 @@ def main():
     value = total * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: the public call (host lists in, the reference-shaped Python `best` list out), every step from
-    # scratch: plan creation + H2D of the tables, both passes, D2H of stripe minima and records, fold replay,
-    # `vals` of the winners.
+    # scratch: one C-ABI call at N=1 (theta_optimize_n2: tables built on the host, staged in pinned memory, one H2D;
+    # both passes; D2H of the status block and records; the fold; winners' columns and vals).
     def e2e_step():
         return search.do_optimization_single(2, P["m"], P["k"], 2, list(P["lower"]), list(P["upper"]), P["r"], P["rN"],
                                              1.0, P["sorted_index"], True, False, rank_limit=total)
@@ -291,9 +291,12 @@ def main():
     tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-    h2d = plan.table_bytes() + plan.m * (8 + 8) + 2 * 8 * (plan.pitch + 1) + 4 * (plan.pitch + 1) + 16 * 256 \
-        + 12 * int(st["n_rescanned"]) + 8 * max(1, len(best))
-    d2h = 8 * st["n_stripes"] + 64 * 2 + 48 * max(1, len(recs)) + (48 + 8 * plan.m + plan.pitch) * max(1, len(best))
+    # bytes that cross PCIe per call: H2D = the plan arena (count tables, r, rN, their prefix sums, status block);
+    # D2H = the status block + the speculative record window of pass 2 (theta_n2.cu: 1024 x 48 B)
+    up256 = lambda v: (v + 255) & ~255
+    h2d = (up256(plan.table_bytes()) + 2 * up256(8 * plan.m) + 2 * up256(8 * (plan.pitch + 1)) + up256(4 * (plan.pitch + 1))
+           + up256(8 * 32))
+    d2h = 8 * 32 + 48 * 1024
     e2e = {"value": total * args.steps / float(tdt.item()), "unit": "candidates/s",
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(tdt.item()) / args.steps,
            "api": "theta_b200.search.do_optimization_single (RunTHetA.py:173 signature), host lists in / best list out",
