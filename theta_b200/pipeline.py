@@ -308,125 +308,104 @@ def calc_all_c_2(best, r, rN, all_tumor, all_normal, intervals_used):
     return out
 
 
-def _extend_setup(c, mu, r, rN, all_tumor, intervals_used):
-    """Common head of calc_all_c_3 / calc_all_c_3_multi_event (python/CalcAllC.py:149-167, 253-271)."""
-    m, n = c.shape
-    c_new = np.zeros((m + 1, n))
-    c_new[:m] = c
-    c_new = c_new * np.asarray(list(rN) + [0], dtype=np.float64)[:, None]  # weighted_C(c_new, rN + [0])
-    c_all = np.zeros((len(all_tumor), n))
-    for i, v in enumerate(intervals_used):
-        c_all[v] = c[i]
-    sum_all = sum([c_new[j][k] * mu[k] for j in range(m) for k in range(n)])
-    return m, n, c_new, c_all, sum_all, sum(r)
+class _RowProbe(object):
+    """One winning n=3 solution extended by a trial row for an interval that was not searched.
+
+    Holds the weighted matrix of the searched intervals plus one spare last row (python/CalcAllC.py:149-167,
+    253-271) and evaluates L3 with that row set to (2, x, y) * normal_i."""
+
+    def __init__(self, c, mu, r, rN):
+        self.m, self.n = c.shape
+        self.mu = mu
+        self.r = list(r)
+        self.cw = np.zeros((self.m + 1, self.n))
+        self.cw[:self.m] = c * np.asarray(rN, dtype=np.float64)[:, None]
+        # |C_w mu| over the searched intervals and the searched tumour reads (CalcAllC.py:165-167)
+        self.sum_all = sum([self.cw[j][k] * mu[k] for j in range(self.m) for k in range(self.n)])
+        self.sum_r = sum(r)
+
+    def optimum(self, tumor_i, normal_i, row, h):
+        """Real-valued copy number of population h that zeroes dL/dx, in units of copies."""
+        return _calculate_x(tumor_i, normal_i, self.sum_r, self.sum_all, self.mu, self.n, row, h) / normal_i
+
+    def nll(self, tumor_i, normal_i, x, y):
+        last = self.cw[self.m]
+        last[0], last[1], last[2] = 2 * normal_i, x * normal_i, y * normal_i
+        return calc_all_c.L3(self.mu, self.cw, self.m + 1, self.r + [tumor_i], self.n)[0]
+
+
+def _floor_ceil(v):
+    return int(max(0, math.floor(v))), int(max(0, math.ceil(v)))
+
+
+def _extend_n3(best, r, rN, all_tumor, all_normal, intervals_used, choose_row):
+    """Shared driver of calc_all_c_3 / calc_all_c_3_multi_event: fill in every unsearched interval with the row
+    `choose_row` picks, then re-evaluate L3 over all intervals."""
+    out = []
+    n_all = len(all_tumor)
+    searched = set(intervals_used)
+    weights = np.asarray(all_normal, dtype=np.float64)[:, None]
+    for c, mu, _likelihood, _vals in best:
+        probe = _RowProbe(c, mu, r, rN)
+        c_all = np.zeros((n_all, probe.n))
+        c_all[np.asarray(intervals_used, dtype=np.int64)] = c
+        for i in (j for j in range(n_all) if j not in searched):
+            c_all[i][0] = 2
+            if all_normal[i] == 0:  # no normal reads: no optimum exists, printed as X
+                c_all[i][1] = c_all[i][2] = -1
+            else:
+                c_all[i][1], c_all[i][2] = choose_row(probe, all_tumor[i], all_normal[i])
+        likelihood, vals = calc_all_c.L3(mu, c_all * weights, n_all, all_tumor, probe.n)
+        out.append([(c_all, mu, likelihood, vals)])
+    return out
+
+
+def _row_single_event(probe, t_i, n_i):
+    """python/CalcAllC.py:183-243: candidates (floor/ceil x, 2), (2, floor/ceil y) and the diagonal (j, j) walked
+    upwards until the NLL rises; the smallest (NLL, row) pair wins (list sort: NLL first, then the row)."""
+    cands = []
+    for x in _floor_ceil(probe.optimum(t_i, n_i, [2, 0, 2], 1)):
+        cands.append((probe.nll(t_i, n_i, x, 2), [x, 2]))
+    for y in _floor_ceil(probe.optimum(t_i, n_i, [2, 2, 0], 2)):
+        cands.append((probe.nll(t_i, n_i, 2, y), [2, y]))
+    prev, j = float("inf"), 0
+    while True:
+        l = probe.nll(t_i, n_i, j, j)
+        cands.append((l, [j, j]))
+        j += 1
+        if l > prev:
+            break
+        prev = l
+    cands.sort()
+    return cands[0][1]
+
+
+def _row_multi_event(probe, t_i, n_i):
+    """python/CalcAllC.py:286-321: x = 0..ceil(x*), y = floor/ceil of the conditional optimum kept on the same side
+    of 2 as x; the first strictly smaller NLL wins."""
+    max_x = max(0, math.ceil(probe.optimum(t_i, n_i, [2, 0, 0], 1)))
+    best_l, best_row = float("inf"), None
+    for x in range(int(max_x) + 1):
+        bot, top = _floor_ceil(probe.optimum(t_i, n_i, [2, x, 0], 2))
+        if x < 2:
+            bot, top = min(bot, 2), min(top, 2)
+        elif x > 2:
+            bot, top = max(2, bot), max(2, top)
+        for y in (bot, top):
+            l = probe.nll(t_i, n_i, x, y)
+            if l < best_l:
+                best_l, best_row = l, (x, y)
+    return best_row
 
 
 def calc_all_c_3(best, r, rN, all_tumor, all_normal, intervals_used):
-    """python/CalcAllC.py:147-249 (--NO_MULTI_EVENT): for every interval left out of the n=3 search pick the row
-    among {(floor x, 2), (ceil x, 2), (2, floor y), (2, ceil y), (j, j) for j = 0, 1, ... until the NLL rises} with the
-    smallest L3 (ties resolved like the reference's list sort: by NLL, then by the row)."""
-    out = []
-    n_all = len(all_tumor)
-    used = set(intervals_used)
-    for c, mu, likelihood, vals in best:
-        m, n, c_new, c_all, sum_all, sum_r = _extend_setup(c, mu, r, rN, all_tumor, intervals_used)
-        for i in range(n_all):
-            if i in used:
-                continue
-            c_all[i][0] = 2
-            if all_normal[i] == 0:
-                c_all[i][1] = -1
-                c_all[i][2] = -1
-                continue
-            rr = list(r) + [all_tumor[i]]
-            cands = []
-            c_new[m][0] = 2 * all_normal[i]
-            c_new[m][2] = 2 * all_normal[i]
-            x = _calculate_x(all_tumor[i], all_normal[i], sum_r, sum_all, mu, n, [2, 0, 2], 1) / all_normal[i]
-            top, bot = int(max(0, math.ceil(x))), int(max(0, math.floor(x)))
-            c_new[m][1] = bot * all_normal[i]
-            x_bot = calc_all_c.L3(mu, c_new, m + 1, rr, n)[0]
-            c_new[m][1] = top * all_normal[i]
-            x_top = calc_all_c.L3(mu, c_new, m + 1, rr, n)[0]
-            cands.append((x_bot, [bot, 2]))
-            cands.append((x_top, [top, 2]))
-            y = _calculate_x(all_tumor[i], all_normal[i], sum_r, sum_all, mu, n, [2, 2, 0], 2) / all_normal[i]
-            top, bot = int(max(0, math.ceil(y))), int(max(0, math.floor(y)))
-            c_new[m][1] = 2 * all_normal[i]
-            c_new[m][2] = bot * all_normal[i]
-            y_bot = calc_all_c.L3(mu, c_new, m + 1, rr, n)[0]
-            c_new[m][2] = top * all_normal[i]
-            y_top = calc_all_c.L3(mu, c_new, m + 1, rr, n)[0]
-            cands.append((y_bot, [2, bot]))
-            cands.append((y_top, [2, top]))
-            prev = float("inf")
-            j = 0
-            while True:
-                c_new[m][1] = j * all_normal[i]
-                c_new[m][2] = j * all_normal[i]
-                l = calc_all_c.L3(mu, c_new, m + 1, rr, n)[0]
-                cands.append((l, [j, j]))
-                j += 1
-                if l > prev:
-                    break
-                prev = l
-            cands.sort()
-            c_all[i][1], c_all[i][2] = cands[0][1]
-        c_all_w = c_all * np.asarray(all_normal, dtype=np.float64)[:, None]
-        likelihood, vals = calc_all_c.L3(mu, c_all_w, n_all, all_tumor, n)
-        out.append([(c_all, mu, likelihood, vals)])
-    return out
+    """CalcAllC.calc_all_c_3 (python/CalcAllC.py:147-249), the --NO_MULTI_EVENT extension."""
+    return _extend_n3(best, r, rN, all_tumor, all_normal, intervals_used, _row_single_event)
 
 
 def calc_all_c_3_multi_event(best, r, rN, all_tumor, all_normal, intervals_used):
-    """python/CalcAllC.py:251-328 (default): for every interval left out of the n=3 search scan x = 0..ceil(x*) for the
-    first tumour population and floor/ceil of the conditional optimum for the second (kept on the same side of 2
-    as x), keeping the first strictly smaller L3."""
-    out = []
-    n_all = len(all_tumor)
-    used = set(intervals_used)
-    for c, mu, likelihood, vals in best:
-        m, n, c_new, c_all, sum_all, sum_r = _extend_setup(c, mu, r, rN, all_tumor, intervals_used)
-        for i in range(n_all):
-            if i in used:
-                continue
-            c_all[i][0] = 2
-            if all_normal[i] == 0:
-                c_all[i][1] = -1
-                c_all[i][2] = -1
-                continue
-            rr = list(r) + [all_tumor[i]]
-            w_x = _calculate_x(all_tumor[i], all_normal[i], sum_r, sum_all, mu, n, [2, 0, 0], 1)
-            max_x = math.ceil(w_x / all_normal[i])
-            c_new[m][0] = 2 * all_normal[i]
-            l_min = float("inf")
-            row_min = None
-            if max_x < 0:
-                max_x = 0
-            for x in range(int(max_x) + 1):
-                c_new[m][1] = x * all_normal[i]
-                y = _calculate_x(all_tumor[i], all_normal[i], sum_r, sum_all, mu, n, [2, x, 0], 2) / all_normal[i]
-                bot, top = int(max(0, math.floor(y))), int(max(0, math.ceil(y)))
-                if x < 2:
-                    bot, top = min(bot, 2), min(top, 2)
-                elif x > 2:
-                    bot, top = max(2, bot), max(2, top)
-                c_new[m][2] = bot * all_normal[i]
-                l_bot = calc_all_c.L3(mu, c_new, m + 1, rr, n)
-                if l_bot[0] < l_min:
-                    l_min = l_bot[0]
-                    row_min = [2, x, bot]
-                c_new[m][2] = top * all_normal[i]
-                l_top = calc_all_c.L3(mu, c_new, m + 1, rr, n)
-                if l_top[0] < l_min:
-                    l_min = l_top[0]
-                    row_min = [2, x, top]
-            c_all[i][1] = row_min[1]
-            c_all[i][2] = row_min[2]
-        c_all_w = c_all * np.asarray(all_normal, dtype=np.float64)[:, None]
-        likelihood, vals = calc_all_c.L3(mu, c_all_w, n_all, all_tumor, n)
-        out.append([(c_all, mu, likelihood, vals)])
-    return out
+    """CalcAllC.calc_all_c_3_multi_event (python/CalcAllC.py:251-328), the default extension."""
+    return _extend_n3(best, r, rN, all_tumor, all_normal, intervals_used, _row_multi_event)
 
 
 def find_mins(best):
