@@ -636,7 +636,7 @@ extern "C" int theta_n3_item_weights(const theta_plan* pl, double* weights) {
 }
 
 // ----------------------------------------------------------------------- launches
-// THETA_N3_BLOCK (tuning knob): threads per CTA of the n=3 search kernel (64, 128, 256 or 512; default: by item count)
+// THETA_N3_BLOCK (tuning knob): threads per CTA of the n=3 search kernel (64, 256 or 512; default: by item count)
 static int g_n3_block = -1;
 
 template <bool EMIT, int BLOCK, int MINB>
@@ -665,11 +665,10 @@ static int launch_n3(const theta_plan* pl, const Search3Params& sp, cudaStream_t
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
         const int64_t per_sm = (int64_t)sp.n_items / sms;
-        block = per_sm >= 256 ? 512 : per_sm >= 128 ? 256 : per_sm >= 64 ? 128 : 64;
+        block = per_sm >= 256 ? 512 : per_sm >= 128 ? 256 : 64;
     }
     switch (block) {
         case 64: return launch_n3_b<EMIT, 64, 8>(pl, sp, st);
-        case 128: return launch_n3_b<EMIT, 128, 4>(pl, sp, st);
         case 512: return launch_n3_b<EMIT, 512, 1>(pl, sp, st);
         default: return launch_n3_b<EMIT, 256, 2>(pl, sp, st);
     }
