@@ -42,8 +42,17 @@ def test_no_cpu_fallback():
         _lib.init(0)
     with pytest.raises(_lib.ThetaError):
         do_optimization_single(2, 3, 2, 2, [0, 0, 0], [2, 2, 2], [5, 6, 7], [5, 5, 5], 1.0, [0, 1, 2], True, False)
-    src = open(os.path.join(ROOT, "theta_b200", "search.py")).read() + open(os.path.join(ROOT, "theta_b200", "_lib.py")).read()
-    assert "theta_oracle" not in src and "import oracle" not in src
+    with pytest.raises(_lib.ThetaError):
+        _lib.optimize_n2([5, 6, 7], [5, 5, 5], [0, 0, 0], [2, 2, 2])
+    with pytest.raises(_lib.ThetaError):
+        do_optimization_single(3, 3, 2, 2, [0, 0, 0], [2, 2, 2], [5, 6, 7], [5, 5, 5], 1.0, [0, 1, 2], True, False)
+    with pytest.raises(_lib.ThetaError):
+        _lib.nll_single([0.3, 0.7], [[2.0, 1.0], [2.0, 3.0]], [4, 5])
+    # nothing of the product imports the oracle
+    import glob
+    for path in glob.glob(os.path.join(ROOT, "theta_b200", "*.py")):
+        src = open(path).read()
+        assert "theta_oracle" not in src and "import oracle" not in src and "refshim" not in src, path
 
 
 def test_fold_replay_matches_sequential_fold():
