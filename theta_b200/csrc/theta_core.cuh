@@ -56,7 +56,7 @@ __device__ __forceinline__ double fast_rcp(double a) {
 
 // ln(g) for positive normal g from a 256-entry table in shared memory: g = 2^e * m, m in [1,2);
 // entry i holds r_i ~ 1/(1 + (i+0.5)/256) and -ln(r_i), so m*r_i = 1 + d with |d| < 2^-9 (one exact fma) and
-// ln g = e ln2 - ln r_i + log1p(d), log1p by a degree-6 Taylor polynomial (truncation < 2e-20).
+// ln g = e ln2 - ln r_i + log1p(d), log1p by a degree-5 Taylor polynomial (truncation d^6/6 < 1e-17).
 // Absolute error ~1e-16, i.e. as accurate as libm's log here, at about half the instructions.
 #define THETA_LOGTAB_SIZE 256
 __device__ __forceinline__ double fast_log(double g, const double2* __restrict__ LT) {
@@ -69,8 +69,7 @@ __device__ __forceinline__ double fast_log(double g, const double2* __restrict__
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
     const double2 t = LT[idx];  // shared memory in the search kernel, L1-resident global in the tile kernels
     const double d = fma(m, t.x, -1.0);
-    double q = fma(d, -1.0 / 6.0, 0.2);
-    q = fma(d, q, -0.25);
+    double q = fma(d, 0.2, -0.25);
     q = fma(d, q, 1.0 / 3.0);
     q = fma(d, q, -0.5);
     const double r = fma(d * d, q, d);
