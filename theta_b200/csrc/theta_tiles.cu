@@ -498,6 +498,170 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) nll_tiles_kernel(const TileP
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Optimizer.solve(C) on explicit tiles (python/Optimizer.py:68-126) with the same warp-granular TMA pipeline and
+// two-phase run walk as the NLL kernel: every run adds its reads to a per-lane histogram R[v] in shared memory
+// (v = copy number), S1 and the zero-read flag of the v = 0 group come from the prefix tables, then n2_solve.
+template <typename F>
+__device__ __forceinline__ void walk_runs(const unsigned char* rp, int words, int m, F&& on_run) {
+    const uint2* rw = reinterpret_cast<const uint2*>(rp);
+    uint32_t cur = rw[0].x & 0xffu;
+    uint32_t pat = cur * 0x01010101u;
+    for (int w0 = 0; w0 < words; w0 += 32) {
+        const int nw = min(32, words - w0);
+        uint32_t mask = 0;
+        const int nblk = (nw + 3) >> 2;
+        for (int jb = 0; jb < nblk; ++jb) {
+            uint32_t m4 = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint2 w = rw[w0 + jb * 4 + u];
+                uint32_t diff;
+                asm("lop3.b32 %0, %1, %2, %3, 0x7e;" : "=r"(diff) : "r"(w.x), "r"(w.y), "r"(pat));
+                if (diff != 0u) m4 |= 1u << u;
+                pat = __byte_perm(w.y, 0u, 0x3333u);
+            }
+            mask |= m4 << (jb * 4);
+        }
+        if (nw < 32) mask &= (1u << nw) - 1u;
+        uint32_t dlo = 0u, dhi = 0u;
+        uint2 w = make_uint2(0u, 0u);
+        int base = 0;
+        for (;;) {
+            if ((dlo | dhi) == 0u) {
+                if (mask == 0u) break;
+                const int wi = w0 + __ffs((int)mask) - 1;
+                mask &= mask - 1u;
+                w = rw[wi];
+                base = wi * 8;
+                dlo = w.x ^ ((w.x << 8) | cur);
+                dhi = w.y ^ __funnelshift_l(w.x, w.y, 8);
+            }
+            const bool in_lo = dlo != 0u;
+            const uint32_t x = in_lo ? dlo : dhi;
+            const int bit8 = (__ffs((int)x) - 1) & 24;
+            on_run(cur, base + (bit8 >> 3) + (in_lo ? 0 : 4));
+            cur = ((in_lo ? w.x : w.y) >> bit8) & 0xffu;
+            const uint32_t keep = ~(0xffu << bit8);
+            if (in_lo) dlo &= keep; else dhi &= keep;
+        }
+    }
+    on_run(cur, m);
+}
+
+template <int WARPS, int KT>
+__host__ __device__ inline size_t solve_smem_bytes(int64_t pitch) {
+    size_t o = sizeof(double2) * (size_t)(pitch + 1);   // (PR, PRN)
+    o = (o + 15) & ~(size_t)15;
+    o += sizeof(int32_t) * (size_t)(pitch + 1);         // ZP
+    o = (o + 127) & ~(size_t)127;
+    o += sizeof(double) * (size_t)WARPS * (KT + 1) * 32;  // histograms
+    o += (size_t)WARPS * 32 * (size_t)pitch;              // one sub-tile per warp
+    return o + 32;
+}
+
+template <int WARPS, int MINB, int KT>
+__global__ void __launch_bounds__(WARPS * 32, MINB) solve_tiles_kernel(const TileParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[WARPS];
+    double2* PRP = reinterpret_cast<double2*>(smem);
+    size_t o = sizeof(double2) * (size_t)(p.pitch + 1);
+    o = (o + 15) & ~(size_t)15;
+    int32_t* ZP = reinterpret_cast<int32_t*>(smem + o);
+    o += sizeof(int32_t) * (size_t)(p.pitch + 1);
+    o = (o + 127) & ~(size_t)127;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* hist = reinterpret_cast<double*>(smem + o) + (size_t)warp * (KT + 1) * 32 + lane;  // hist[v * 32]
+    o += sizeof(double) * (size_t)WARPS * (KT + 1) * 32;
+    const size_t slot_bytes = (size_t)32 * p.pitch;
+    unsigned char* ring = smem + o + (size_t)warp * slot_bytes;
+    uint64_t* bar = bars + warp;
+    for (int i = tid; i <= p.pitch; i += WARPS * 32) {
+        PRP[i] = make_double2(p.PR[i], p.PRN[i]);
+        ZP[i] = p.ZP[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < WARPS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int words = (int)(p.pitch >> 3);
+    const int64_t n_sub = (p.count + 31) >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t GW = (int64_t)gridDim.x * WARPS;
+    const N2Const kc = p.kc;
+    if (lane == 0 && gw < n_sub) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_subtile(p, ring, bar, gw);
+    }
+    int it = 0;
+    for (int64_t t = gw; t < n_sub; t += GW, ++it) {
+        const int64_t row = t * 32 + lane;
+        const bool live = row < p.count;
+        mbar_wait(bar, (uint32_t)it & 1u);
+        __syncwarp();
+        double R[KT + 1];
+        double s1 = 0.0;
+        bool z0 = false, bad = false;
+        if (live) {
+#pragma unroll
+            for (int v = 0; v <= KT; ++v) hist[v * 32] = 0.0;
+            double pr_s = 0.0, prn_s = 0.0;
+            int zp_s = 0;
+            walk_runs(ring + (size_t)lane * p.pitch, words, kc.m, [&](uint32_t v, int e) {
+                const double2 pp = PRP[e];
+                const int zp = ZP[e];
+                const double wgt = pp.x - pr_s, dn = pp.y - prn_s;
+                if (v > (uint32_t)KT) {
+                    if (dn != 0.0 || wgt != 0.0) bad = true;
+                } else {
+                    s1 = fma((double)v, dn, s1);
+                    hist[v * 32] += wgt;
+                    if (v == 0u && zp - zp_s > 0) z0 = true;
+                }
+                pr_s = pp.x; prn_s = pp.y; zp_s = zp;
+            });
+#pragma unroll
+            for (int v = 0; v <= KT; ++v) R[v] = hist[v * 32];
+        }
+        __syncwarp();  // every lane is done with the sub-tile: request the next one, solve meanwhile
+        if (lane == 0) {
+            const int64_t tn = t + GW;
+            if (tn < n_sub) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_subtile(p, ring, bar, tn);
+            }
+        }
+        if (live) {
+            SolveOut so;
+            n2_solve<KT + 1>(R, s1, z0, kc, -1.0, so);
+            if (bad) { so.status = THETA_ST_NONE_NAN; so.mu = 0.0; so.nll = 0.0; }
+            p.mu_out[row] = so.mu;
+            p.nll_out[row] = so.nll;
+            p.status_out[row] = so.status;
+        }
+    }
+}
+
+template <int KT>
+static int launch_solve(const theta_plan* pl, const TileParams& tp, cudaStream_t st) {
+    constexpr int WARPS = 8, MINB = 2;
+    const size_t smem = solve_smem_bytes<WARPS, KT>(tp.pitch);
+    if (smem > 227 * 1024) return -1000;  // caller falls back to the CTA-granular kernel
+    auto kern = solve_tiles_kernel<WARPS, MINB, KT>;
+    THETA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 1;
+    THETA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
+    if (bps < 1) bps = 1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    const int64_t n_sub = (tp.count + 31) / 32;
+    const int grid = (int)std::min<int64_t>((n_sub + WARPS - 1) / WARPS, (int64_t)sms * bps);
+    kern<<<grid, WARPS * 32, smem, st>>>(tp);
+    THETA_CUDA(cudaGetLastError());
+    return THETA_OK;
+}
+
 static int g_nll_variant = -1;  // THETA_NLL_VARIANT: 0 = 8 warps x 2 stages, 1 = 4 x 2, 2 = 8 x 1, 3 = 4 x 1, 4 = 16 x 1, 5/6 = 8 x 1 with a register cap
 
 template <int WARPS, int STAGES, int MINB, bool N3 = false>
@@ -641,7 +805,7 @@ extern "C" int theta_solve_tiles_n2_dev(theta_plan* pl, const int8_t* cols_dev, 
         tp.cols = cols_dev; tp.pitch = pitch; tp.count = count; tp.PR = pl->d_PR; tp.PRN = pl->d_PRN; tp.ZP = pl->d_ZP;
         tp.kc = pl->kc; tp.mu_out = mu_dev; tp.nll_out = nll_dev; tp.status_out = status_dev; tp.logtab = pl->d_logtab;
         switch (pl->KT) {
-#define THETA_TS(KTV) case KTV: rc = launch_tiles<true, KTV>(pl, tp, st); break;
+#define THETA_TS(KTV) case KTV: rc = launch_solve<KTV>(pl, tp, st); if (rc == -1000) rc = launch_tiles<true, KTV>(pl, tp, st); break;
             THETA_TS(2) THETA_TS(3) THETA_TS(4) THETA_TS(5) THETA_TS(6) THETA_TS(7) THETA_TS(8) THETA_TS(10) THETA_TS(12) THETA_TS(15)
 #undef THETA_TS
             default: set_error("unsupported level count"); rc = THETA_ERR_UNSUPPORTED;

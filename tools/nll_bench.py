@@ -22,6 +22,13 @@ def one(wl):
     _lib.check(lib.theta_enumerate_n2_dev(plan.handle, plan.count() // 3, cnt, tiles.data_ptr(), pitch, None))
     _lib.check(lib.theta_solve_tiles_n2_dev(plan.handle, tiles.data_ptr(), pitch, cnt, mu.data_ptr(), nll.data_ptr(), stt.data_ptr(), None))
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        _lib.check(lib.theta_solve_tiles_n2_dev(plan.handle, tiles.data_ptr(), pitch, cnt, mu.data_ptr(), nll.data_ptr(), stt.data_ptr(), None))
+    e1.record()
+    torch.cuda.synchronize()
+    print("solve_tiles: %.3f ms per launch, %.3e candidates/s" % (e0.elapsed_time(e1) / 5, cnt / (e0.elapsed_time(e1) / 5 * 1e-3)))
     ref = nll.clone()
     nll.zero_()
     for _ in range(3):
