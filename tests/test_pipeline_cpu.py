@@ -58,3 +58,23 @@ def test_model_selection_matches_reference(tmp_path):
     sel, path = pipeline.model_selection(os.path.join(str(tmp_path), "b.intervals"), os.path.join(str(tmp_path), "b.n2.results"),
                                          os.path.join(str(tmp_path), "b.n3.results"))
     assert sel == 3 and open(path).read() == open(os.path.join(str(tmp_path), "b.n3.results")).read()
+
+
+def test_cli_argument_surface(tmp_path):
+    """The reference's flags (FileIO.parse_arguments, python/FileIO.py:45-227): names, defaults, and the quirks that
+    are kept (n=3 default of 20 intervals only when -n 3 is given, FileIO.py:170) or fixed (K up to 7, Q4)."""
+    import pytest
+    from theta_b200 import run_theta
+    f = tmp_path / "x.intervals"
+    f.write_text("#ID\tchrm\tstart\tend\ttumorCount\tnormalCount\n1\t1\t0\t10\t5\t5\n2\t1\t10\t20\t6\t5\n")
+    a = run_theta.parse_arguments([str(f)])
+    assert (a.N, a.MAX_K, a.TAU, a.MAX_NORMAL, a.NUM_PROCESSES, a.NUM_INTERVALS) == (None, 3, 2, 1.0, 1, 100)
+    assert a.OUTPUT_PREFIX == "x" and not a.BOUNDS_ONLY and not a.NO_MULTI_EVENT and not a.FORCE
+    assert run_theta.parse_arguments([str(f), "-n", "3"]).NUM_INTERVALS == 20
+    assert run_theta.parse_arguments([str(f), "-n", "3", "--NUM_INTERVALS", "8"]).NUM_INTERVALS == 8
+    assert run_theta.parse_arguments([str(f), "-n", "2", "-k", "7", "-m", "0.6", "-p", "pre"]).MAX_K == 7
+    for bad in (["-n", "4"], ["-k", "8"], ["-m", "1.5"], ["--BAF"]):
+        with pytest.raises(SystemExit):
+            run_theta.parse_arguments([str(f)] + bad)
+    with pytest.raises(SystemExit):
+        run_theta.parse_arguments([str(tmp_path / "missing.intervals")])
