@@ -208,10 +208,14 @@ int theta_search_n3_pass2(theta_plan* plan, double global_min, double prior_min,
 /* Every candidate of items [item_begin, item_end) in enumeration order, as row-index strings. */
 int theta_enumerate_n3(theta_plan* plan, uint64_t item_begin, uint64_t item_end, uint8_t* paths_host, uint64_t cap,
                        uint64_t* n_out);
-/* Optimizer.solve on explicit candidates given as row-index strings [count][m]. */
+/* Optimizer.solve on explicit candidates given as row-index strings [count][m].
+ * mode 0: grouped-statistics solver, except rank-deficient candidates (rows on one line / a zero tumour column),
+ *         which take the reference-order solver (per-interval sums in the reference's arithmetic order, libm-exact
+ *         pow, MINPACK hybrj + hybrd restated: the only way to reproduce what the reference returns for them);
+ * mode 1: reference-order solver for every candidate;  mode 2: grouped solver for every candidate. */
 int theta_solve_rows_n3(theta_plan* plan, const uint8_t* paths_host, int64_t count, double* mu_host /* [count][3] */,
                         double* muhat_host /* [count][3] or NULL */, double* nll_host, int32_t* status_host,
-                        double* vals_host /* [count][m] or NULL */);
+                        double* vals_host /* [count][m] or NULL */, int32_t mode);
 
 /* ---- CalcAllC.L2 / L3 (CalcAllC.py:44-76): masked NLL of one weighted matrix at a given mu ---- */
 /* Cw is [m][n] row-major fp64 (already weighted by rN); valid_i = Cw[i][0] != 0 (L2 with mu==0: Cw[i][1] != 0).

@@ -6,7 +6,7 @@ freezes its outputs as small JSON fixtures, so that the oracle restatement and
 the CUDA path can be checked on the GPU box, where /root/reference does not
 exist.  Floats are written with repr() precision (exact round trip).
 
-    python oracle/make_golden.py [--only kat,config1,synth_n2,n3_small,edge]
+    python oracle/make_golden.py [--only kat,config1,synth_n2,n3_small,n3_rankdef,edge]
 """
 import argparse
 import contextlib
@@ -245,6 +245,50 @@ def gen_synth_n3(R):
     _dump("synth_n3_candidates.json", out)
 
 
+def rankdef_space():
+    """A real-shaped m=16 n=3 space: the 16 longest intervals of the reference's example (real read counts, the number
+    of intervals its n=3 interval selection keeps with --NUM_INTERVALS 16), lower bounds 0 so that zero tumour columns
+    occur, upper bounds 2..4 in sorted order."""
+    rows = [ln.split("\t") for ln in open(os.path.join(GOLD, "Example.intervals")).read().strip().split("\n")[1:]]
+    iv = sorted(((int(x[3]) - int(x[2]), int(x[4]), int(x[5])) for x in rows), reverse=True)[:16]
+    r, rN, si = O.sort_r([v[2] for v in iv], [v[1] for v in iv])
+    return r, rN, si, [0] * 16, [2] * 9 + [3] * 4 + [4] * 3
+
+
+def gen_n3_rankdef(R):
+    """>= 10^4 rank-deficient candidates (all rows on one line of the (a, b) plane, which includes the zero-column and
+    identical-column classes) of a real-shaped m=16 space through the live Optimizer.solve.
+    They are listed by enumerating the space restricted to the rows of each line (theta_oracle.enumerate_n3 row_ok)."""
+    r, rN, si, lb, ub = rankdef_space()
+    m = len(r)
+    rows, _ = O.n3_graph(max(ub), 2)
+    lines = set()
+    for i, p_ in enumerate(rows):
+        for q in rows[i + 1:]:
+            lines.add(frozenset(x for x in rows if (q[0] - p_[0]) * (x[1] - p_[1]) - (q[1] - p_[1]) * (x[0] - p_[0]) == 0))
+    paths = set()
+    for L in sorted(lines, key=lambda L: sorted(L)):
+        for n_, path in enumerate(O.enumerate_n3(lb, ub, row_ok=lambda row: row in L)):
+            if n_ >= 1500:
+                break
+            paths.add(tuple(path))
+    paths = sorted(paths)
+    opt = R.Optimizer.Optimizer(r, rN, m, 3, 2, upper_bound=1.0)
+    recs = []
+    t0 = time.time()
+    for path in paths:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            s_ = opt.solve(O.rows_to_matrix(path, rows))
+        recs.append([list(path)] + ([None, None] if s_ is None else [[float(v) for v in s_[0]], float(s_[1])]))
+    print("n3 rank-deficient", len(recs), "none", sum(1 for q in recs if q[2] is None),
+          "nan", sum(1 for q in recs if q[2] is not None and q[2] != q[2]), "%.0fs" % (time.time() - t0))
+    _dump("n3_rankdef_m16.json", dict(m=m, r=r, rN=rN, lower=lb, upper=ub, sorted_index=si, rows=[list(x) for x in rows],
+                                      records=recs))
+    import subprocess
+    subprocess.check_call(["gzip", "-9", "-f", os.path.join(GOLD, "n3_rankdef_m16.json")])
+
+
 def gen_config1_cli(R):
     """The reference's own CLI on config #1 (RunTHetA.main, ~3 min): .n2.results and .n2.withBounds as text fixtures,
     plus the input file itself (the reference's example *data*, needed on the GPU box)."""
@@ -356,6 +400,8 @@ def main():
         gen_n3_small(R)
     if "synth_n3" in todo:
         gen_synth_n3(R)
+    if "n3_rankdef" in todo:
+        gen_n3_rankdef(R)
     if "config1" in todo:
         gen_config1(R)
     if "config1_cli" in todo:

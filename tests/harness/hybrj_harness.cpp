@@ -17,7 +17,7 @@ struct RefSys {
         for (int k = 0; k < 3; ++k) f[k] = (-s[k]) - x[3];
         f[3] = 1 - ((x[0] + x[1]) + x[2]);
     }
-    void jac(const double* x, double* J) {  // column-major J[i + 4*j] = d f_i / d x_j
+    int jac(const double* x, const double*, double* J) {  // column-major J[i + 4*j] = d f_i / d x_j
         for (int a = 0; a < 16; ++a) J[a] = 0.0;
         for (int k = 0; k < 3; ++k)
             for (int h = 0; h < 3; ++h) {
@@ -30,6 +30,7 @@ struct RefSys {
             }
         for (int i = 0; i < 4; ++i) { J[3 + 4 * i] = -1.0; J[i + 4 * 3] = -1.0; }
         J[3 + 4 * 3] = 0.0;
+        return 0;
     }
 };
 

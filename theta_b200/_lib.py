@@ -72,7 +72,7 @@ SYMBOLS = {
     "theta_search_n3_pass1": (C.c_int, [_VP, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), _VP]),
     "theta_search_n3_pass2": (C.c_int, [_VP, C.c_double, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP, _VP]),
     "theta_enumerate_n3": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
-    "theta_solve_rows_n3": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP]),
+    "theta_solve_rows_n3": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, C.c_int32]),
     "theta_enumerate_n2": (C.c_int, [_VP, C.c_uint64, C.c_int64, _VP, C.c_int64]),
     "theta_enumerate_n2_dev": (C.c_int, [_VP, C.c_uint64, C.c_int64, _VP, C.c_int64, _VP]),
     "theta_tile_pitch": (C.c_int64, [C.c_int32]),
@@ -273,8 +273,9 @@ class Plan(object):
             check(rc)
             return paths[:int(n.value)]
 
-    def solve_rows(self, paths, want_vals=False):
-        """Optimizer.solve (n=3) on row-index strings [count, m] -> (mu[count,3], muhat, nll, status, vals)."""
+    def solve_rows(self, paths, want_vals=False, mode=0):
+        """Optimizer.solve (n=3) on row-index strings [count, m] -> (mu[count,3], muhat, nll, status, vals).
+        mode: 0 auto (reference-order solver for rank-deficient candidates), 1 reference-order always, 2 grouped."""
         paths = np.ascontiguousarray(np.asarray(paths, dtype=np.uint8))
         cnt = paths.shape[0]
         mu = np.zeros((cnt, 3))
@@ -284,7 +285,7 @@ class Plan(object):
         vals = np.zeros((cnt, self.m)) if want_vals else None
         if cnt:
             check(load().theta_solve_rows_n3(self._h, ptr(paths), cnt, ptr(mu), ptr(mh), ptr(nll), ptr(st),
-                                             ptr(vals) if want_vals else None))
+                                             ptr(vals) if want_vals else None, int(mode)))
         return mu, mh, nll, st, vals
 
     def nll_rows(self, paths, mu):

@@ -9,7 +9,7 @@
 // hybrj, qrfac, qform, dogleg, r1updt, r1mpyq, enorm) step by step, including its storage
 // conventions (R packed by rows, Givens rotations encoded in a single number).
 // Everything is __host__ __device__ so the same code is unit-tested on the CPU against SciPy
-// (tests/test_hybrj_port.py builds a host harness) and runs inside the CUDA kernels.
+// (tests/test_n3_solver_host.py builds host harnesses from tests/harness/) and runs inside the CUDA kernels.
 #pragma once
 #include <math.h>
 
@@ -39,31 +39,32 @@ constexpr int LR = N * (N + 1) / 2;
 constexpr double EPSMCH = 2.220446049250313e-16;   // dpmpar(1)
 constexpr double GIANT = 1.7976931348623157e308;   // dpmpar(3)
 
-THETA_HDN double enorm(int n, const double* x) {
-    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
-    double s1 = 0.0, s2 = 0.0, s3 = 0.0, x1max = 0.0, x3max = 0.0;
-    const double agiant = rgiant / (double)n;
+template <class T>
+THETA_HDN T enorm(int n, const T* x) {
+    const T rdwarf = 3.834e-20, rgiant = 1.304e19;
+    T s1 = 0.0, s2 = 0.0, s3 = 0.0, x1max = 0.0, x3max = 0.0;
+    const T agiant = rgiant / (T)n;
 #pragma unroll
     for (int i = 0; i < n; ++i) {
-        const double xabs = fabs(x[i]);
+        const T xabs = fabs(x[i]);
         if (xabs > rdwarf && xabs < agiant) {
             s2 += xabs * xabs;
         } else if (xabs <= rdwarf) {
             if (xabs > x3max) {
-                const double t = x3max / xabs;
+                const T t = x3max / xabs;
                 s3 = 1.0 + s3 * (t * t);
                 x3max = xabs;
             } else if (xabs != 0.0) {
-                const double t = xabs / x3max;
+                const T t = xabs / x3max;
                 s3 += t * t;
             }
         } else {
             if (xabs > x1max) {
-                const double t = x1max / xabs;
+                const T t = x1max / xabs;
                 s1 = 1.0 + s1 * (t * t);
                 x1max = xabs;
             } else {
-                const double t = xabs / x1max;
+                const T t = xabs / x1max;
                 s1 += t * t;
             }
         }
@@ -77,7 +78,8 @@ THETA_HDN double enorm(int n, const double* x) {
 }
 
 // a is column-major N x N: a[i + N*j]
-THETA_MPI void qrfac(double* a, double* rdiag, double* acnorm) {
+template <class T>
+THETA_MPI void qrfac(T* a, T* rdiag, T* acnorm) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         acnorm[j] = enorm(N, a + N * j);
@@ -85,7 +87,7 @@ THETA_MPI void qrfac(double* a, double* rdiag, double* acnorm) {
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        double ajnorm = enorm(N - j, a + j + N * j);
+        T ajnorm = enorm(N - j, a + j + N * j);
         if (ajnorm != 0.0) {
             if (a[j + N * j] < 0.0) ajnorm = -ajnorm;
 #pragma unroll
@@ -93,10 +95,10 @@ THETA_MPI void qrfac(double* a, double* rdiag, double* acnorm) {
             a[j + N * j] += 1.0;
 #pragma unroll
             for (int k = j + 1; k < N; ++k) {
-                double sum = 0.0;
+                T sum = 0.0;
 #pragma unroll
                 for (int i = j; i < N; ++i) sum += a[i + N * j] * a[i + N * k];
-                const double temp = sum / a[j + N * j];
+                const T temp = sum / a[j + N * j];
 #pragma unroll
                 for (int i = j; i < N; ++i) a[i + N * k] -= temp * a[i + N * j];
             }
@@ -105,7 +107,8 @@ THETA_MPI void qrfac(double* a, double* rdiag, double* acnorm) {
     }
 }
 
-THETA_MPI void qform(double* q, double* wa) {
+template <class T>
+THETA_MPI void qform(T* q, T* wa) {
 #pragma unroll
     for (int j = 1; j < N; ++j)
 #pragma unroll
@@ -122,10 +125,10 @@ THETA_MPI void qform(double* q, double* wa) {
         if (wa[k] != 0.0) {
 #pragma unroll
             for (int j = k; j < N; ++j) {
-                double sum = 0.0;
+                T sum = 0.0;
 #pragma unroll
                 for (int i = k; i < N; ++i) sum += q[i + N * j] * wa[i];
-                const double temp = sum / wa[k];
+                const T temp = sum / wa[k];
 #pragma unroll
                 for (int i = k; i < N; ++i) q[i + N * j] -= temp * wa[i];
             }
@@ -134,8 +137,9 @@ THETA_MPI void qform(double* q, double* wa) {
 }
 
 // r: upper triangle packed by rows (0-based l); x: output step
-THETA_MPI void dogleg(const double* r, const double* diag, const double* qtb, double delta, double* x, double* wa1,
-                     double* wa2) {
+template <class T>
+THETA_MPI void dogleg(const T* r, const T* diag, const T* qtb, T delta, T* x, T* wa1,
+                     T* wa2) {
     // Gauss-Newton direction
     int jj = LR;  // 0-based index one past the last diagonal (1-based jj = LR + 1)
 #pragma unroll
@@ -143,13 +147,13 @@ THETA_MPI void dogleg(const double* r, const double* diag, const double* qtb, do
         const int j = N - k;  // 0-based
         jj -= k;              // now the 0-based index of r(j,j)
         int l = jj + 1;
-        double sum = 0.0;
+        T sum = 0.0;
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
             sum += r[l] * x[i];
             ++l;
         }
-        double temp = r[jj];
+        T temp = r[jj];
         if (temp == 0.0) {
             l = j;  // 0-based index of r(0,j)
 #pragma unroll
@@ -167,13 +171,13 @@ THETA_MPI void dogleg(const double* r, const double* diag, const double* qtb, do
         wa1[j] = 0.0;
         wa2[j] = diag[j] * x[j];
     }
-    const double qnorm = enorm(N, wa2);
+    const T qnorm = enorm(N, wa2);
     if (qnorm <= delta) return;
     // scaled gradient direction
     int l = 0;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        const double temp = qtb[j];
+        const T temp = qtb[j];
 #pragma unroll
         for (int i = j; i < N; ++i) {
             wa1[i] += r[l] * temp;
@@ -181,16 +185,16 @@ THETA_MPI void dogleg(const double* r, const double* diag, const double* qtb, do
         }
         wa1[j] = wa1[j] / diag[j];
     }
-    const double gnorm = enorm(N, wa1);
-    double sgnorm = 0.0;
-    double alpha = delta / qnorm;
+    const T gnorm = enorm(N, wa1);
+    T sgnorm = 0.0;
+    T alpha = delta / qnorm;
     if (gnorm != 0.0) {
 #pragma unroll
         for (int j = 0; j < N; ++j) wa1[j] = (wa1[j] / gnorm) / diag[j];
         l = 0;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            double sum = 0.0;
+            T sum = 0.0;
 #pragma unroll
             for (int i = j; i < N; ++i) {
                 sum += r[l] * wa1[i];
@@ -198,25 +202,26 @@ THETA_MPI void dogleg(const double* r, const double* diag, const double* qtb, do
             }
             wa2[j] = sum;
         }
-        double temp = enorm(N, wa2);
+        T temp = enorm(N, wa2);
         sgnorm = (gnorm / temp) / temp;
         alpha = 0.0;
         if (sgnorm < delta) {
-            const double bnorm = enorm(N, qtb);
+            const T bnorm = enorm(N, qtb);
             temp = (bnorm / gnorm) * (bnorm / qnorm) * (sgnorm / delta);
-            const double dq = delta / qnorm, sd = sgnorm / delta;
+            const T dq = delta / qnorm, sd = sgnorm / delta;
             temp = temp - dq * (sd * sd) + sqrt((temp - dq) * (temp - dq) + (1.0 - dq * dq) * (1.0 - sd * sd));
             alpha = (dq * (1.0 - sd * sd)) / temp;
         }
     }
-    const double temp = (1.0 - alpha) * fmin(sgnorm, delta);
+    const T temp = (1.0 - alpha) * fmin(sgnorm, delta);
 #pragma unroll
     for (int j = 0; j < N; ++j) x[j] = temp * wa1[j] + alpha * x[j];
 }
 
 // s: lower triangular stored by columns (== R packed by rows); m = n = N
-THETA_MPI void r1updt(double* s, const double* u, double* v, double* w, bool* sing) {
-    const double p5 = 0.5, p25 = 0.25;
+template <class T>
+THETA_MPI void r1updt(T* s, const T* u, T* v, T* w, bool* sing) {
+    const T p5 = 0.5, p25 = 0.25;
     int jj = LR - 1;  // 0-based index of s(N-1,N-1)
     w[N - 1] = s[jj];
 #pragma unroll
@@ -225,15 +230,15 @@ THETA_MPI void r1updt(double* s, const double* u, double* v, double* w, bool* si
         jj -= (N - j);              // 0-based index of s(j,j)
         w[j] = 0.0;
         if (v[j] != 0.0) {
-            double c, sn, tau;
+            T c, sn, tau;
             if (fabs(v[N - 1]) < fabs(v[j])) {
-                const double cotan = v[N - 1] / v[j];
+                const T cotan = v[N - 1] / v[j];
                 sn = p5 / sqrt(p25 + p25 * (cotan * cotan));
                 c = sn * cotan;
                 tau = 1.0;
                 if (fabs(c) * GIANT > 1.0) tau = 1.0 / c;
             } else {
-                const double tn = v[j] / v[N - 1];
+                const T tn = v[j] / v[N - 1];
                 c = p5 / sqrt(p25 + p25 * (tn * tn));
                 sn = c * tn;
                 tau = sn;
@@ -243,7 +248,7 @@ THETA_MPI void r1updt(double* s, const double* u, double* v, double* w, bool* si
             int l = jj;
 #pragma unroll
             for (int i = j; i < N; ++i) {
-                const double temp = c * s[l] - sn * w[i];
+                const T temp = c * s[l] - sn * w[i];
                 w[i] = sn * s[l] + c * w[i];
                 s[l] = temp;
                 ++l;
@@ -256,15 +261,15 @@ THETA_MPI void r1updt(double* s, const double* u, double* v, double* w, bool* si
 #pragma unroll
     for (int j = 0; j < N - 1; ++j) {
         if (w[j] != 0.0) {
-            double c, sn, tau;
+            T c, sn, tau;
             if (fabs(s[jj]) < fabs(w[j])) {
-                const double cotan = s[jj] / w[j];
+                const T cotan = s[jj] / w[j];
                 sn = p5 / sqrt(p25 + p25 * (cotan * cotan));
                 c = sn * cotan;
                 tau = 1.0;
                 if (fabs(c) * GIANT > 1.0) tau = 1.0 / c;
             } else {
-                const double tn = w[j] / s[jj];
+                const T tn = w[j] / s[jj];
                 c = p5 / sqrt(p25 + p25 * (tn * tn));
                 sn = c * tn;
                 tau = sn;
@@ -272,7 +277,7 @@ THETA_MPI void r1updt(double* s, const double* u, double* v, double* w, bool* si
             int l = jj;
 #pragma unroll
             for (int i = j; i < N; ++i) {
-                const double temp = c * s[l] + sn * w[i];
+                const T temp = c * s[l] + sn * w[i];
                 w[i] = -sn * s[l] + c * w[i];
                 s[l] = temp;
                 ++l;
@@ -287,11 +292,12 @@ THETA_MPI void r1updt(double* s, const double* u, double* v, double* w, bool* si
 }
 
 // a: m x N column-major with leading dimension lda
-THETA_MPI void r1mpyq(int m, double* a, int lda, const double* v, const double* w) {
+template <class T>
+THETA_MPI void r1mpyq(int m, T* a, int lda, const T* v, const T* w) {
 #pragma unroll
     for (int nmj = 1; nmj <= N - 1; ++nmj) {
         const int j = N - 1 - nmj;
-        double c, sn;
+        T c, sn;
         if (fabs(v[j]) > 1.0) {
             c = 1.0 / v[j];
             sn = sqrt(1.0 - c * c);
@@ -301,14 +307,14 @@ THETA_MPI void r1mpyq(int m, double* a, int lda, const double* v, const double* 
         }
 #pragma unroll
         for (int i = 0; i < m; ++i) {
-            const double temp = c * a[i + lda * j] - sn * a[i + lda * (N - 1)];
+            const T temp = c * a[i + lda * j] - sn * a[i + lda * (N - 1)];
             a[i + lda * (N - 1)] = sn * a[i + lda * j] + c * a[i + lda * (N - 1)];
             a[i + lda * j] = temp;
         }
     }
 #pragma unroll
     for (int j = 0; j < N - 1; ++j) {
-        double c, sn;
+        T c, sn;
         if (fabs(w[j]) > 1.0) {
             c = 1.0 / w[j];
             sn = sqrt(1.0 - c * c);
@@ -318,7 +324,7 @@ THETA_MPI void r1mpyq(int m, double* a, int lda, const double* v, const double* 
         }
 #pragma unroll
         for (int i = 0; i < m; ++i) {
-            const double temp = c * a[i + lda * j] + sn * a[i + lda * (N - 1)];
+            const T temp = c * a[i + lda * j] + sn * a[i + lda * (N - 1)];
             a[i + lda * (N - 1)] = -sn * a[i + lda * j] + c * a[i + lda * (N - 1)];
             a[i + lda * j] = temp;
         }
@@ -329,20 +335,20 @@ struct Result {
     int info, nfev, njev;
 };
 
-// Sys must provide:  void fcn(const double* x, double* fvec);  void jac(const double* x, double* fjac /*col-major*/);
-template <class Sys>
-THETA_MPI Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double factor) {
-    const double p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
-    double fvec[N], fjac[N * N], diag[N], r[LR], qtf[N], wa1[N], wa2[N], wa3[N], wa4[N];
+// Sys must provide:  void fcn(const T* x, T* fvec);  void jac(const T* x, T* fjac /*col-major*/);
+template <class T, class Sys>
+THETA_MPI Result hybrj(Sys& sys, T* x, T xtol, int maxfev, T factor) {
+    const T p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
+    T fvec[N], fjac[N * N], diag[N], r[LR], qtf[N], wa1[N], wa2[N], wa3[N], wa4[N];
     Result res{0, 0, 0};
     sys.fcn(x, fvec);
     res.nfev = 1;
-    double fnorm = enorm(N, fvec);
+    T fnorm = enorm(N, fvec);
     int iter = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0;
-    double delta = 0.0, xnorm = 0.0;
+    T delta = 0.0, xnorm = 0.0;
     for (;;) {  // outer loop: (re)compute the Jacobian
         bool jeval = true;
-        sys.jac(x, fjac);
+        res.nfev += sys.jac(x, fvec, fjac);
         ++res.njev;
         qrfac(fjac, wa1, wa2);
         if (iter == 1) {
@@ -362,10 +368,10 @@ THETA_MPI Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double fact
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             if (fjac[j + N * j] != 0.0) {
-                double sum = 0.0;
+                T sum = 0.0;
 #pragma unroll
                 for (int i = j; i < N; ++i) sum += fjac[i + N * j] * qtf[i];
-                const double temp = -sum / fjac[j + N * j];
+                const T temp = -sum / fjac[j + N * j];
 #pragma unroll
                 for (int i = j; i < N; ++i) qtf[i] += fjac[i + N * j] * temp;
             }
@@ -393,17 +399,17 @@ THETA_MPI Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double fact
                 wa2[j] = x[j] + wa1[j];
                 wa3[j] = diag[j] * wa1[j];
             }
-            const double pnorm = enorm(N, wa3);
+            const T pnorm = enorm(N, wa3);
             if (iter == 1) delta = fmin(delta, pnorm);
             sys.fcn(wa2, wa4);
             ++res.nfev;
-            const double fnorm1 = enorm(N, wa4);
-            double actred = -1.0;
+            const T fnorm1 = enorm(N, wa4);
+            T actred = -1.0;
             if (fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
             int l = 0;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                double sum = 0.0;
+                T sum = 0.0;
 #pragma unroll
                 for (int j = i; j < N; ++j) {
                     sum += r[l] * wa1[j];
@@ -411,10 +417,10 @@ THETA_MPI Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double fact
                 }
                 wa3[i] = qtf[i] + sum;
             }
-            const double temp = enorm(N, wa3);
-            double prered = 0.0;
+            const T temp = enorm(N, wa3);
+            T prered = 0.0;
             if (temp < fnorm) prered = 1.0 - (temp / fnorm) * (temp / fnorm);
-            double ratio = 0.0;
+            T ratio = 0.0;
             if (prered > 0.0) ratio = actred / prered;
             if (ratio < p1) {
                 ncsuc = 0;
@@ -451,7 +457,7 @@ THETA_MPI Result hybrj(Sys& sys, double* x, double xtol, int maxfev, double fact
             if (ncfail == 2) break;  // recompute the Jacobian
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                double sum = 0.0;
+                T sum = 0.0;
 #pragma unroll
                 for (int i = 0; i < N; ++i) sum += fjac[i + N * j] * wa4[i];
                 wa2[j] = (sum - wa3[j]) / pnorm;

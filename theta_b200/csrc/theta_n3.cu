@@ -292,7 +292,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) n3_search_kernel(const Search3Par
                     skip = n3_screen(G, dfs.S1, dfs.S2, D.kc, ws, thr, lb, LT) && !p.verify;
                 }
                 if (!skip) {
-                    n3_solve(G, dfs.S1, dfs.S2, D.kc, o);
+                    const ref3::Ctx rc{m, D.r, D.rN, dfs.path, 1, D.ra, D.rb, D.kc.tau, D.kc.tau * D.kc.A, dfs.S1, dfs.S2};
+                    n3_solve_auto(G, dfs.S1, dfs.S2, D.kc, rc, EMIT ? THETA_N3_MODE_REF : THETA_N3_MODE_AUTO, o);
                     ++n_exact;
                     if (o.status < THETA_ST_NONE_SIGN) {
                         ++solved;
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) n3_search_kernel(const Search3Par
 // Optimizer.solve on explicit row-index strings
 __global__ void __launch_bounds__(kBlock3) n3_solve_rows_kernel(const N3Dev D0, const uint8_t* paths, int64_t count,
                                                                 double* mu, double* muhat, double* nll, int32_t* status,
-                                                                double* vals) {
+                                                                double* vals, int mode) {
     __shared__ N3Dev D;
     if (threadIdx.x == 0) D = D0;
     __syncthreads();
@@ -366,8 +367,11 @@ __global__ void __launch_bounds__(kBlock3) n3_solve_rows_kernel(const N3Dev D0, 
         if (cnt[g]) { G.R[n] = R[g]; G.a[n] = D.ra[g]; G.b[n] = D.rb[g]; ++n; }
     G.G = n;
     Solve3Out o;
-    n3_solve(G, S1, S2, D.kc, o);
-    if (bad) { o.status = THETA_ST_NONE_NAN; o.nll = 0.0; }
+    if (bad) { o.status = THETA_ST_NONE_NAN; o.nll = 0.0; o.mu[0] = o.mu[1] = o.mu[2] = 0.0; o.muhat[0] = o.muhat[1] = o.muhat[2] = 0.0; }
+    else {
+        const ref3::Ctx rc{m, D.r, D.rN, pth, 1, D.ra, D.rb, D.kc.tau, D.kc.tau * D.kc.A, S1, S2};
+        n3_solve_auto(G, S1, S2, D.kc, rc, mode, o);
+    }
     for (int j = 0; j < 3; ++j) {
         mu[i * 3 + j] = o.mu[j];
         if (muhat) muhat[i * 3 + j] = o.muhat[j];
@@ -926,7 +930,7 @@ extern "C" int theta_enumerate_n3(theta_plan* pl, uint64_t item_begin, uint64_t 
 }
 
 extern "C" int theta_solve_rows_n3(theta_plan* pl, const uint8_t* paths_host, int64_t count, double* mu_host,
-                                   double* muhat_host, double* nll_host, int32_t* status_host, double* vals_host) {
+                                   double* muhat_host, double* nll_host, int32_t* status_host, double* vals_host, int32_t mode) {
     int rc = check_n3(pl);
     if (rc) return rc;
     if (!paths_host || !mu_host || !nll_host || !status_host) { set_error("null argument"); return THETA_ERR_INVALID; }
@@ -945,7 +949,7 @@ extern "C" int theta_solve_rows_n3(theta_plan* pl, const uint8_t* paths_host, in
         N3Dev D;
         fill_dev(pl, &D);
         const int grid = (int)((count + kBlock3 - 1) / kBlock3);
-        n3_solve_rows_kernel<<<grid, kBlock3>>>(D, d_p, count, d_mu, d_mh, d_nll, d_st, d_vals);
+        n3_solve_rows_kernel<<<grid, kBlock3>>>(D, d_p, count, d_mu, d_mh, d_nll, d_st, d_vals, (int)mode);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(mu_host, d_mu, sizeof(double) * 3 * count, cudaMemcpyDeviceToHost);

@@ -13,6 +13,7 @@
 #include "hybrj4.cuh"
 #include "bfgs_ls.cuh"
 #include "theta_core.cuh"
+#include "n3_ref.cuh"
 
 namespace theta {
 
@@ -53,7 +54,7 @@ struct Kkt3 {
         f[2] = -(t2 * s2) - x[3];
         f[3] = 1.0 - ((x[0] + x[1]) + x[2]);
     }
-    THETA_HDN void jac(const double* x, double* J) {
+    THETA_HDN int jac(const double* x, const double*, double* J) {
         const double u0 = x[0] * t0, u1 = x[1] * t1, u2 = x[2] * t2;
         double j00 = 0, j01 = 0, j02 = 0, j11 = 0, j12 = 0, j22 = 0;
         for (int i = 0; i < g->G; ++i) {
@@ -78,6 +79,7 @@ struct Kkt3 {
             J[i + 4 * 3] = -1.0;
         }
         J[3 + 4 * 3] = 0.0;
+        return 0;
     }
 };
 
@@ -288,6 +290,30 @@ THETA_HDN void n3_solve(const Groups3& g, double S1, double S2, const N3Const& k
     o.status = status;
     if (status == THETA_ST_NONE_RANGE) return;
     n3_finish(g, S1, S2, k, mh, o);
+}
+
+// Which solver a candidate takes (mode): 0 = grouped statistics (n3_solve) unless the candidate is rank-deficient
+// or an interval has no normal reads -- then the reference's result is a function of its own rounding sequence and
+// only the reference-order solver (n3_ref.cuh) reproduces it; 1 = reference-order solver always (the records a
+// search returns: mu and NLL then carry the reference's roundings, not just its tolerance); 2 = grouped always.
+#define THETA_N3_MODE_AUTO 0
+#define THETA_N3_MODE_REF 1
+#define THETA_N3_MODE_GROUPED 2
+THETA_HDN void n3_solve_auto(const Groups3& g, double S1, double S2, const N3Const& k, const ref3::Ctx& c, int mode,
+                             Solve3Out& o) {
+    const bool ref = mode == THETA_N3_MODE_REF ||
+                     (mode == THETA_N3_MODE_AUTO && (k.any_zero_rN || ref3::rank_deficient(g.G, g.R, g.a, g.b, S1, S2)));
+    if (!ref) {
+        n3_solve(g, S1, S2, k, o);
+        return;
+    }
+    const ref3::StatusCodes sc{THETA_ST_OK, THETA_ST_FALLBACK_X0, THETA_ST_FALLBACK_MOVED, THETA_ST_NONE_RANGE};
+    ref3::Out r;
+    ref3::solve(c, sc, r);
+    for (int j = 0; j < 3; ++j) { o.mu[j] = r.mu[j]; o.muhat[j] = r.muhat[j]; }
+    o.nll = r.nll;
+    o.status = r.status;
+    o.nfev = r.nfev;
 }
 
 }  // namespace theta

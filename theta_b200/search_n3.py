@@ -61,7 +61,12 @@ def search_n3(plan, leaf_cap=256, stream=None):
     b, e = shard_items(w, rank, world)
     local_min = plan.pass1_n3(b, e, stream)
     st = plan.stats()
-    null_nll = plan.null_nll()
+    # the reference's first "candidate" is the all-[tau,0,0] matrix built from iter = [0]*m, bounds ignored
+    # (RunTHetA.py:148,188, Enumerator.py:54,154-160 -- Q2); Optimizer.solve returns garbage mu and (usually) the
+    # all-normal likelihood for it: row index 0 is (0, 0), and the reference-order solver reproduces both
+    bmu, _, bnll, bst, _ = plan.solve_rows(np.zeros((1, plan.m), dtype=np.uint8), mode=1)
+    has_bogus = int(bst[0]) < _lib.ST_NONE_SIGN
+    null_nll = float(bnll[0]) if has_bogus else INF
     g, prior = exchange_minima(local_min, dist, rank, world)
     recs, paths = plan.pass2_n3(g, prior, stream)
     st.update({k: v for k, v in plan.stats().items() if k in ("n_rescanned", "ms_pass2")})
@@ -71,17 +76,18 @@ def search_n3(plan, leaf_cap=256, stream=None):
     n_cand = sum(e[1] for e in extras)
     # the stream the reference folds: the all-[tau,0,0] matrix first (RunTHetA.py:148,188 -- Q2), whose
     # NLL is the all-normal likelihood, then the candidates in enumeration order
-    keys = np.concatenate([[0], allrecs["rank"].astype(np.uint64) + np.uint64(1)]).astype(np.uint64)
-    nlls = np.concatenate([[null_nll], allrecs["nll"]])
+    nb = 1 if has_bogus else 0
+    keys = np.concatenate([[0] * nb, allrecs["rank"].astype(np.uint64) + np.uint64(1)]).astype(np.uint64)
+    nlls = np.concatenate([[null_nll] * nb, allrecs["nll"]])
     idx = fold_replay(keys, nlls, dup_first=False)
     res = SearchResultN3()
     res.best = []
     for i in idx:
-        if i == 0:
-            res.best.append((None, (float("nan"),) * 3, null_nll, _lib.ST_DEGENERATE))
+        if i < nb:
+            res.best.append((None, tuple(float(x) for x in bmu[0]), null_nll, int(bst[0])))
         else:
-            r = allrecs[i - 1]
-            res.best.append((allpaths[i - 1].copy(), tuple(float(x) for x in r["mu"]), float(r["nll"]), int(r["status"])))
+            r = allrecs[i - nb]
+            res.best.append((allpaths[i - nb].copy(), tuple(float(x) for x in r["mu"]), float(r["nll"]), int(r["status"])))
     res.records, res.paths = allrecs, allpaths
     res.count = n_cand + 1
     res.n_solved = n_solved + 1
