@@ -195,16 +195,27 @@ int theta_nll_rows_n3(theta_plan* plan, const uint8_t* rows_host, int64_t pitch,
 /* Row table of the plan: rows[g] = (a_g, b_g) in the reference's order (first component fastest). */
 int theta_n3_rows(const theta_plan* plan, int32_t* a, int32_t* b, int32_t* n_rows);
 /* Cut the DFS forest into lexicographically ordered work items (sub-trees) of at most ~leaf_cap
- * candidates (count DP of TimeEstimate.count_number_matrices_3, TimeEstimate.py:113-142, per sub-tree). */
+ * candidates (count DP of TimeEstimate.count_number_matrices_3, TimeEstimate.py:113-142, per sub-tree).
+ * leaf_cap <= 0: 256, or less for small spaces so that there are enough items to fill the GPU. */
 int theta_n3_prepare(theta_plan* plan, int64_t leaf_cap, int64_t max_items, uint64_t* n_items);
 int theta_n3_item_weights(const theta_plan* plan, double* weights /* [n_items] estimated leaves */);
 /* 1 if theta_n3_prepare stopped at max_items: the items then cover only a lexicographic prefix of the space. */
 int theta_n3_truncated(const theta_plan* plan, int32_t* truncated);
-/* Pass 1 / pass 2 over items [item_begin, item_end): same contract as the n=2 passes; a record's
- * `rank` is (item << 32) | sequence number inside the item, `flags` indexes paths_host. */
-int theta_search_n3_pass1(theta_plan* plan, uint64_t item_begin, uint64_t item_end, double* local_min, void* stream);
-int theta_search_n3_pass2(theta_plan* plan, double global_min, double prior_min, theta_cand* out_host, uint64_t cap,
-                          uint64_t* n_out, uint8_t* paths_host /* [cap][m] row indices */, void* stream);
+/* n=3 search of items [item_begin, item_end).  The fold of RunTHetA.py:198-206 is determined by the rank-ordered
+ * candidates inside the 1e-3-connected cluster of NLL values that contains the global minimum, so the
+ * search needs no prefix-minimum history:
+ *   theta_search_n3_min     local_min = exact minimum NLL of the shard.  Every leaf is screened by a rigorous lower
+ *                           bound against T + window + 1e-3, T = best exact NLL known (t_seed: an upper bound of the
+ *                           global minimum known beforehand, e.g. another shard's; +inf if none); survivors are solved
+ *                           and kept in the plan.  window <= 0: 4e-3.
+ *   theta_search_n3_window  every candidate of the shard with NLL <= global_min + window, or a NaN likelihood (Q6), in
+ *                           enumeration order, re-solved in reference order; rank = (item << 32) | position inside the
+ *                           item, flags indexes paths_host.  The caller checks that the cluster ends inside the window
+ *                           (a gap > 1e-3 below global_min + window) and otherwise searches again with a wider one. */
+int theta_search_n3_min(theta_plan* plan, uint64_t item_begin, uint64_t item_end, double t_seed, double window,
+                        double* local_min, void* stream);
+int theta_search_n3_window(theta_plan* plan, double global_min, double window, theta_cand* out_host, uint64_t cap,
+                           uint64_t* n_out, uint8_t* paths_host /* [cap][m] row indices */, void* stream);
 /* Every candidate of items [item_begin, item_end) in enumeration order, as row-index strings. */
 int theta_enumerate_n3(theta_plan* plan, uint64_t item_begin, uint64_t item_end, uint8_t* paths_host, uint64_t cap,
                        uint64_t* n_out);

@@ -14,7 +14,8 @@ extern "C" int n3_ref_solve_host(int m, int tau, const double* r, const double* 
     ref3::Ctx c{m, r, rN, row, 1, ra, rb, (double)tau, S0, S1, S2};
     ref3::StatusCodes sc{0, 3, 4, 10};
     ref3::Out o;
-    ref3::solve(c, sc, o);
+    ref3::SerialExec ex;
+    ref3::solve(c, sc, ex, o);
     for (int j = 0; j < 3; ++j) { mu[j] = o.mu[j]; muhat[j] = o.muhat[j]; }
     *nll = o.nll; *nfev = o.nfev;
     return o.status;

@@ -100,7 +100,7 @@ def test_two_rank_search_matches_sequential_fold():
 
 class ModelPlanN3(object):
     """Stands in for an n=3 _lib.Plan: items of a few leaves each over a given NLL stream; same prepare /
-    item_weights / pass1_n3 / pass2_n3 / null_nll / stats contract as the C ABI."""
+    item_weights / search_min_n3 / window_n3 / solve_rows / stats contract as the C ABI."""
 
     def __init__(self, nll, per_item, null_nll, m=5):
         self.nll = np.asarray(nll, dtype=np.float64)
@@ -108,8 +108,9 @@ class ModelPlanN3(object):
         self._null = null_nll
         self.m = m
         self.range = (0, 0)
+        self.windows = []
 
-    def prepare(self, leaf_cap=256, max_items=1 << 22):
+    def prepare(self, leaf_cap=0, max_items=1 << 22):
         self.n_items = (len(self.nll) + self.per_item - 1) // self.per_item
         self.truncated = False
         return self.n_items
@@ -117,32 +118,26 @@ class ModelPlanN3(object):
     def item_weights(self):
         return np.full(self.n_items, float(self.per_item))
 
-    def null_nll(self):
-        return self._null
+    def solve_rows(self, paths, want_vals=False, mode=0):  # only the all-[tau,0,0] pseudo candidate is asked for
+        assert len(paths) == 1 and not np.any(paths) and mode == 1
+        return np.full((1, 3), 1.0 / 3), None, np.array([self._null]), np.array([0], dtype=np.int32), None
 
     def _span(self):
         b, e = self.range
         return b * self.per_item, min(len(self.nll), e * self.per_item)
 
-    def pass1_n3(self, b, e, stream=None):
+    def search_min_n3(self, b, e, t_seed=float("inf"), window=0.0, stream=None):
         self.range = (b, e)
+        self.windows.append(window)
         lo, hi = self._span()
         v = self.nll[lo:hi]
         v = v[~np.isnan(v)]
         return float(v.min()) if len(v) else float("inf")
 
-    def pass2_n3(self, g, prior=float("inf"), stream=None):
+    def window_n3(self, g, window=0.0, stream=None):
         from theta_b200 import _lib
         lo, hi = self._span()
-        keep, run = [], prior
-        for k in range(lo, hi):
-            v = self.nll[k]
-            if np.isnan(v):
-                continue
-            if v < run or v <= g + 2.5e-3:
-                keep.append((k, v))
-            if v < run:
-                run = v
+        keep = [(k, self.nll[k]) for k in range(lo, hi) if self.nll[k] <= g + window]
         out = np.zeros(len(keep), dtype=_lib.CAND_DTYPE)
         paths = np.zeros((len(keep), self.m), dtype=np.uint8)
         for i, (k, v) in enumerate(keep):
@@ -163,16 +158,18 @@ def _worker_n3(rank, world, port, nll, null_nll, q):
     from theta_b200 import search_n3
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        res = search_n3.search_n3(ModelPlanN3(nll, 7, null_nll))
+        plan = ModelPlanN3(nll, 7, null_nll)
+        res = search_n3.search_n3(plan)
         best = [None if b[0] is None else int(sum(int(x) << (8 * j) for j, x in enumerate(b[0]))) for b in res.best]
-        q.put((rank, best, res.min_nll, res.count, res.n_solved))
+        q.put((rank, best, res.min_nll, res.count, res.n_solved, len(plan.windows)))
     finally:
         dist.destroy_process_group()
 
 
 def test_two_rank_n3_search_matches_sequential_fold():
-    """n=3 host path on 2 gloo ranks: items sharded by weight, min all-reduce, record + path gather, and the fold
-    over the stream that starts with the all-[tau,0,0] pseudo candidate (Q2)."""
+    """n=3 host path on 2 gloo ranks: items sharded by weight, min all-reduce, record + path gather, the check that
+    the tie cluster ends inside the window (the stream below chains ties well past the first window, so the search
+    has to widen it), and the fold over the stream that starts with the all-[tau,0,0] pseudo candidate (Q2)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import theta_oracle as O
     rng = np.random.default_rng(9)
@@ -192,7 +189,8 @@ def test_two_rank_n3_search_matches_sequential_fold():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, best, g, count, solved in outs:
+    for rank, best, g, count, solved, n_windows in outs:
         assert best == want, "rank %d" % rank
+        assert n_windows >= 1
         assert g == min(float(np.nanmin(nll)), null_nll)
         assert count == n + 1 and solved == int((~np.isnan(nll)).sum()) + 1

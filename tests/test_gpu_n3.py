@@ -87,8 +87,8 @@ def test_search_matches_reference_best(lib, golden):
 
 
 def test_search_equals_bruteforce_fold(lib, golden, monkeypatch):
-    """pass1/pass2 + replay == the reference fold over every solved candidate (computed on the GPU too); with the
-    screening of pass 1 on (default) and off (then the solved count is the exact one)."""
+    """search (minimum, window records, cluster check, replay) == the reference fold over every solved candidate
+    (computed on the GPU too); with the screening on (default) and off (then the solved count is the exact one)."""
     from theta_b200.search import fold_replay
     from theta_b200.search_n3 import search_n3
     case = golden("n3_small_full.json.gz")[2]
@@ -97,10 +97,10 @@ def test_search_equals_bruteforce_fold(lib, golden, monkeypatch):
         monkeypatch.setenv("THETA_N3_SCREEN", screen)
         res = search_n3(plan, leaf_cap=cap)
         paths = plan.enumerate_n3()
-        mu, mh, nll, st, _ = plan.solve_rows(paths)
+        mu, mh, nll, st, _ = plan.solve_rows(paths, mode=1)
         ok = st < 8
         keys = np.concatenate([[0], np.nonzero(ok)[0] + 1]).astype(np.uint64)
-        vals = np.concatenate([[plan.null_nll()], nll[ok]])
+        vals = np.concatenate([plan.solve_rows(np.zeros((1, plan.m), dtype=np.uint8), mode=1)[2], nll[ok]])
         full = fold_replay(keys, vals, dup_first=False)
         want = [None if i == 0 else tuple(paths[int(keys[i]) - 1]) for i in full]
         got = [None if b[0] is None else tuple(b[0]) for b in res.best]
@@ -113,9 +113,10 @@ def test_search_equals_bruteforce_fold(lib, golden, monkeypatch):
 
 
 def test_screening_bound_is_sound(lib, golden, monkeypatch):
-    """Pass 1 of the n=3 search skips the exact solve of leaves whose Frank-Wolfe lower bound (n3_screen) proves them
-    irrelevant.  THETA_VERIFY_APPROX=1 solves every leaf and counts leaves whose bound exceeds the exact NLL: must be
-    0 on the golden spaces and on 1.5 M candidates of the config #4 shape; and the records must not depend on it."""
+    """The walk kernel skips the exact solve of leaves whose Frank-Wolfe lower bound (walk_screen) proves them outside
+    the tie window of the minimum.  THETA_VERIFY_APPROX=1 solves every leaf and counts leaves whose bound exceeds the
+    exact NLL: must be 0 on the golden spaces and on ~1.5 M candidates of the config #4 shape; and the minimum and
+    the window records must not depend on the screen (on, verify, off) nor on the bootstrap waves."""
     import sys, os
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
     import theta_oracle as O
@@ -134,21 +135,23 @@ def test_screening_bound_is_sound(lib, golden, monkeypatch):
                 monkeypatch.setenv("THETA_VERIFY_APPROX", "1")
             if mode == "off":
                 monkeypatch.setenv("THETA_N3_SCREEN", "0")
-            g = plan.pass1_n3(0, end)
+            g = plan.search_min_n3(0, end)
             st = plan.stats()
-            recs, paths = plan.pass2_n3(g)
+            recs, paths = plan.window_n3(g)
             out[mode] = (g, st, recs.copy(), paths.copy())
         monkeypatch.delenv("THETA_VERIFY_APPROX", raising=False)
         monkeypatch.delenv("THETA_N3_SCREEN", raising=False)
-        assert out["verify"][1]["n_bound_violations"] == 0
+        for mode in ("screen", "verify", "off"):
+            assert out[mode][1]["n_bound_violations"] == 0, mode
         assert out["verify"][1]["n_exact"] == out["verify"][1]["n_candidates"] == out["off"][1]["n_candidates"]
+        assert out["screen"][1]["n_candidates"] == out["off"][1]["n_candidates"]
         assert out["screen"][0] == out["off"][0] == out["verify"][0]
         for mode in ("screen", "verify"):
             assert out[mode][2]["nll"].tobytes() == out["off"][2]["nll"].tobytes()
             assert out[mode][2]["rank"].tobytes() == out["off"][2]["rank"].tobytes()
             assert out[mode][3].tobytes() == out["off"][3].tobytes()
         if out["off"][1]["n_candidates"] > 100000:
-            assert out["screen"][1]["n_exact"] < out["off"][1]["n_candidates"] // 2  # the screen does skip
+            assert out["screen"][1]["n_exact"] < out["off"][1]["n_candidates"] // 20  # the screen does skip
         plan.close()
 
 

@@ -148,3 +148,41 @@ def test_filter_records_host_function():
                 run = v
         got = _lib.filter_records(recs.copy(), near, prior)
         assert [int(x) for x in got["rank"]] == want
+
+
+def test_rank_free_window_fold_equals_sequential_fold():
+    """The n=3 search keeps no prefix-minimum history: it replays the reference fold (RunTHetA.py:198-206) over the
+    candidates within a window of the global minimum only, after checking that the 1e-3-connected cluster of the
+    minimum ends inside the window (theta_b200/search_n3.py).  Randomised streams with exact ties, chains of near
+    ties, 1e-3-edge cases and NaN likelihoods (Q6): the windowed fold must equal the sequential one whenever the
+    check passes, and widening must terminate."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import theta_oracle as O
+    from theta_b200.search import fold_replay
+    from theta_b200.search_n3 import cluster_top
+    rng = np.random.default_rng(11)
+    widened = 0
+    for trial in range(4000):
+        n = int(rng.integers(1, 120))
+        steps = rng.choice([0.0, 1e-3, 9.99e-4, 1.001e-3, 4e-4, 2.0, 50.0], size=n)
+        nll = 1e6 + np.cumsum(rng.choice([-1, 1], size=n) * steps)
+        if trial % 3 == 0:
+            nll[rng.integers(0, n, max(1, n // 10))] = np.nan
+        want = O.fold([(i, float(v)) for i, v in enumerate(nll)])
+        fin = nll[~np.isnan(nll)]
+        if len(fin) == 0:
+            assert want == list(range(n))
+            continue
+        g = float(fin.min())
+        window = 4e-3
+        while True:
+            keep = [i for i in range(n) if np.isnan(nll[i]) or nll[i] <= g + window]
+            vals = [float(nll[i]) for i in keep if not np.isnan(nll[i])]
+            if cluster_top(vals, g) + 1e-3 < g + window - 1e-6:
+                break
+            window *= 8
+            widened += 1
+            assert window < 1e9
+        idx = fold_replay(np.array(keep, dtype=np.uint64) + 1, nll[keep], dup_first=False)
+        assert [keep[i] for i in idx] == want, (trial, window)
+    assert widened > 50  # the widening path is exercised

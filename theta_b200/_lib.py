@@ -69,8 +69,8 @@ SYMBOLS = {
     "theta_n3_prepare": (C.c_int, [_VP, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
     "theta_n3_item_weights": (C.c_int, [_VP, _VP]),
     "theta_n3_truncated": (C.c_int, [_VP, C.POINTER(C.c_int32)]),
-    "theta_search_n3_pass1": (C.c_int, [_VP, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), _VP]),
-    "theta_search_n3_pass2": (C.c_int, [_VP, C.c_double, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP, _VP]),
+    "theta_search_n3_min": (C.c_int, [_VP, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.POINTER(C.c_double), _VP]),
+    "theta_search_n3_window": (C.c_int, [_VP, C.c_double, C.c_double, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP, _VP]),
     "theta_enumerate_n3": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
     "theta_solve_rows_n3": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, C.c_int32]),
     "theta_enumerate_n2": (C.c_int, [_VP, C.c_uint64, C.c_int64, _VP, C.c_int64]),
@@ -224,7 +224,7 @@ class Plan(object):
         check(load().theta_n3_rows(self._h, ptr(a), ptr(b), C.byref(n)))
         return [(int(x), int(y)) for x, y in zip(a[:n.value], b[:n.value])]
 
-    def prepare(self, leaf_cap=256, max_items=1 << 22):
+    def prepare(self, leaf_cap=0, max_items=1 << 22):
         n = C.c_uint64()
         check(load().theta_n3_prepare(self._h, int(leaf_cap), int(max_items), C.byref(n)))
         self.n_items = int(n.value)
@@ -239,19 +239,22 @@ class Plan(object):
             check(load().theta_n3_item_weights(self._h, ptr(w)))
         return w
 
-    def pass1_n3(self, item_begin, item_end, stream=None):
+    def search_min_n3(self, item_begin, item_end, t_seed=float("inf"), window=0.0, stream=None):
+        """Exact minimum NLL of the items [item_begin, item_end) (theta_search_n3_min)."""
         g = C.c_double()
-        check(load().theta_search_n3_pass1(self._h, int(item_begin), int(item_end), C.byref(g), stream))
+        check(load().theta_search_n3_min(self._h, int(item_begin), int(item_end), float(t_seed), float(window),
+                                         C.byref(g), stream))
         return float(g.value)
 
-    def pass2_n3(self, global_min, prior_min=float("inf"), stream=None):
+    def window_n3(self, global_min, window=0.0, stream=None):
+        """Records + row-index paths of every candidate within `window` of global_min (theta_search_n3_window)."""
         cap = 1 << 12
         while True:
             buf = np.zeros(cap, dtype=CAND_DTYPE)
             paths = np.zeros((cap, self.m), dtype=np.uint8)
             n = C.c_uint64()
-            rc = load().theta_search_n3_pass2(self._h, float(global_min), float(prior_min), ptr(buf), cap, C.byref(n),
-                                              ptr(paths), stream)
+            rc = load().theta_search_n3_window(self._h, float(global_min), float(window), ptr(buf), cap, C.byref(n),
+                                               ptr(paths), stream)
             if rc == ERR_OVERFLOW and n.value > cap:
                 cap = int(n.value) + 16
                 continue

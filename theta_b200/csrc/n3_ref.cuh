@@ -50,41 +50,101 @@ struct Ctx {
     }
 };
 
+// How the per-interval sums are executed.  Every sum of the reference runs left to right over the intervals, and that
+// order is part of the result; the terms themselves (divisions, pow, log) are independent.
+//   SerialExec  one thread does everything (host tests, thread-per-candidate kernels).
+//   WarpExec    (device) the 32 lanes of a warp compute the terms of their intervals into shared memory, then every
+//               lane adds them up in interval order -- the same roundings, ~30x less latency; all lanes hold identical
+//               values afterwards, so the scalar MINPACK / line-search code around the sums stays warp-uniform.
+// term(i, t) writes the K addends of interval i.
+struct SerialExec {
+    template <int K, class F>
+    THETA_HD void sums(int n, F& term, xf64* out) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k] = 0.0;
+        for (int i = 0; i < n; ++i) {
+            xf64 t[K];
+            term(i, t);
+#pragma unroll
+            for (int k = 0; k < K; ++k) out[k] += t[k];
+        }
+    }
+};
+#ifdef __CUDACC__
+struct WarpExec {
+    double* scratch;  // [9][n_max] doubles of shared memory owned by this warp
+    int stride;       // n_max
+    template <int K, class F>
+    __host__ __device__ __forceinline__ void sums(int n, F& term, xf64* out) {
+#ifdef __CUDA_ARCH__
+        const int lane = threadIdx.x & 31;
+        for (int i = lane; i < n; i += 32) {
+            xf64 t[K];
+            term(i, t);
+#pragma unroll
+            for (int k = 0; k < K; ++k) scratch[k * stride + i] = t[k].v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k] = 0.0;
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) out[k] += xf64(scratch[k * stride + i]);
+        }
+        __syncwarp();
+#endif
+    }
+};
+#endif
+
 // equations / jacobian (Optimizer.py:267-318) for fsolve
+struct EqTerm {
+    const Ctx* c;
+    const xf64* x;
+    THETA_HD void operator()(int i, xf64* t) const {
+        xf64 c0, c1, c2;
+        c->chat(i, c0, c1, c2);
+        const xf64 d = (c0 * x[0] + c1 * x[1]) + c2 * x[2];  // sum([C_hat[i][j]*mu[j] ...]): 0 + t0 + t1 + t2
+        const xf64 ri = c->r[i];
+        t[0] = (ri * c0) / d;  // dLambda_dMu_numers[k][i] / d
+        t[1] = (ri * c1) / d;
+        t[2] = (ri * c2) / d;
+    }
+};
+struct JacTerm {
+    const Ctx* c;
+    const xf64* x;
+    THETA_HD void operator()(int i, xf64* t) const {
+        xf64 ch[3];
+        c->chat(i, ch[0], ch[1], ch[2]);
+        const xf64 d = (ch[0] * x[0] + ch[1] * x[1]) + ch[2] * x[2];
+        const xf64 d2 = glibc::pow2(d.v);  // (...)**2 on a numpy float64
+        const xf64 ri = c->r[i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const xf64 rk = ri * ch[k];
+#pragma unroll
+            for (int h = 0; h < 3; ++h) t[3 * k + h] = (rk * ch[h]) / d2;
+        }
+    }
+};
+template <class Exec>
 struct Kkt {
     const Ctx* c;
+    Exec* ex;
     THETA_HDN void fcn(const xf64* x, xf64* f) {
-        xf64 s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        for (int i = 0; i < c->m; ++i) {
-            xf64 c0, c1, c2;
-            c->chat(i, c0, c1, c2);
-            const xf64 d = (c0 * x[0] + c1 * x[1]) + c2 * x[2];  // sum([C_hat[i][j]*mu[j] ...]): 0 + t0 + t1 + t2
-            const xf64 ri = c->r[i];
-            s0 += (ri * c0) / d;  // dLambda_dMu_numers[k][i] / d
-            s1 += (ri * c1) / d;
-            s2 += (ri * c2) / d;
-        }
-        f[0] = (-s0) - x[3];
-        f[1] = (-s1) - x[3];
-        f[2] = (-s2) - x[3];
+        xf64 s[3];
+        EqTerm term{c, x};
+        ex->template sums<3>(c->m, term, s);
+        f[0] = (-s[0]) - x[3];
+        f[1] = (-s[1]) - x[3];
+        f[2] = (-s[2]) - x[3];
         f[3] = xf64(1.0) - ((x[0] + x[1]) + x[2]);
     }
     THETA_HDN int jac(const xf64* x, const xf64*, xf64* J) {  // column-major J[i + 4 j] = d f_i / d x_j
         xf64 s[9];
-        for (int a = 0; a < 9; ++a) s[a] = 0.0;
-        for (int i = 0; i < c->m; ++i) {
-            xf64 ch[3];
-            c->chat(i, ch[0], ch[1], ch[2]);
-            const xf64 d = (ch[0] * x[0] + ch[1] * x[1]) + ch[2] * x[2];
-            const xf64 d2 = glibc::pow2(d.v);  // (...)**2 on a numpy float64
-            const xf64 ri = c->r[i];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const xf64 rk = ri * ch[k];
-#pragma unroll
-                for (int h = 0; h < 3; ++h) s[3 * k + h] += (rk * ch[h]) / d2;
-            }
-        }
+        JacTerm term{c, x};
+        ex->template sums<9>(c->m, term, s);
 #pragma unroll
         for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -100,35 +160,47 @@ struct Kkt {
 };
 
 // L3_hat and dL3_hat (Optimizer.py:246-265, sign error kept: Q7) along x0 + alpha pk, per interval
+struct LhatTerm {
+    const Ctx* c;
+    xf64 M0, M1, M2;
+    THETA_HD void operator()(int i, xf64* t) const {
+        xf64 c0, c1, c2;
+        c->chat(i, c0, c1, c2);
+        const xf64 d = (c0 * M0 + c1 * M1) + c2 * M2;
+        t[0] = xf64(c->r[i]) * xf64(log(d.v));  // log of a negative number is NaN, as in numpy
+    }
+};
+struct DLhatTerm {
+    const Ctx* c;
+    xf64 M0, M1;
+    THETA_HD void operator()(int i, xf64* t) const {
+        xf64 c0, c1, c2;
+        c->chat(i, c0, c1, c2);
+        const xf64 n0 = c0 - c2, n1 = c1 - c2;
+        const xf64 den = (n0 * M0 + n1 * M1) + c2;
+        const xf64 ri = c->r[i];
+        t[0] = ri * (n0 / den);
+        t[1] = ri * (n1 / den);
+    }
+};
+template <class Exec>
 struct Ray {
     const Ctx* c;
+    Exec* ex;
     double x0[2], pk[2];
     THETA_HDN double L3_hat(double m0, double m1) const {
         const xf64 M0 = m0, M1 = m1;
-        const xf64 M2 = xf64(1.0) - (M0 + M1);
-        xf64 tot = 0.0;
-        for (int i = 0; i < c->m; ++i) {
-            xf64 c0, c1, c2;
-            c->chat(i, c0, c1, c2);
-            const xf64 d = (c0 * M0 + c1 * M1) + c2 * M2;
-            tot += xf64(c->r[i]) * xf64(log(d.v));  // log of a negative number is NaN, as in numpy
-        }
-        return -tot.v;
+        LhatTerm term{c, M0, M1, xf64(1.0) - (M0 + M1)};
+        xf64 tot[1];
+        ex->template sums<1>(c->m, term, tot);
+        return -tot[0].v;
     }
     THETA_HDN void dL3_hat(double m0, double m1, double* out) const {
-        const xf64 M0 = m0, M1 = m1;
-        xf64 v0 = 0.0, v1 = 0.0;
-        for (int i = 0; i < c->m; ++i) {
-            xf64 c0, c1, c2;
-            c->chat(i, c0, c1, c2);
-            const xf64 n0 = c0 - c2, n1 = c1 - c2;
-            const xf64 den = (n0 * M0 + n1 * M1) + c2;
-            const xf64 ri = c->r[i];
-            v0 += ri * (n0 / den);
-            v1 += ri * (n1 / den);
-        }
-        out[0] = v0.v;
-        out[1] = v1.v;
+        DLhatTerm term{c, xf64(m0), xf64(m1)};
+        xf64 v[2];
+        ex->template sums<2>(c->m, term, v);
+        out[0] = v[0].v;
+        out[1] = v[1].v;
     }
     THETA_HD double phi(double alpha) const {
         return L3_hat((xf64(x0[0]) + xf64(alpha) * xf64(pk[0])).v, (xf64(x0[1]) + xf64(alpha) * xf64(pk[1])).v);
@@ -171,6 +243,32 @@ struct MeqSys {
     }
 };
 
+// L3 (Optimizer.py:236-244): denom = sum over columns (outer) and intervals (inner) of C_w[h][j] mu[j], left to right
+struct DenTerm {
+    const Ctx* c;
+    const xf64* y;
+    THETA_HD void operator()(int q, xf64* t) const {
+        const int j = q / c->m, h = q - j * c->m;
+        const int g = c->row[(size_t)h * c->rstride];
+        const double cj = j == 0 ? c->tau : (j == 1 ? (double)c->ra[g] : (double)c->rb[g]);
+        t[0] = (xf64(c->rN[h]) * xf64(cj)) * y[j];
+    }
+};
+struct L3Term {
+    const Ctx* c;
+    const xf64* y;
+    xf64 denom;
+    double* vals;  // optional: numer_i / denom
+    THETA_HD void operator()(int i, xf64* t) const {
+        const int g = c->row[(size_t)i * c->rstride];
+        const xf64 w = c->rN[i];
+        const xf64 numer = ((w * xf64(c->tau)) * y[0] + (w * xf64((double)c->ra[g])) * y[1]) + (w * xf64((double)c->rb[g])) * y[2];
+        const xf64 v = numer / denom;
+        if (vals) vals[i] = v.v;
+        t[0] = xf64(c->r[i]) * xf64(log(v.v));
+    }
+};
+
 struct Out {
     double mu[3];     // M3's answer
     double muhat[3];  // what went into M3
@@ -183,11 +281,12 @@ struct StatusCodes {
     int ok, fallback_x0, fallback_moved, none_range;
 };
 
-THETA_HDN void solve(const Ctx& c, const StatusCodes& sc, Out& o) {
+template <class Exec>
+THETA_HDN void solve(const Ctx& c, const StatusCodes& sc, Exec& ex, Out& o, double* vals = nullptr) {
     o.nll = 0.0;
     for (int j = 0; j < 3; ++j) o.mu[j] = o.muhat[j] = 0.0;
     // ---- fsolve(equations, [1/3, 1/3, 1/3, 1], fprime=jacobian)
-    Kkt sys{&c};
+    Kkt<Exec> sys{&c, &ex};
     const double third = 1.0 / 3.0;
     xf64 x[4] = {third, third, third, 1.0};
     const mp::Result res = mp::hybrj<xf64>(sys, x, xf64(1.49012e-8), 500, xf64(100.0));
@@ -199,7 +298,7 @@ THETA_HDN void solve(const Ctx& c, const StatusCodes& sc, Out& o) {
     int status = sc.ok;
     if (!in_range) {
         // ---- fmin_bfgs(L3_hat, [1/3, 1/3], fprime=dL3_hat): first iteration (see theta_n3.cuh::n3_solve)
-        Ray ray{&c, {third, third}, {0.0, 0.0}};
+        Ray<Exec> ray{&c, &ex, {third, third}, {0.0, 0.0}};
         double g0[2];
         const double f0 = ray.L3_hat(third, third);
         ray.dL3_hat(third, third, g0);
@@ -234,22 +333,13 @@ THETA_HDN void solve(const Ctx& c, const StatusCodes& sc, Out& o) {
     for (int j = 0; j < 3; ++j) ms.mu[j] = mh[j];
     xf64 y[4] = {0.33, 0.33, 0.33, 0.0};
     mp::hybrj<xf64>(ms, y, xf64(1.49012e-8), 1000, xf64(100.0));
-    // ---- L3(answer, C_w, r): denom = sum over columns (outer) and intervals (inner), left to right
-    xf64 denom = 0.0;
-    for (int j = 0; j < 3; ++j)
-        for (int h = 0; h < c.m; ++h) {
-            const int g = c.row[(size_t)h * c.rstride];
-            const double cj = j == 0 ? c.tau : (j == 1 ? (double)c.ra[g] : (double)c.rb[g]);
-            denom += (xf64(c.rN[h]) * xf64(cj)) * y[j];
-        }
-    xf64 tot = 0.0;
-    for (int i = 0; i < c.m; ++i) {
-        const int g = c.row[(size_t)i * c.rstride];
-        const xf64 w = c.rN[i];
-        const xf64 numer = ((w * xf64(c.tau)) * y[0] + (w * xf64((double)c.ra[g])) * y[1]) + (w * xf64((double)c.rb[g])) * y[2];
-        tot += xf64(c.r[i]) * xf64(log((numer / denom).v));
-    }
-    o.nll = -tot.v;
+    // ---- L3(answer, C_w, r)
+    xf64 denom[1], tot[1];
+    DenTerm dt{&c, y};
+    ex.template sums<1>(3 * c.m, dt, denom);
+    L3Term lt{&c, y, denom[0], vals};
+    ex.template sums<1>(c.m, lt, tot);
+    o.nll = -tot[0].v;
     for (int j = 0; j < 3; ++j) o.mu[j] = y[j].v;
 }
 

@@ -7,11 +7,16 @@
 // Work decomposition: the reference's DFS visits row sequences in lexicographic order of row index.
 // The host cuts the DFS forest into *items* -- sub-trees given by a prefix of row indices -- using the
 // count DP of TimeEstimate.count_number_matrices_3 (python/TimeEstimate.py:113-142) per sub-tree, and
-// lists them in lexicographic order, so item order == enumeration order.  Every GPU thread takes items
-// from a ticket counter and walks its sub-tree depth first with the reference's pruning rules,
-// keeping the grouped statistics (R_g, S1, S2) incrementally (exact integer sums in fp64).
+// lists them in lexicographic order, so item order == enumeration order.  Two kernels alternate:
+//   n3_walk_kernel         every thread takes items from a ticket counter and walks its sub-tree depth first with the
+//                          reference's pruning rules, keeping the grouped statistics (R_g, S1, S2) incrementally (exact
+//                          integer sums in fp64), and screens each leaf with a rigorous lower bound of its NLL against
+//                          the best exact NLL known; survivors are queued;
+//   n3_solve_queue_kernel  solves the queued survivors (grouped-statistics hybrj, or the reference-order solver for
+//                          rank-deficient candidates) and lowers the best NLL.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -36,12 +41,24 @@ struct theta_n3_state {
     double* d_rN = nullptr;
     uint8_t* d_prefix = nullptr;
     uint32_t* d_off = nullptr;
-    double* d_item_min = nullptr;
     unsigned long long* d_ctr = nullptr;
-    std::vector<double> h_item_min;
     std::vector<std::vector<double>> est;  // est[i][g*2+sw]: completions of a prefix ending in row g at interval i (no mu-bounds)
+    // survivor queue of the last search (kept for theta_search_n3_window)
+    uint32_t* d_q_meta = nullptr;
+    double* d_q_lb = nullptr;
+    theta_cand* d_q_res = nullptr;
+    uint8_t* d_q_path = nullptr;
+    size_t q_cap = 0;
+    uint64_t q_count = 0;
+    double window = 0.0;
+    uint32_t* d_ref_list = nullptr;  // queue slots left to the warp-cooperative reference-order solver ([q_cap])
+    unsigned long long* d_ctr_rows = nullptr;  // counters of theta_solve_rows_n3 (kCtrWords)
+    uint32_t* d_list = nullptr;   // wave-0 item list of the range [list_begin, list_end)
+    uint64_t list_begin = 0, list_end = 0;
+    uint32_t list_n0 = 0;
     uint64_t p1_begin = 0, p1_end = 0;
     unsigned long long nan_nll = 0;
+    unsigned long long it_hist[3] = {0, 0, 0};
     bool truncated = false;
 };
 
@@ -87,260 +104,520 @@ __host__ __device__ inline bool step_bounds(int pa, int pb, int ca, int cb, uint
     return ratio_val(mn) <= ratio_val(mx);
 }
 
-template <int MAXM>
-struct Dfs {
-    uint8_t path[MAXM], mn[MAXM], mx[MAXM], sw[MAXM];
-    double R[kMaxRows3];
-    uint16_t cnt[kMaxRows3];
-    double S1, S2;
-    int depth;  // last filled position
-    int base;   // depth of the item prefix's last position
+// ======================================================================= device: walk + screen (kernel A)
+//
+// One thread per work item (a DFS sub-tree), items taken from a ticket counter.  Everything a thread touches while
+// walking lives in registers or in shared memory laid out [slot][thread] (bank = thread: conflict-free whatever
+// depth each lane is at) -- no local memory:
+//   path   one byte per interval, four per 32-bit word: row index | 0x80 if that push changed (mn, mx, switch)
+//   undo   the (mn, mx, switch) values replaced by such pushes (kUndo entries; deeper: recomputed by replay)
+//   R[g]   reads per row type (exact integers in fp64), plus a 64-bit "present" mask in a register
+// Leaves are screened against T + margin (T: the best exact NLL known when the wave started) or a fixed threshold;
+// survivors go to a global queue (path + lower bound) that the solve kernel (kernel B) drains.  The 33 k-instruction
+// solver is never part of this kernel, so it runs at ~100 registers with no block-level synchronisation.
+static constexpr int kUndo = 12;
 
-    __device__ void reset(int NR) {
-        for (int g = 0; g < NR; ++g) { R[g] = 0.0; cnt[g] = 0; }
-        S1 = S2 = 0.0;
-        depth = -1;
+struct WalkParams {
+    N3Dev D;
+    const uint8_t* prefix;
+    const uint32_t* off;
+    const uint32_t* list;        // explicit item list (NULL: item = item_begin + ticket)
+    uint32_t item_begin;
+    uint32_t n_work;
+    unsigned long long* ctr;     // kCtr* below
+    double margin;               // threshold = min(fixed_thr, T + margin)
+    double fixed_thr;
+    uint32_t* q_meta;            // [cap][2]: item, leaf ordinal inside the item
+    double* q_lb;                // [cap] screening bound of the survivor (verification)
+    uint8_t* q_path;             // [cap][m]
+    unsigned long long q_cap;
+    int enumerate_only;          // every leaf is a survivor, nothing is screened
+    int screen;                  // 0: off, 1: fp32 logarithms, 2: fp64 table logarithms
+    int verify;                  // THETA_VERIFY_APPROX=1: every leaf is solved, bounds are checked against the exact NLL
+    int block;
+    uint32_t scout_stride;       // > 0: scout wave -- every scout_stride-th leaf of each item gets the full Newton bound,
+                                 // the leaf with the lowest bound is queued (slot = ticket), nothing else
+    int count_leaves;            // add the leaves walked to the candidate count (off in the scout wave)
+};
+enum { kCtrTicket = 0, kCtrLeaves = 1, kCtrQueue = 2, kCtrDone = 3, kCtrSolved = 4, kCtrNfev = 5, kCtrNan = 6, kCtrViol = 7,
+       kCtrT = 8, kCtrIt0 = 9, kCtrIt1 = 10, kCtrIt2 = 11, kCtrRef = 12, kCtrRefQ = 13, kCtrRefDone = 14, kCtrWords = 16 };
+
+struct Walk {
+    // shared-memory views of this thread (stride B between slots)
+    uint32_t* pw;
+    uint32_t* undo;
+    double* R;
+    const uint64_t* allow;
+    const double* r;
+    const double* rN;
+    const float* ratio;
+    const N3Dev* D;
+    int B;
+    double S1, S2;
+    uint64_t present;
+    int depth, base, nundo, m;
+    uint8_t mn, mx, sw;
+
+    __device__ __forceinline__ int get(int pos) const { return (int)((pw[(pos >> 2) * B] >> ((pos & 3) * 8)) & 0xffu); }
+    __device__ __forceinline__ void set(int pos, int v) {
+        uint32_t& w = pw[(pos >> 2) * B];
+        const int sh = (pos & 3) * 8;
+        w = (w & ~(0xffu << sh)) | ((uint32_t)v << sh);
     }
-    __device__ void push(const N3Dev& D, int pos, int g, uint8_t mnc, uint8_t mxc, uint8_t s) {
-        path[pos] = (uint8_t)g; mn[pos] = mnc; mx[pos] = mxc; sw[pos] = s;
-        R[g] += D.r[pos];
-        cnt[g] += 1;
-        S1 += D.rN[pos] * (double)D.ra[g];
-        S2 += D.rN[pos] * (double)D.rb[g];
+    __device__ __forceinline__ int row(int pos) const { return get(pos) & 0x3f; }
+    // Enumerator._generate_next_C_3_recurse's bound update (step_bounds above) on the ratio table
+    __device__ __forceinline__ bool step(int pg, int cg, uint8_t& mnc, uint8_t& mxc) const {
+        const int x = (int)D->ra[cg] - (int)D->ra[pg], y = (int)D->rb[cg] - (int)D->rb[pg];
+        if (x != 0 && y != 0) {
+            const uint8_t c = ratio_code(x, y);
+            if (x > 0) { if (ratio[c] > ratio[mnc]) mnc = c; }
+            else { if (ratio[c] < ratio[mxc]) mxc = c; }
+        }
+        return ratio[mnc] <= ratio[mxc];
+    }
+    __device__ __forceinline__ void push(int pos, int g, uint8_t mnc, uint8_t mxc, uint8_t s) {
+        const bool changed = (mnc != mn) | (mxc != mx) | (s != sw);
+        if (changed) {
+            if (nundo < kUndo) undo[nundo * B] = (uint32_t)mn | ((uint32_t)mx << 8) | ((uint32_t)sw << 16);
+            ++nundo;
+            mn = mnc; mx = mxc; sw = s;
+        }
+        set(pos, g | (changed ? 0x80 : 0));
+        R[g * B] += r[pos];
+        present |= 1ull << g;
+        S1 += rN[pos] * (double)D->ra[g];
+        S2 += rN[pos] * (double)D->rb[g];
         depth = pos;
     }
-    __device__ void pop(const N3Dev& D) {
-        const int pos = depth, g = path[pos];
-        R[g] -= D.r[pos];
-        cnt[g] -= 1;
-        S1 -= D.rN[pos] * (double)D.ra[g];
-        S2 -= D.rN[pos] * (double)D.rb[g];
+    __device__ void replay(int upto) {  // (mn, mx, switch) after positions 0..upto; only when the undo log overflowed
+        uint8_t mnc = 0, mxc = 255, s = 0;
+        for (int i = 0; i <= upto; ++i) {
+            const int g = row(i);
+            if (i == 0) s = (D->ra[g] == D->rb[g]) ? 1 : 0;
+            else {
+                step(row(i - 1), g, mnc, mxc);
+                s = (s && D->ra[g] == D->rb[g]) ? 1 : 0;
+            }
+        }
+        mn = mnc; mx = mxc; sw = s;
+    }
+    __device__ __forceinline__ void pop() {
+        const int pos = depth, v = get(pos), g = v & 0x3f;
+        double& Rg = R[g * B];
+        Rg -= r[pos];
+        if (Rg == 0.0) present &= ~(1ull << g);
+        S1 -= rN[pos] * (double)D->ra[g];
+        S2 -= rN[pos] * (double)D->rb[g];
+        if (v & 0x80) {
+            --nundo;
+            if (nundo < kUndo) {
+                const uint32_t e = undo[nundo * B];
+                mn = (uint8_t)(e & 0xff); mx = (uint8_t)((e >> 8) & 0xff); sw = (uint8_t)((e >> 16) & 1);
+            } else {
+                replay(pos - 1);
+            }
+        }
         depth = pos - 1;
     }
-    __device__ uint64_t children(const N3Dev& D) const {
-        uint64_t c = D.edges[path[depth]] & D.allow[depth + 1];
-        if (sw[depth]) c &= D.symmask;
+    __device__ __forceinline__ uint64_t children() const {
+        uint64_t c = D->edges[row(depth)] & allow[depth + 1];
+        if (sw) c &= D->symmask;
         return c;
     }
-    // replay an item prefix (already validated by the host)
-    __device__ void load_prefix(const N3Dev& D, const uint8_t* pre, int len) {
-        reset(D.kc.NR);
-        uint8_t mnc = 0, mxc = 255, s = 0;
+    __device__ void load_prefix(const uint8_t* pre, int len) {
+        for (int g = 0; g < D->kc.NR; ++g) R[g * B] = 0.0;
+        present = 0;
+        S1 = S2 = 0.0;
+        nundo = 0;
+        mn = 0; mx = 255; sw = 0;
+        depth = -1;
         for (int i = 0; i < len; ++i) {
             const int g = pre[i];
-            if (i == 0) s = (D.ra[g] == D.rb[g]) ? 1 : 0;
+            uint8_t mnc = mn, mxc = mx, s;
+            if (i == 0) s = (D->ra[g] == D->rb[g]) ? 1 : 0;
             else {
-                step_bounds(D.ra[path[i - 1]], D.rb[path[i - 1]], D.ra[g], D.rb[g], mnc, mxc);
-                s = (s && D.ra[g] == D.rb[g]) ? 1 : 0;
+                step(row(i - 1), g, mnc, mxc);
+                s = (sw && D->ra[g] == D->rb[g]) ? 1 : 0;
             }
-            push(D, i, g, mnc, mxc, s);
+            push(i, g, mnc, mxc, s);
         }
         base = len - 1;
     }
     // advance to the next leaf of the sub-tree; `fresh` = nothing visited yet in this item
-    __device__ bool next_leaf(const N3Dev& D, bool fresh) {
-        const int last = D.kc.m - 1;
+    __device__ bool next_leaf(bool fresh) {
+        const int last = m - 1;
         uint64_t cand;
         if (fresh) {
             if (depth == last) return true;  // the prefix itself is a complete candidate
-            cand = children(D);
+            cand = children();
         } else {
             if (depth == base) return false;  // item was a single leaf
-            const int g = path[depth];
-            pop(D);
-            cand = children(D) & ~((2ull << g) - 1ull);
+            const int g = row(depth);
+            pop();
+            cand = children() & ~((2ull << g) - 1ull);
         }
         for (;;) {
             bool pushed = false;
+            const int pg = row(depth);
             while (cand) {
                 const int c = __ffsll((long long)cand) - 1;
                 cand &= cand - 1;
-                uint8_t mnc = mn[depth], mxc = mx[depth];
-                const int pg = path[depth];
-                if (step_bounds(D.ra[pg], D.rb[pg], D.ra[c], D.rb[c], mnc, mxc)) {
-                    const uint8_t s = (sw[depth] && D.ra[c] == D.rb[c]) ? 1 : 0;
-                    push(D, depth + 1, c, mnc, mxc, s);
+                uint8_t mnc = mn, mxc = mx;
+                if (step(pg, c, mnc, mxc)) {
+                    const uint8_t s = (sw && D->ra[c] == D->rb[c]) ? 1 : 0;
+                    push(depth + 1, c, mnc, mxc, s);
                     pushed = true;
                     break;
                 }
             }
             if (pushed) {
                 if (depth == last) return true;
-                cand = children(D);
+                cand = children();
             } else {
                 if (depth == base) return false;
-                const int g = path[depth];
-                pop(D);
-                cand = children(D) & ~((2ull << g) - 1ull);
+                const int g = row(depth);
+                pop();
+                cand = children() & ~((2ull << g) - 1ull);
             }
         }
     }
-    __device__ void groups(const N3Dev& D, Groups3& G) const {
-        int n = 0;
-        for (int g = 0; g < D.kc.NR; ++g) {
-            if (cnt[g]) {
-                G.R[n] = R[g];
-                G.a[n] = (double)D.ra[g];
-                G.b[n] = (double)D.rb[g];
-                ++n;
+};
+
+// n3_screen (theta_n3.cuh) on the walker's state: groups are the set bits of `present`.
+__device__ __forceinline__ bool walk_screen(const Walk& w, const N3Const& k, Screen3& ws, double thr, double& lb_out,
+                                            const double2* LT, int& iters) {
+    lb_out = -INFINITY;
+    iters = 0;
+    const double S1 = w.S1, S2 = w.S2;
+    if (k.any_zero_rN || !(S1 > 0.0) || !(S2 > 0.0)) return false;
+    const double t1 = k.A / S1, t2 = k.A / S2;  // A d_g = y0 + a (A/S1) y1 + b (A/S2) y2
+    const double E = (LT ? 1e-11 : THETA_N3_APPROX_C) * k.Rtot;
+    double y0 = ws.y0, y1 = ws.y1;
+    if (!(y0 > 1e-6 && y1 > 1e-6 && y0 + y1 < 1.0 - 1e-6)) { y0 = 1.0 / 3.0; y1 = 1.0 / 3.0; }
+    for (int it = 0; it < 3; ++it) {
+        iters = it + 1;
+        const double y2 = 1.0 - (y0 + y1);
+        const double u1 = y1 * t1, u2 = y2 * t2;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, h00 = 0.0, h01 = 0.0, h02 = 0.0, h11 = 0.0, h12 = 0.0, h22 = 0.0, lacc = 0.0;
+        bool ok = true;
+        for (uint64_t msk = w.present; msk; msk &= msk - 1) {
+            const int g = __ffsll((long long)msk) - 1;
+            const double a = (double)w.D->ra[g], b = (double)w.D->rb[g], R = w.R[g * w.B];
+            const double d = y0 + a * u1 + b * u2;  // A d_g > 0 in the interior
+            const double r = fast_rcp1(d);
+            const double q = R * r, qq = q * r, aq = a * qq, bq = b * qq;
+            s0 += q; s1 = fma(a, q, s1); s2 = fma(b, q, s2);
+            h00 += qq; h01 += aq; h02 += bq; h11 = fma(a, aq, h11); h12 = fma(a, bq, h12); h22 = fma(b, bq, h22);
+            if (LT) {
+                lacc = fma(R, fast_log(d, LT), lacc);
+            } else {
+                const float df = (float)d;
+                if (!(df >= 3.0517578125e-05f && df <= 32768.0f)) ok = false;
+                lacc = fma(R, (double)__log2f(df), lacc);
             }
         }
-        G.G = n;
+        if (!ok) return false;
+        const double G0 = s0, G1 = t1 * s1, G2 = t2 * s2;
+        const double gap = fmax(G0, fmax(G1, G2)) - k.Rtot;
+        const double fy = LT ? k.K0 - lacc : fma(-0.6931471805599453094, lacc, k.K0);
+        const double lb = fy - fmax(gap, 0.0) * (1.0 + 1e-9) - E;
+        if (lb > lb_out) lb_out = lb;
+        if (lb > thr) { ws.y0 = y0; ws.y1 = y1; return true; }
+        if (it == 2) break;
+        const double g0 = -(G0 - G2), g1 = -(G1 - G2);
+        const double H00 = h00, H01 = t1 * h01, H02 = t2 * h02, H11 = t1 * t1 * h11, H12 = t1 * t2 * h12, H22 = t2 * t2 * h22;
+        const double r00 = H00 - 2.0 * H02 + H22, r01 = H01 - H02 - H12 + H22, r11 = H11 - 2.0 * H12 + H22;
+        const double det = r00 * r11 - r01 * r01;
+        if (!(det > 0.0)) break;
+        const double idet = 1.0 / det;
+        const double e0 = -(r11 * g0 - r01 * g1) * idet, e1 = -(r00 * g1 - r01 * g0) * idet, e2 = -(e0 + e1);
+        double alpha = 1.0;
+        if (e0 < 0.0) alpha = fmin(alpha, 0.9 * y0 / -e0);
+        if (e1 < 0.0) alpha = fmin(alpha, 0.9 * y1 / -e1);
+        if (e2 < 0.0) alpha = fmin(alpha, 0.9 * y2 / -e2);
+        if (!(alpha > 0.0)) break;
+        y0 = fma(alpha, e0, y0);
+        y1 = fma(alpha, e1, y1);
+        if (!(y0 > 0.0 && y1 > 0.0 && y0 + y1 < 1.0)) break;
     }
-};
+    ws.y0 = y0; ws.y1 = y1;
+    return false;
+}
 
-struct Search3Params {
-    N3Dev D;
-    const uint8_t* prefix;
-    const uint32_t* off;
-    uint32_t item_begin;
-    uint32_t n_items;            // pass 1: number of items from item_begin; pass 2: listed items
-    double* item_min;            // [n_items] (pass 1, indexed from item_begin)
-    unsigned long long* ctr;     // [0] ticket [1] solved [2] nfev [3] emitted [4] nan [5] leaves
-    const uint32_t* list;        // pass 2 (NULL: item = ticket)
-    const double* prior;         // pass 2
-    const uint64_t* rank_base;   // pass 2 over sub-items: (parent item << 32) | (sub-item << 12); NULL: item << 32
-    double near_thr;
-    theta_cand* emit;
-    uint8_t* emit_paths;
-    unsigned long long emit_cap;
-    int enumerate_only;          // emit every leaf's path, no solve
-    int screen;                  // pass 1: skip the exact solve of leaves that n3_screen proves irrelevant
-    int verify;                  // THETA_VERIFY_APPROX=1: solve every leaf and count leaves whose bound exceeds the exact NLL
-};
+__host__ __device__ inline size_t walk_smem_fixed(int m) { return (size_t)((m + 1) & ~1) * 24 + sizeof(double2) * THETA_LOGTAB_SIZE + 256 * sizeof(float); }
+__host__ __device__ inline size_t walk_smem_per_thread(int m, int NR) { return (size_t)NR * 8 + (size_t)((m + 3) / 4) * 4 + kUndo * 4; }
 
-// The per-candidate solver (hybrj restatement + fallback) is ~200 KB of machine code, far more than the
-// instruction caches hold, so warps that run it at unrelated phases each stream it from L2 ("no instruction"
-// was the top stall).  The leaf loop is therefore block-synchronous: every thread advances its own DFS to its
-// next leaf (cheap, divergent), the block meets at a barrier, and all warps enter the solver together and
-// move through it roughly in step, sharing the fetched instructions.
-template <int MAXM, bool EMIT, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) n3_search_kernel(const Search3Params p) {
+__global__ void n3_walk_kernel(const WalkParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
     __shared__ N3Dev D;
-    __shared__ double2 s_LT[THETA_LOGTAB_SIZE];
-    if (threadIdx.x == 0) D = p.D;
-    if (p.screen == 2) for (int i = threadIdx.x; i < THETA_LOGTAB_SIZE; i += BLOCK) s_LT[i] = p.D.logtab[i];
+    const int tid = threadIdx.x, B = p.block;
+    const int m = p.D.kc.m, NR = p.D.kc.NR, mp = (m + 1) & ~1, PW = (m + 3) / 4;
+    uint64_t* s_allow = reinterpret_cast<uint64_t*>(smem);
+    double* s_r = reinterpret_cast<double*>(s_allow + mp);
+    double* s_rN = s_r + mp;
+    double2* s_LT = reinterpret_cast<double2*>(s_rN + mp);
+    float* s_ratio = reinterpret_cast<float*>(s_LT + THETA_LOGTAB_SIZE);
+    double* s_R = reinterpret_cast<double*>(s_ratio + 256);
+    uint32_t* s_path = reinterpret_cast<uint32_t*>(s_R + (size_t)NR * B);
+    uint32_t* s_undo = s_path + (size_t)PW * B;
+    if (tid == 0) D = p.D;
+    for (int i = tid; i < m; i += B) { s_allow[i] = p.D.allow[i]; s_r[i] = p.D.r[i]; s_rN[i] = p.D.rN[i]; }
+    for (int i = tid; i < THETA_LOGTAB_SIZE; i += B) s_LT[i] = p.D.logtab[i];
+    for (int i = tid; i < 256; i += B) s_ratio[i] = (float)ratio_val((uint8_t)i);
     __syncthreads();
     const double2* LT = p.screen == 2 ? s_LT : nullptr;
-    Dfs<MAXM> dfs;
-    Groups3 G;
-    unsigned long long solved = 0, nfev = 0, nan_nll = 0, leaves = 0, n_exact = 0, n_viol = 0;
-    const int m = D.kc.m;
-    // pass 1 screens every leaf with a rigorous lower bound (n3_screen) against T = the best exact NLL this
-    // thread has seen so far -- all of it at lower ranks: a thread takes items in increasing order and walks
-    // each in enumeration order -- so a skipped leaf is neither a strict prefix minimum nor in the tie window
+    Walk w;
+    w.pw = s_path + tid; w.undo = s_undo + tid; w.R = s_R + tid;
+    w.allow = s_allow; w.r = s_r; w.rN = s_rN; w.ratio = s_ratio; w.D = &D; w.B = B; w.m = m;
+    const double T = __longlong_as_double((long long)p.ctr[kCtrT]);  // fixed for the launch: the solve kernel runs between waves
+    const double thr = fmin(p.fixed_thr, T + p.margin);
     Screen3 ws{1.0 / 3.0, 1.0 / 3.0};
-    double T = INFINITY;
-    const double screen_margin = 3.0 * THETA_TIE_MARGIN;
-    bool has_item = false, exhausted = false, fresh = true;
-    uint32_t ticket = 0, item = 0, seq = 0;
-    double prior = 0.0, tmin = INFINITY;
+    unsigned long long leaves = 0, it1 = 0, it2 = 0, it3 = 0;
+    if (p.scout_stride) {
+        // scout wave: which leaf of an item looks best?  Every scout_stride-th leaf (an unbiased sample over the item)
+        // gets the full Newton bound; the exact NLL of the chosen leaves gives the first threshold T.
+        for (;;) {
+            const uint32_t ticket = (uint32_t)atomicAdd(&p.ctr[kCtrTicket], 1ULL);
+            if (ticket >= p.n_work) break;
+            const uint32_t item = p.list ? p.list[ticket] : p.item_begin + ticket;
+            w.load_prefix(p.prefix + p.off[item], (int)(p.off[item + 1] - p.off[item]));
+            uint32_t seq = 0;
+            bool fresh = true;
+            double best_lb = INFINITY;
+            p.q_meta[2 * (size_t)ticket] = item;
+            p.q_meta[2 * (size_t)ticket + 1] = 0xffffffffu;  // "no leaf"
+            p.q_lb[ticket] = -INFINITY;
+            const uint32_t phase = ticket % p.scout_stride;
+            while (w.next_leaf(fresh)) {
+                fresh = false;
+                if (seq % p.scout_stride == phase) {
+                    double lb;
+                    int iters;
+                    walk_screen(w, D.kc, ws, INFINITY, lb, LT, iters);
+                    if (lb < best_lb || best_lb == INFINITY) {
+                        best_lb = lb;
+                        p.q_meta[2 * (size_t)ticket + 1] = seq;
+                        uint8_t* dst = p.q_path + (size_t)ticket * m;
+                        for (int i = 0; i < m; ++i) dst[i] = (uint8_t)w.row(i);
+                    }
+                }
+                ++seq;
+            }
+            atomicMax(&p.ctr[kCtrQueue], (unsigned long long)ticket + 1ULL);
+        }
+        return;
+    }
+    // Warp-synchronous leaf loop: every lane first advances its own DFS to its next leaf (divergent, cheap), the warp
+    // reconverges, and all lanes that have a leaf screen it together (the expensive, regular part).
+    bool have_item = false, done = false, fresh = true;
+    uint32_t item = 0, seq = 0;
     for (;;) {
         bool have_leaf = false;
-        while (!have_leaf && !exhausted) {
-            if (!has_item) {
-                ticket = (uint32_t)atomicAdd(&p.ctr[0], 1ULL);
-                if (ticket >= p.n_items) { exhausted = true; break; }
-                item = EMIT ? (p.list ? p.list[ticket] : ticket) : p.item_begin + ticket;
-                prior = EMIT ? p.prior[ticket] : 0.0;
-                dfs.load_prefix(D, p.prefix + p.off[item], (int)(p.off[item + 1] - p.off[item]));
-                tmin = INFINITY;
+        while (!have_leaf && !done) {
+            if (!have_item) {
+                const uint32_t ticket = (uint32_t)atomicAdd(&p.ctr[kCtrTicket], 1ULL);
+                if (ticket >= p.n_work) { done = true; break; }
+                item = p.list ? p.list[ticket] : p.item_begin + ticket;
+                w.load_prefix(p.prefix + p.off[item], (int)(p.off[item + 1] - p.off[item]));
                 seq = 0;
                 fresh = true;
-                has_item = true;
-                if (!EMIT && p.screen) {
-                    // Tighten T with the minima of items that other threads have already finished: every item with
-                    // a smaller ticket is at lower ranks, so its minimum (the exact NLL of one of its leaves, written
-                    // once when the item completes; NaN until then) is a valid T.  Look well behind the tickets
-                    // that are still in flight, 16 samples spread over everything older.
-                    const long long lag = 2LL * (long long)gridDim.x * BLOCK;
-                    const long long j0 = (long long)ticket - lag;
-                    if (j0 >= 0) {
-                        const long long stride = j0 / 16 + 1;
-                        for (long long j = j0; j >= 0; j -= stride) {
-                            const double v = __ldcg(p.item_min + j);
-                            if (v == v) T = fmin(T, v);
-                        }
-                    }
-                }
+                have_item = true;
             }
-            if (dfs.next_leaf(D, fresh)) {
-                fresh = false;
-                have_leaf = true;
-            } else {
-                if (!EMIT) p.item_min[ticket] = tmin;
-                has_item = false;
-            }
+            if (w.next_leaf(fresh)) { fresh = false; have_leaf = true; }
+            else have_item = false;
         }
-        if (!__syncthreads_or(have_leaf ? 1 : 0)) break;
+        __syncwarp();
+        if (__all_sync(0xffffffffu, !have_leaf)) break;
         if (have_leaf) {
             ++leaves;
-            bool emit = false;
-            Solve3Out o;
-            o.status = THETA_ST_NONE_NAN;
-            if (!p.enumerate_only) {
-                dfs.groups(D, G);
-                // (deferring the leaves that survive the screen so that the solver runs with full warps was
-                // measured slower: surviving leaves cluster in time, and the longer divergent screening loops
-                // between solver rounds cost more than they save)
-                bool skip = false;
-                double lb = -INFINITY;
-                if (p.screen) {
-                    // pass 2 emits a leaf only if NLL <= near_thr or NLL < min(prior, item minimum so far): a leaf whose
-                    // lower bound exceeds both thresholds is neither emitted nor changes the item minimum
-                    const double thr = EMIT ? fmax(p.near_thr, fmin(prior, tmin)) : T + screen_margin;
-                    skip = n3_screen(G, dfs.S1, dfs.S2, D.kc, ws, thr, lb, LT) && !p.verify;
-                }
-                if (!skip) {
-                    const ref3::Ctx rc{m, D.r, D.rN, dfs.path, 1, D.ra, D.rb, D.kc.tau, D.kc.tau * D.kc.A, dfs.S1, dfs.S2};
-                    n3_solve_auto(G, dfs.S1, dfs.S2, D.kc, rc, EMIT ? THETA_N3_MODE_REF : THETA_N3_MODE_AUTO, o);
-                    ++n_exact;
-                    if (o.status < THETA_ST_NONE_SIGN) {
-                        ++solved;
-                        nfev += o.nfev;
-                        if (o.nll != o.nll) {
-                            ++nan_nll;
-                            emit = true;  // Misc.isClose(nan, x) is True (Q6)
-                        } else {
-                            if (EMIT) emit = (o.nll <= p.near_thr) || (o.nll < prior && o.nll < tmin);
-                            tmin = fmin(tmin, o.nll);
-                            T = fmin(T, o.nll);
-                            if (p.verify && lb > o.nll) ++n_viol;
-                        }
-                    }
-                }
-            } else {
-                emit = true;
+            bool keep = true;
+            double lb = -INFINITY;
+            if (!p.enumerate_only && p.screen) {
+                int iters;
+                keep = !walk_screen(w, D.kc, ws, thr, lb, LT, iters) || p.verify;
+                it1 += iters <= 1; it2 += iters == 2; it3 += iters >= 3;
             }
-            if (EMIT && emit) {
-                const unsigned long long slot = atomicAdd(&p.ctr[3], 1ULL);
-                if (slot < p.emit_cap) {
-                    theta_cand c;
-                    c.rank = (p.rank_base ? p.rank_base[ticket] : ((uint64_t)item << 32)) + seq;
-                    c.nll = o.nll;
-                    c.mu[0] = o.mu[0]; c.mu[1] = o.mu[1]; c.mu[2] = o.mu[2];
-                    c.status = o.status;
-                    c.flags = (int32_t)slot;
-                    p.emit[slot] = c;
-                    uint8_t* dst = p.emit_paths + slot * (size_t)m;
-                    for (int i = 0; i < m; ++i) dst[i] = dfs.path[i];
+            if (keep) {
+                const unsigned long long slot = atomicAdd(&p.ctr[kCtrQueue], 1ULL);
+                if (slot < p.q_cap) {
+                    p.q_meta[2 * slot] = item;
+                    p.q_meta[2 * slot + 1] = seq;
+                    p.q_lb[slot] = lb;
+                    uint8_t* dst = p.q_path + slot * (size_t)m;
+                    for (int i = 0; i < m; ++i) dst[i] = (uint8_t)w.row(i);
                 }
             }
             ++seq;
         }
     }
-    if (solved) atomicAdd(&p.ctr[1], solved);
-    if (nfev) atomicAdd(&p.ctr[2], nfev);
-    if (nan_nll) atomicAdd(&p.ctr[4], nan_nll);
-    if (leaves) atomicAdd(&p.ctr[5], leaves);
-    if (n_exact) atomicAdd(&p.ctr[6], n_exact);
-    if (n_viol) atomicAdd(&p.ctr[7], n_viol);
+    if (leaves && p.count_leaves) atomicAdd(&p.ctr[kCtrLeaves], leaves);
+    if (it1) atomicAdd(&p.ctr[kCtrIt0], it1);
+    if (it2) atomicAdd(&p.ctr[kCtrIt1], it2);
+    if (it3) atomicAdd(&p.ctr[kCtrIt2], it3);
+}
+
+// ======================================================================= device: solve the survivors (kernel B)
+struct SolveParams {
+    N3Dev D;
+    unsigned long long* ctr;
+    const uint32_t* q_meta;
+    const double* q_lb;
+    const uint8_t* q_path;
+    theta_cand* q_res;           // [cap]: rank = (item << 32) | leaf ordinal, flags = queue slot
+    unsigned long long q_cap;
+    uint32_t* ref_list;          // [cap] slots left to the warp-cooperative reference-order solver (n3_solve_ref_kernel)
+    int mode;                    // THETA_N3_MODE_*
+    int enumerate_only;
+    int skip_ref;                // scout wave: rank-deficient candidates are not needed for the threshold -- leave them out
+};
+
+__global__ void __launch_bounds__(kBlock3) n3_solve_queue_kernel(const SolveParams p) {
+    __shared__ N3Dev D;
+    if (threadIdx.x == 0) D = p.D;
+    __syncthreads();
+    const unsigned long long count = min(p.ctr[kCtrQueue], p.q_cap), done = p.ctr[kCtrDone];
+    const int m = D.kc.m;
+    unsigned long long solved = 0, nfev = 0, nnan = 0, viol = 0;
+    double best = INFINITY;
+    for (unsigned long long slot = done + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; slot < count;
+         slot += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint8_t* pth = p.q_path + slot * (size_t)m;
+        theta_cand c;
+        c.rank = ((uint64_t)p.q_meta[2 * slot] << 32) | p.q_meta[2 * slot + 1];
+        c.flags = (int32_t)slot;
+        c.nll = 0.0; c.mu[0] = c.mu[1] = c.mu[2] = 0.0; c.status = THETA_ST_NONE_NAN;
+        if (!p.enumerate_only && p.q_meta[2 * slot + 1] != 0xffffffffu) {
+            double R[kMaxRows3];
+            uint16_t cnt[kMaxRows3];
+            for (int g = 0; g < D.kc.NR; ++g) { R[g] = 0.0; cnt[g] = 0; }
+            double S1 = 0.0, S2 = 0.0;
+            for (int j = 0; j < m; ++j) {
+                const int g = pth[j];
+                R[g] += D.r[j];
+                cnt[g] += 1;
+                S1 += D.rN[j] * (double)D.ra[g];
+                S2 += D.rN[j] * (double)D.rb[g];
+            }
+            Groups3 G;
+            int n = 0;
+            for (int g = 0; g < D.kc.NR; ++g)
+                if (cnt[g]) { G.R[n] = R[g]; G.a[n] = D.ra[g]; G.b[n] = D.rb[g]; ++n; }
+            G.G = n;
+            const bool ref = p.mode == THETA_N3_MODE_REF ||
+                             (p.mode == THETA_N3_MODE_AUTO && (D.kc.any_zero_rN || ref3::rank_deficient(G.G, G.R, G.a, G.b, S1, S2)));
+            if (ref) {  // one warp per candidate does these (~30x less latency than one thread)
+                if (!p.skip_ref) {
+                    const unsigned long long k = atomicAdd(&p.ctr[kCtrRefQ], 1ULL);
+                    p.ref_list[k] = (uint32_t)slot;
+                }
+                c.status = -1;
+            } else {
+                Solve3Out o;
+                n3_solve(G, S1, S2, D.kc, o);
+                c.nll = o.nll; c.mu[0] = o.mu[0]; c.mu[1] = o.mu[1]; c.mu[2] = o.mu[2]; c.status = o.status;
+                if (o.status < THETA_ST_NONE_SIGN) {
+                    ++solved;
+                    nfev += o.nfev;
+                    if (o.nll != o.nll) ++nnan;
+                    else {
+                        best = fmin(best, o.nll);
+                        if (p.q_lb[slot] > o.nll) ++viol;
+                    }
+                }
+            }
+        }
+        p.q_res[slot] = c;
+    }
+    // NLL >= 0, so the bit pattern orders like the value; +inf (nothing solved) never lowers T
+    if (best < INFINITY && best >= 0.0) atomicMin(&p.ctr[kCtrT], (unsigned long long)__double_as_longlong(best));
+    if (solved) atomicAdd(&p.ctr[kCtrSolved], solved);
+    if (nfev) atomicAdd(&p.ctr[kCtrNfev], nfev);
+    if (nnan) atomicAdd(&p.ctr[kCtrNan], nnan);
+    if (viol) atomicAdd(&p.ctr[kCtrViol], viol);
+}
+
+// Reference-order solves, one warp per candidate (n3_ref.cuh::WarpExec).  Work list: slots [RefDone, RefQ) of ref_list.
+// Results go either to the search queue (q_res + counters + T) or to the arrays of theta_solve_rows_n3.
+struct RefParams {
+    N3Dev D;
+    unsigned long long* ctr;
+    const uint32_t* ref_list;
+    const uint8_t* paths;        // [slot][m]
+    theta_cand* q_res;           // search mode (or NULL)
+    const double* q_lb;
+    double* mu;                  // rows mode: [slot][3], [slot][3], [slot], [slot], [slot][m] or NULL
+    double* muhat;
+    double* nll;
+    int32_t* status;
+    double* vals;
+    int warps;                   // per CTA
+};
+
+__global__ void n3_solve_ref_kernel(const RefParams p) {
+    extern __shared__ __align__(16) double ref_scratch[];
+    __shared__ N3Dev D;
+    if (threadIdx.x == 0) D = p.D;
+    __syncthreads();
+    const int m = D.kc.m, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned long long count = p.ctr[kCtrRefQ], done = p.ctr[kCtrRefDone];
+    ref3::WarpExec ex{ref_scratch + (size_t)wid * 9 * m, m};
+    const ref3::StatusCodes sc{THETA_ST_OK, THETA_ST_FALLBACK_X0, THETA_ST_FALLBACK_MOVED, THETA_ST_NONE_RANGE};
+    for (unsigned long long idx = done + (unsigned long long)blockIdx.x * p.warps + wid; idx < count;
+         idx += (unsigned long long)gridDim.x * p.warps) {
+        const uint32_t slot = p.ref_list[idx];
+        const uint8_t* pth = p.paths + (size_t)slot * m;
+        double S1 = 0.0, S2 = 0.0;  // exact integers: any summation order gives the same double
+        for (int j = lane; j < m; j += 32) {
+            const int g = pth[j];
+            S1 += D.rN[j] * (double)D.ra[g];
+            S2 += D.rN[j] * (double)D.rb[g];
+        }
+        for (int o = 16; o; o >>= 1) {
+            S1 += __shfl_xor_sync(0xffffffffu, S1, o);
+            S2 += __shfl_xor_sync(0xffffffffu, S2, o);
+        }
+        const ref3::Ctx rc{m, D.r, D.rN, pth, 1, D.ra, D.rb, D.kc.tau, D.kc.tau * D.kc.A, S1, S2};
+        ref3::Out o;
+        ref3::solve(rc, sc, ex, o, p.vals ? p.vals + (size_t)slot * m : nullptr);
+        if (lane == 0) {
+            atomicAdd(&p.ctr[kCtrRef], 1ULL);
+            if (p.q_res) {
+                theta_cand& c = p.q_res[slot];
+                c.nll = o.nll; c.mu[0] = o.mu[0]; c.mu[1] = o.mu[1]; c.mu[2] = o.mu[2]; c.status = o.status;
+                if (o.status < THETA_ST_NONE_SIGN) {
+                    atomicAdd(&p.ctr[kCtrSolved], 1ULL);
+                    atomicAdd(&p.ctr[kCtrNfev], (unsigned long long)o.nfev);
+                    if (o.nll != o.nll) atomicAdd(&p.ctr[kCtrNan], 1ULL);
+                    else {
+                        if (o.nll >= 0.0 && o.nll < INFINITY) atomicMin(&p.ctr[kCtrT], (unsigned long long)__double_as_longlong(o.nll));
+                        if (p.q_lb[slot] > o.nll) atomicAdd(&p.ctr[kCtrViol], 1ULL);
+                    }
+                }
+            } else {
+                for (int j = 0; j < 3; ++j) {
+                    p.mu[(size_t)slot * 3 + j] = o.mu[j];
+                    if (p.muhat) p.muhat[(size_t)slot * 3 + j] = o.muhat[j];
+                }
+                p.nll[slot] = o.nll;
+                p.status[slot] = o.status;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// between waves: everything queued so far has been solved; the next wave starts a fresh ticket count
+__global__ void n3_advance_kernel(unsigned long long* ctr, unsigned long long cap) {
+    ctr[kCtrDone] = min(ctr[kCtrQueue], cap);
+    ctr[kCtrRefDone] = ctr[kCtrRefQ];
+    ctr[kCtrTicket] = 0;
 }
 
 // Optimizer.solve on explicit row-index strings
 __global__ void __launch_bounds__(kBlock3) n3_solve_rows_kernel(const N3Dev D0, const uint8_t* paths, int64_t count,
                                                                 double* mu, double* muhat, double* nll, int32_t* status,
-                                                                double* vals, int mode) {
+                                                                double* vals, int mode, unsigned long long* ctr,
+                                                                uint32_t* ref_list) {
     __shared__ N3Dev D;
     if (threadIdx.x == 0) D = D0;
     __syncthreads();
@@ -369,8 +646,13 @@ __global__ void __launch_bounds__(kBlock3) n3_solve_rows_kernel(const N3Dev D0, 
     Solve3Out o;
     if (bad) { o.status = THETA_ST_NONE_NAN; o.nll = 0.0; o.mu[0] = o.mu[1] = o.mu[2] = 0.0; o.muhat[0] = o.muhat[1] = o.muhat[2] = 0.0; }
     else {
-        const ref3::Ctx rc{m, D.r, D.rN, pth, 1, D.ra, D.rb, D.kc.tau, D.kc.tau * D.kc.A, S1, S2};
-        n3_solve_auto(G, S1, S2, D.kc, rc, mode, o);
+        const bool ref = mode == THETA_N3_MODE_REF ||
+                         (mode == THETA_N3_MODE_AUTO && (D.kc.any_zero_rN || ref3::rank_deficient(G.G, G.R, G.a, G.b, S1, S2)));
+        if (ref) {  // left to n3_solve_ref_kernel, which writes mu / muhat / nll / status / vals of this candidate
+            ref_list[atomicAdd(&ctr[kCtrRefQ], 1ULL)] = (uint32_t)i;
+            return;
+        }
+        n3_solve(G, S1, S2, D.kc, o);
     }
     for (int j = 0; j < 3; ++j) {
         mu[i * 3 + j] = o.mu[j];
@@ -437,7 +719,8 @@ int theta_n3_plan_init(theta_plan* pl) {
     THETA_CUDA(theta::dmalloc(&s->d_allow, sizeof(uint64_t) * m));
     THETA_CUDA(theta::dmalloc(&s->d_r, sizeof(double) * m));
     THETA_CUDA(theta::dmalloc(&s->d_rN, sizeof(double) * m));
-    THETA_CUDA(theta::dmalloc(&s->d_ctr, sizeof(unsigned long long) * 8));
+    THETA_CUDA(theta::dmalloc(&s->d_ctr, sizeof(unsigned long long) * kCtrWords));
+    THETA_CUDA(theta::dmalloc(&s->d_ctr_rows, sizeof(unsigned long long) * kCtrWords));
     THETA_CUDA(cudaMemcpy(s->d_allow, s->allow.data(), sizeof(uint64_t) * m, cudaMemcpyHostToDevice));
     THETA_CUDA(cudaMemcpy(s->d_r, rd.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
     THETA_CUDA(cudaMemcpy(s->d_rN, rnd.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
@@ -474,7 +757,8 @@ void theta_n3_plan_free(theta_plan* pl) {
     theta_n3_state* s = pl->n3;
     if (!s) return;
     theta::dfree(s->d_allow); theta::dfree(s->d_r); theta::dfree(s->d_rN); theta::dfree(s->d_prefix); theta::dfree(s->d_off);
-    theta::dfree(s->d_item_min); theta::dfree(s->d_ctr);
+    theta::dfree(s->d_ctr); theta::dfree(s->d_ctr_rows); theta::dfree(s->d_ref_list); theta::dfree(s->d_q_meta); theta::dfree(s->d_q_lb); theta::dfree(s->d_q_res); theta::dfree(s->d_q_path);
+    theta::dfree(s->d_list);
     delete s;
     pl->n3 = nullptr;
 }
@@ -565,21 +849,6 @@ struct Expander {
             rec(depth + 1, mn2, mx2, (sw && (s->eqmask >> w2 & 1)) ? 1 : 0);
         }
     }
-    // the sub-trees of one item (given by its prefix), each with at most `cap` leaves, in enumeration order
-    void run_from_prefix(const uint8_t* pre, int len) {
-        path.assign(pl->m, 0);
-        uint8_t mn = 0, mx = 255;
-        int sw = 0;
-        for (int i = 0; i < len; ++i) {
-            path[i] = pre[i];
-            if (i == 0) sw = (s->eqmask >> pre[0] & 1) ? 1 : 0;
-            else {
-                theta::step_bounds(s->ra[pre[i - 1]], s->rb[pre[i - 1]], s->ra[pre[i]], s->rb[pre[i]], mn, mx);
-                sw = (sw && (s->eqmask >> pre[i] & 1)) ? 1 : 0;
-            }
-        }
-        rec(len - 1, mn, mx, sw);
-    }
     void run() {
         build_est();
         path.assign(pl->m, 0);
@@ -601,23 +870,35 @@ extern "C" int theta_n3_prepare(theta_plan* pl, int64_t leaf_cap, int64_t max_it
     int rc = check_n3(pl);
     if (rc) return rc;
     theta_n3_state* s = pl->n3;
-    if (leaf_cap < 1) leaf_cap = 256;
+    const bool auto_cap = leaf_cap < 1;
+    if (auto_cap) leaf_cap = 256;
     if (max_items < 1) max_items = 1 << 22;
-    Expander ex{pl, s};
-    ex.max_items = (size_t)max_items;
-    ex.cap = (double)leaf_cap;
     // If the space is too large for max_items sub-trees of leaf_cap candidates, the list is cut after
-    // max_items items: the search then covers a lexicographic prefix of the space (a rank budget).
-    ex.overflow = false;
-    ex.run();
-    s->truncated = ex.overflow;
+    // max_items items: the search then covers a lexicographic prefix of the space (a rank budget) and
+    // theta_n3_truncated() reports it.
+    for (int round = 0; round < 2; ++round) {
+        Expander ex{pl, s};
+        ex.max_items = (size_t)max_items;
+        ex.cap = (double)leaf_cap;
+        ex.overflow = false;
+        ex.run();
+        s->truncated = ex.overflow;
+        if (!auto_cap || round == 1 || ex.overflow) break;
+        // small spaces: one thread per item needs tens of thousands of items to fill the machine
+        const size_t ni0 = s->off.size() - 1;
+        double tot = 0.0;
+        for (double w : s->weight) tot += w;
+        if (ni0 >= 32768 || tot <= (double)ni0) break;
+        leaf_cap = std::max<int64_t>(1, (int64_t)(tot / 32768.0));
+        if (leaf_cap >= 256) break;
+    }
     const size_t ni = s->off.size() - 1;
-    theta::dfree(s->d_prefix); theta::dfree(s->d_off); theta::dfree(s->d_item_min);
-    s->d_prefix = nullptr; s->d_off = nullptr; s->d_item_min = nullptr;
+    theta::dfree(s->d_prefix); theta::dfree(s->d_off);
+    s->d_prefix = nullptr; s->d_off = nullptr;
+    s->list_begin = s->list_end = 0; s->q_count = 0;
     if (ni) {
         THETA_CUDA(theta::dmalloc(&s->d_prefix, std::max<size_t>(1, s->prefix.size())));
         THETA_CUDA(theta::dmalloc(&s->d_off, sizeof(uint32_t) * (ni + 1)));
-        THETA_CUDA(theta::dmalloc(&s->d_item_min, sizeof(double) * ni));
         THETA_CUDA(cudaMemcpy(s->d_prefix, s->prefix.data(), s->prefix.size(), cudaMemcpyHostToDevice));
         THETA_CUDA(cudaMemcpy(s->d_off, s->off.data(), sizeof(uint32_t) * (ni + 1), cudaMemcpyHostToDevice));
     }
@@ -640,270 +921,295 @@ extern "C" int theta_n3_item_weights(const theta_plan* pl, double* weights) {
 }
 
 // ----------------------------------------------------------------------- launches
-// THETA_N3_BLOCK (tuning knob): threads per CTA of the n=3 search kernel (64, 256 or 512; default: by item count)
-static int g_n3_block = -1;
+static int n3_env_screen() {
+    const char* es = getenv("THETA_N3_SCREEN");  // 0: off, 1: fp32 logarithms, 2: fp64 table logarithms
+    return es ? atoi(es) : kScreenDefault;
+}
+static int n3_env_verify() {
+    const char* ev = getenv("THETA_VERIFY_APPROX");
+    return (ev && ev[0] == '1') ? 1 : 0;
+}
 
-template <bool EMIT, int BLOCK, int MINB>
-static int launch_n3_b(const theta_plan* pl, const Search3Params& sp, cudaStream_t st) {
+// survivor queue: meta | lower bounds | results | paths, grown on demand, kept until the plan is freed
+static int ensure_queue(theta_n3_state* s, int m, size_t cap) {
+    if (cap <= s->q_cap) return THETA_OK;
+    theta::dfree(s->d_q_meta); theta::dfree(s->d_q_lb); theta::dfree(s->d_q_res); theta::dfree(s->d_q_path); theta::dfree(s->d_ref_list);
+    s->d_q_meta = nullptr; s->d_q_lb = nullptr; s->d_q_res = nullptr; s->d_q_path = nullptr; s->d_ref_list = nullptr;
+    s->q_cap = 0;
+    THETA_CUDA(theta::dmalloc(&s->d_ref_list, sizeof(uint32_t) * cap));
+    THETA_CUDA(theta::dmalloc(&s->d_q_meta, sizeof(uint32_t) * 2 * cap));
+    THETA_CUDA(theta::dmalloc(&s->d_q_lb, sizeof(double) * cap));
+    THETA_CUDA(theta::dmalloc(&s->d_q_res, sizeof(theta_cand) * cap));
+    THETA_CUDA(theta::dmalloc(&s->d_q_path, cap * (size_t)m));
+    s->q_cap = cap;
+    return THETA_OK;
+}
+
+// CTA size of the walk kernel: the one that keeps the most threads resident given its shared-memory state
+static int walk_config(const theta_plan* pl, int* block, int* ctas_per_sm, size_t* smem) {
+    const theta_n3_state* s = pl->n3;
+    static bool attr_set[64] = {false};
+    if (pl->device >= 0 && pl->device < 64 && !attr_set[pl->device]) {
+        THETA_CUDA(cudaFuncSetAttribute(n3_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        attr_set[pl->device] = true;
+    }
+    int best_b = 0, best_n = 0;
+    size_t best_s = 0;
+    const int cands[4] = {256, 128, 64, 32};
+    for (int ci = 0; ci < 4; ++ci) {
+        const int b = cands[ci];
+        const size_t sm = walk_smem_fixed(pl->m) + (size_t)b * walk_smem_per_thread(pl->m, s->NR);
+        if (sm > 227 * 1024 - 2048) continue;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, n3_walk_kernel, b, sm) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (nb * b > best_n * best_b) { best_b = b; best_n = nb; best_s = sm; }
+    }
+    if (!best_b) { set_error("n=3 walk kernel: m=%d does not fit shared memory", pl->m); return THETA_ERR_UNSUPPORTED; }
+    *block = best_b; *ctas_per_sm = best_n; *smem = best_s;
+    return THETA_OK;
+}
+
+struct WalkArgs {
+    const uint32_t* d_list = nullptr;
+    uint32_t item_begin = 0, n_work = 0;
+    const uint8_t* d_prefix = nullptr;
+    const uint32_t* d_off = nullptr;
+    double margin = 0.0, fixed_thr = INFINITY;
+    uint32_t scout_stride = 0;
+    int enumerate_only = 0, screen = 0, verify = 0, count_leaves = 1;
+};
+
+static int run_walk(const theta_plan* pl, const WalkArgs& a, cudaStream_t st) {
+    theta_n3_state* s = pl->n3;
+    if (a.n_work == 0) return THETA_OK;
+    int block, per_sm;
+    size_t smem;
+    int rc = walk_config(pl, &block, &per_sm, &smem);
+    if (rc) return rc;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-    const int m = pl->m;
-    const int64_t threads_wanted = (int64_t)sp.n_items;
-    int grid = (int)std::min<int64_t>((threads_wanted + BLOCK - 1) / BLOCK, (int64_t)sms * MINB);
-    if (grid < 1) grid = 1;
-    if (m <= 64) n3_search_kernel<64, EMIT, BLOCK, MINB><<<grid, BLOCK, 0, st>>>(sp);
-    else if (m <= 256) n3_search_kernel<256, EMIT, BLOCK, MINB><<<grid, BLOCK, 0, st>>>(sp);
-    else n3_search_kernel<1024, EMIT, BLOCK, MINB><<<grid, BLOCK, 0, st>>>(sp);
+    WalkParams p{};
+    fill_dev(pl, &p.D);
+    p.prefix = a.d_prefix ? a.d_prefix : s->d_prefix;
+    p.off = a.d_off ? a.d_off : s->d_off;
+    p.list = a.d_list; p.item_begin = a.item_begin; p.n_work = a.n_work;
+    p.ctr = s->d_ctr; p.margin = a.margin; p.fixed_thr = a.fixed_thr;
+    p.q_meta = s->d_q_meta; p.q_lb = s->d_q_lb; p.q_path = s->d_q_path; p.q_cap = s->q_cap;
+    p.enumerate_only = a.enumerate_only; p.screen = a.screen; p.verify = a.verify; p.block = block;
+    p.scout_stride = a.scout_stride; p.count_leaves = a.count_leaves;
+    // small spaces: fewer threads per CTA so that the items spread over the SMs
+    while (block > 32 && (int64_t)a.n_work < (int64_t)sms * block) {
+        block /= 2;
+        smem = walk_smem_fixed(pl->m) + (size_t)block * walk_smem_per_thread(pl->m, s->NR);
+        p.block = block;
+    }
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)a.n_work + block - 1) / block, (int64_t)sms * per_sm * 2));
+    n3_walk_kernel<<<grid, block, smem, st>>>(p);
     THETA_CUDA(cudaGetLastError());
     return THETA_OK;
 }
 
-template <bool EMIT>
-static int launch_n3(const theta_plan* pl, const Search3Params& sp, cudaStream_t st) {
-    if (g_n3_block < 0) {
-        const char* e = getenv("THETA_N3_BLOCK");
-        g_n3_block = e ? atoi(e) : 0;
+// one warp per candidate, 9 m doubles of shared memory per warp
+static int launch_ref(const theta_plan* pl, RefParams& rp, int max_ctas, cudaStream_t st) {
+    const size_t per_warp = (size_t)9 * pl->m * sizeof(double);
+    int warps = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
+    if (warps < 1) { set_error("n=3 reference-order solver: m=%d does not fit shared memory", pl->m); return THETA_ERR_UNSUPPORTED; }
+    const size_t smem = per_warp * warps;
+    static size_t attr_smem[64] = {0};
+    if (pl->device >= 0 && pl->device < 64 && smem > attr_smem[pl->device] && smem > 48 * 1024) {
+        THETA_CUDA(cudaFuncSetAttribute(n3_solve_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem[pl->device] = smem;
     }
-    int block = g_n3_block;
-    if (block == 0) {  // the largest CTA that still gives every SM at least half a CTA of items
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-        const int64_t per_sm = (int64_t)sp.n_items / sms;
-        block = per_sm >= 256 ? 512 : per_sm >= 128 ? 256 : 64;
-    }
-    switch (block) {
-        case 64: return launch_n3_b<EMIT, 64, 8>(pl, sp, st);
-        case 512: return launch_n3_b<EMIT, 512, 1>(pl, sp, st);
-        default: return launch_n3_b<EMIT, 256, 2>(pl, sp, st);
-    }
+    rp.warps = warps;
+    n3_solve_ref_kernel<<<max_ctas, warps * 32, smem, st>>>(rp);
+    THETA_CUDA(cudaGetLastError());
+    return THETA_OK;
 }
 
-extern "C" int theta_search_n3_pass1(theta_plan* pl, uint64_t item_begin, uint64_t item_end, double* local_min, void* stream) {
+static int run_solve(const theta_plan* pl, int mode, int enumerate_only, int skip_ref, cudaStream_t st) {
+    theta_n3_state* s = pl->n3;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    SolveParams p{};
+    fill_dev(pl, &p.D);
+    p.ctr = s->d_ctr; p.q_meta = s->d_q_meta; p.q_lb = s->d_q_lb; p.q_path = s->d_q_path; p.q_res = s->d_q_res;
+    p.q_cap = s->q_cap; p.mode = mode; p.enumerate_only = enumerate_only; p.ref_list = s->d_ref_list; p.skip_ref = skip_ref;
+    n3_solve_queue_kernel<<<sms * 4, kBlock3, 0, st>>>(p);
+    THETA_CUDA(cudaGetLastError());
+    if (!enumerate_only && !skip_ref) {
+        RefParams rp{};
+        fill_dev(pl, &rp.D);
+        rp.ctr = s->d_ctr; rp.ref_list = s->d_ref_list; rp.paths = s->d_q_path; rp.q_res = s->d_q_res; rp.q_lb = s->d_q_lb;
+        int rc = launch_ref(pl, rp, sms * 2, st);
+        if (rc) return rc;
+    }
+    n3_advance_kernel<<<1, 1, 0, st>>>(s->d_ctr, (unsigned long long)s->q_cap);
+    THETA_CUDA(cudaGetLastError());
+    return THETA_OK;
+}
+
+// Pass 1 of the n=3 search over items [item_begin, item_end): the exact minimum NLL of the shard, and -- kept in
+// the plan -- every candidate whose screening bound is within `window` (+ margin) of the best NLL known when it was
+// screened, solved.  Two waves: a scout over ~8192 items spread over the shard (every 8th leaf gets the full Newton
+// bound, the most promising leaf of each item is solved exactly: the first T), then everything against that T.
+// Order does not matter (the fold needs only the candidates within the tie cluster of the global minimum,
+// DESIGN.md "rank-free record set"), so T is one number shared by every thread, wave and GPU (t_seed).
+extern "C" int theta_search_n3_min(theta_plan* pl, uint64_t item_begin, uint64_t item_end, double t_seed, double window,
+                                   double* local_min, void* stream) {
     int rc = check_n3(pl);
     if (rc) return rc;
     if (!local_min) { set_error("null argument"); return THETA_ERR_INVALID; }
     theta_n3_state* s = pl->n3;
-    const uint64_t ni = s->off.size() ? s->off.size() - 1 : 0;
     if (s->off.empty()) { set_error("theta_n3_prepare has not been called"); return THETA_ERR_INVALID; }
+    const uint64_t ni = s->off.size() - 1;
     if (item_end > ni) item_end = ni;
     if (item_begin > item_end) { set_error("bad item range"); return THETA_ERR_INVALID; }
+    if (!(window > 0.0)) window = 4.0 * THETA_TIE_MARGIN;
     cudaStream_t st = (cudaStream_t)stream;
-    s->p1_begin = item_begin; s->p1_end = item_end;
+    s->p1_begin = item_begin; s->p1_end = item_end; s->q_count = 0; s->window = window;
     pl->stats = theta_search_stats{};
     pl->stats.min_nll = INFINITY;
     *local_min = INFINITY;
     const uint64_t n = item_end - item_begin;
-    s->h_item_min.assign(n, INFINITY);
     if (n == 0) return THETA_OK;
-    THETA_CUDA(cudaMemsetAsync(s->d_ctr, 0, sizeof(unsigned long long) * 8, st));
-    THETA_CUDA(cudaMemsetAsync(s->d_item_min, 0xff, sizeof(double) * n, st));  // NaN = "item not finished yet"
-    Search3Params sp{};
-    fill_dev(pl, &sp.D);
-    sp.prefix = s->d_prefix; sp.off = s->d_off; sp.item_begin = (uint32_t)item_begin; sp.n_items = (uint32_t)n;
-    sp.item_min = s->d_item_min; sp.ctr = s->d_ctr;
-    {
-        const char* ev = getenv("THETA_VERIFY_APPROX");
-        sp.verify = (ev && ev[0] == '1') ? 1 : 0;
-        const char* es = getenv("THETA_N3_SCREEN");  // 0: off, 1: fp32 logarithms, 2: fp64 table logarithms
-        sp.screen = es ? atoi(es) : kScreenDefault;
+    double wtot = 0.0;
+    for (uint64_t i = item_begin; i < item_end; ++i) wtot += s->weight[i];
+    const int screen = n3_env_screen(), verify = n3_env_verify();
+    const bool waves = screen && !verify && wtot > 65536.0;
+    // wave lists
+    uint32_t n0 = 0;
+    if (waves) {
+        const uint64_t stride = std::max<uint64_t>(1, n / 8192);
+        if (s->list_begin != item_begin || s->list_end != item_end || !s->d_list) {
+            std::vector<uint32_t> l0;
+            for (uint64_t i = item_begin; i < item_end; i += stride) l0.push_back((uint32_t)i);
+            theta::dfree(s->d_list); s->d_list = nullptr;
+            THETA_CUDA(theta::dmalloc(&s->d_list, sizeof(uint32_t) * l0.size()));
+            THETA_CUDA(cudaMemcpyAsync(s->d_list, l0.data(), sizeof(uint32_t) * l0.size(), cudaMemcpyHostToDevice, st));
+            THETA_CUDA(cudaStreamSynchronize(st));
+            s->list_begin = item_begin; s->list_end = item_end; s->list_n0 = (uint32_t)l0.size();
+        }
+        n0 = s->list_n0;
     }
-    cudaEvent_t e0, e1;
-    THETA_CUDA(cudaEventCreate(&e0)); THETA_CUDA(cudaEventCreate(&e1));
-    THETA_CUDA(cudaEventRecord(e0, st));
-    rc = launch_n3<false>(pl, sp, st);
-    if (rc) return rc;
-    THETA_CUDA(cudaEventRecord(e1, st));
-    unsigned long long ctr[8];
-    THETA_CUDA(cudaMemcpyAsync(s->h_item_min.data(), s->d_item_min, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    THETA_CUDA(cudaMemcpyAsync(ctr, s->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, st));
-    THETA_CUDA(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&pl->stats.ms_pass1, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    double g = INFINITY;
-    for (double v : s->h_item_min) if (v < g) g = v;
-    pl->stats.n_candidates = ctr[5];
-    pl->stats.n_solved = ctr[1];  // of the leaves that were solved exactly (all of them with THETA_N3_SCREEN=0)
-    pl->stats.n_exact = ctr[6];
-    pl->stats.n_bound_violations = ctr[7];
+    size_t cap = (verify || !screen) ? (size_t)wtot + 1024 : (size_t)1 << 16;
+    if (!waves) cap = std::max(cap, (size_t)std::min(wtot, 65536.0) + 1024);
+    unsigned long long ctr[kCtrWords];
+    float ms = 0.f;
+    for (int attempt = 0;; ++attempt) {
+        rc = ensure_queue(s, pl->m, cap);
+        if (rc) return rc;
+        unsigned long long init[kCtrWords] = {0};
+        double seed = (t_seed == t_seed && t_seed >= 0.0) ? t_seed : INFINITY;
+        std::memcpy(&init[kCtrT], &seed, 8);
+        THETA_CUDA(cudaMemcpyAsync(s->d_ctr, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        cudaEvent_t e0, e1;
+        THETA_CUDA(cudaEventCreate(&e0)); THETA_CUDA(cudaEventCreate(&e1));
+        THETA_CUDA(cudaEventRecord(e0, st));
+        WalkArgs a;
+        a.margin = window + THETA_TIE_MARGIN; a.screen = screen; a.verify = verify;
+        const int mode = THETA_N3_MODE_AUTO;
+        if (waves) {  // scout wave: its exact solves give the threshold T of the full wave
+            a.d_list = s->d_list; a.n_work = n0; a.count_leaves = 0;
+            a.scout_stride = (uint32_t)std::max(4.0, wtot / (double)n / 8.0);  // ~8 sampled leaves per scout item
+            rc = run_walk(pl, a, st);
+            if (!rc) rc = run_solve(pl, mode, 0, 1, st);
+        }
+        a.d_list = nullptr; a.item_begin = (uint32_t)item_begin; a.n_work = (uint32_t)n; a.scout_stride = 0; a.count_leaves = 1;
+        if (!rc) rc = run_walk(pl, a, st);
+        if (!rc) rc = run_solve(pl, mode, 0, 0, st);
+        if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+        THETA_CUDA(cudaEventRecord(e1, st));
+        THETA_CUDA(cudaMemcpyAsync(ctr, s->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, st));
+        THETA_CUDA(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (ctr[kCtrQueue] <= cap) break;
+        if (attempt >= 6) { set_error("n=3 survivor queue overflow (%llu survivors)", ctr[kCtrQueue]); return THETA_ERR_OVERFLOW; }
+        cap = std::max<size_t>(2 * cap, (size_t)ctr[kCtrQueue] + 1024);  // a large tie cluster: retry with room for it
+    }
+    double g;
+    std::memcpy(&g, &ctr[kCtrT], 8);
+    s->q_count = ctr[kCtrQueue];
+    s->nan_nll = ctr[kCtrNan];
+    pl->stats.n_candidates = ctr[kCtrLeaves];
+    pl->stats.n_solved = ctr[kCtrSolved];
+    pl->stats.n_exact = ctr[kCtrQueue];
+    pl->stats.n_bound_violations = ctr[kCtrViol];
     pl->stats.n_stripes = n;
-    pl->stats.newton_iters = ctr[1] ? (double)ctr[2] / (double)ctr[1] : 0.0;
+    pl->stats.n_rescanned = ctr[kCtrRef];  // survivors that took the reference-order solver
+    pl->stats.newton_iters = ctr[kCtrSolved] ? (double)ctr[kCtrNfev] / (double)ctr[kCtrSolved] : 0.0;
     pl->stats.min_nll = g;
-    s->nan_nll = ctr[4];
+    pl->stats.ms_pass1 = ms;
+    s->it_hist[0] = ctr[kCtrIt0]; s->it_hist[1] = ctr[kCtrIt1]; s->it_hist[2] = ctr[kCtrIt2];
+    if (getenv("THETA_DEBUG"))
+        fprintf(stderr, "[theta n3] leaves %llu survivors %llu (ref-order %llu) screen iterations 1/2/3: %llu/%llu/%llu  %.2f ms\n",
+                ctr[kCtrLeaves], ctr[kCtrQueue], ctr[kCtrRef], ctr[kCtrIt0], ctr[kCtrIt1], ctr[kCtrIt2], ms);
     *local_min = g;
     return THETA_OK;
 }
 
-static int run_emit(theta_plan* pl, const std::vector<uint32_t>& list, const std::vector<double>& prior, double near_thr,
-                    int enumerate_only, std::vector<theta_cand>* recs, std::vector<uint8_t>* paths, cudaStream_t st) {
-    theta_n3_state* s = pl->n3;
-    const int m = pl->m;
-    recs->clear(); paths->clear();
-    if (list.empty()) return THETA_OK;
-    // Pass 2 walks only a handful of items, one thread each: cut every listed item into sub-trees of at most
-    // kSubCap leaves (same expander, started from the item's prefix) so that the walk is spread over many threads.
-    // Records keep the enumeration order through rank = (parent item << 32) | (sub-item << 12) | leaf-in-sub-item.
-    constexpr double kSubCap = 16.0;
-    std::vector<uint8_t> sub_prefix;
-    std::vector<uint32_t> sub_off(1, 0);
-    std::vector<double> sub_weight, sub_prior;
-    std::vector<uint64_t> sub_rank;
-    const bool split = !enumerate_only && !s->est.empty();
-    if (split) {
-        Expander ex{pl, s};
-        ex.cap = kSubCap;
-        ex.max_items = (size_t)1 << 30;
-        ex.o_prefix = &sub_prefix; ex.o_off = &sub_off; ex.o_weight = &sub_weight;
-        for (size_t k = 0; k < list.size(); ++k) {
-            const uint32_t it = list[k];
-            const uint8_t* pre = s->prefix.data() + s->off[it];
-            const int len = (int)(s->off[it + 1] - s->off[it]);
-            const size_t first = sub_off.size() - 1;
-            if (s->weight[it] <= kSubCap * 1048576.0) ex.run_from_prefix(pre, len);
-            size_t n_sub = sub_off.size() - 1 - first;
-            if (n_sub == 0 || n_sub >= ((size_t)1 << 20)) {  // not split (huge item, or nothing survived): the item itself
-                sub_prefix.resize(sub_off[first]); sub_off.resize(first + 1); sub_weight.resize(first);
-                sub_prefix.insert(sub_prefix.end(), pre, pre + len);
-                sub_off.push_back((uint32_t)sub_prefix.size());
-                sub_weight.push_back(s->weight[it]);
-                n_sub = 1;
-            }
-            for (size_t j = 0; j < n_sub; ++j) {
-                sub_rank.push_back(((uint64_t)it << 32) | ((uint64_t)j << 12));
-                sub_prior.push_back(prior[k]);
-            }
-        }
-    }
-    const size_t n_work = split ? sub_rank.size() : list.size();
-    uint32_t* d_list = nullptr; double* d_prior = nullptr; theta_cand* d_emit = nullptr; uint8_t* d_paths = nullptr;
-    uint8_t* d_sub_prefix = nullptr; uint32_t* d_sub_off = nullptr; uint64_t* d_sub_rank = nullptr;
-    int rc = THETA_OK;
-    cudaError_t e = cudaSuccess;
-    if (split) {
-        e = theta::dmalloc(&d_sub_prefix, std::max<size_t>(1, sub_prefix.size()));
-        if (e == cudaSuccess) e = theta::dmalloc(&d_sub_off, sizeof(uint32_t) * sub_off.size());
-        if (e == cudaSuccess) e = theta::dmalloc(&d_sub_rank, sizeof(uint64_t) * n_work);
-        if (e == cudaSuccess) e = theta::dmalloc(&d_prior, sizeof(double) * n_work);
-        if (e == cudaSuccess) e = cudaMemcpy(d_sub_prefix, sub_prefix.data(), sub_prefix.size(), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d_sub_off, sub_off.data(), sizeof(uint32_t) * sub_off.size(), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d_sub_rank, sub_rank.data(), sizeof(uint64_t) * n_work, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d_prior, sub_prior.data(), sizeof(double) * n_work, cudaMemcpyHostToDevice);
-    } else {
-        e = theta::dmalloc(&d_list, sizeof(uint32_t) * list.size());
-        if (e == cudaSuccess) e = theta::dmalloc(&d_prior, sizeof(double) * list.size());
-        if (e == cudaSuccess) e = cudaMemcpy(d_list, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d_prior, prior.data(), sizeof(double) * list.size(), cudaMemcpyHostToDevice);
-    }
-    if (e != cudaSuccess) rc = cuda_fail(e, "n3 emit setup", __FILE__, __LINE__);
-    size_t cap = 1 << 14;
-    for (int attempt = 0; rc == THETA_OK && attempt < 8; ++attempt) {
-        theta::dfree(d_emit); theta::dfree(d_paths); d_emit = nullptr; d_paths = nullptr;
-        e = theta::dmalloc(&d_emit, sizeof(theta_cand) * cap);
-        if (e == cudaSuccess) e = theta::dmalloc(&d_paths, cap * (size_t)m);
-        if (e == cudaSuccess) e = cudaMemsetAsync(s->d_ctr, 0, sizeof(unsigned long long) * 8, st);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "n3 emit buffers", __FILE__, __LINE__); break; }
-        Search3Params sp{};
-        fill_dev(pl, &sp.D);
-        sp.prefix = split ? d_sub_prefix : s->d_prefix; sp.off = split ? d_sub_off : s->d_off;
-        sp.n_items = (uint32_t)n_work; sp.ctr = s->d_ctr;
-        sp.list = split ? nullptr : d_list; sp.rank_base = split ? d_sub_rank : nullptr;
-        sp.prior = d_prior; sp.near_thr = near_thr; sp.emit = d_emit; sp.emit_paths = d_paths;
-        sp.emit_cap = cap; sp.enumerate_only = enumerate_only;
-        {
-            const char* ev = getenv("THETA_VERIFY_APPROX");
-            sp.verify = (ev && ev[0] == '1') ? 1 : 0;
-            const char* es = getenv("THETA_N3_SCREEN");
-            sp.screen = enumerate_only ? 0 : (es ? atoi(es) : kScreenDefault);
-        }
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        cudaEventRecord(e0, st);
-        rc = launch_n3<true>(pl, sp, st);
-        cudaEventRecord(e1, st);
-        unsigned long long ctr[8] = {0};
-        if (rc == THETA_OK) {
-            e = cudaMemcpyAsync(ctr, s->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) rc = cuda_fail(e, "n3 pass2", __FILE__, __LINE__);
-        }
-        cudaEventElapsedTime(&pl->stats.ms_pass2, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        if (rc) break;
-        if (ctr[3] > cap) { cap = (size_t)ctr[3] + 1024; continue; }
-        recs->resize(ctr[3]);
-        paths->resize((size_t)ctr[3] * m);
-        if (ctr[3]) {
-            e = cudaMemcpy(recs->data(), d_emit, sizeof(theta_cand) * ctr[3], cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess) e = cudaMemcpy(paths->data(), d_paths, (size_t)ctr[3] * m, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) rc = cuda_fail(e, "n3 pass2 D2H", __FILE__, __LINE__);
-        }
-        break;
-    }
-    theta::dfree(d_list); theta::dfree(d_prior); theta::dfree(d_emit); theta::dfree(d_paths);
-    theta::dfree(d_sub_prefix); theta::dfree(d_sub_off); theta::dfree(d_sub_rank);
-    if (rc) return rc;
-    // sort by enumeration order, carrying the paths along
-    std::vector<uint32_t> idx(recs->size());
-    for (size_t i = 0; i < idx.size(); ++i) idx[i] = (uint32_t)i;
-    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return (*recs)[a].rank < (*recs)[b].rank; });
-    std::vector<theta_cand> r2(recs->size());
-    std::vector<uint8_t> p2(paths->size());
-    for (size_t i = 0; i < idx.size(); ++i) {
-        r2[i] = (*recs)[idx[i]];
-        std::memcpy(p2.data() + i * (size_t)m, paths->data() + (size_t)(*recs)[idx[i]].flags * m, m);
-        r2[i].flags = (int32_t)i;
-    }
-    recs->swap(r2);
-    paths->swap(p2);
-    return THETA_OK;
-}
+static int solve_rows_dev(theta_plan* pl, const uint8_t* d_p, int64_t count, double* d_mu, double* d_mh, double* d_nll,
+                          int32_t* d_st, double* d_vals, int mode, cudaStream_t st);
 
-extern "C" int theta_search_n3_pass2(theta_plan* pl, double global_min, double prior_min, theta_cand* out_host, uint64_t cap,
-                                     uint64_t* n_out, uint8_t* paths_host, void* stream) {
+// Every solved candidate of the shard with NLL <= global_min + window, or a NaN likelihood (Misc.isClose(nan, x) is
+// True: Q6), in enumeration order, re-solved by the reference-order solver (mode 1) so that mu and NLL carry the
+// reference's own roundings.  `window` must not exceed the one given to theta_search_n3_min.
+extern "C" int theta_search_n3_window(theta_plan* pl, double global_min, double window, theta_cand* out_host, uint64_t cap,
+                                      uint64_t* n_out, uint8_t* paths_host, void* stream) {
     int rc = check_n3(pl);
     if (rc) return rc;
     if (!n_out) { set_error("null argument"); return THETA_ERR_INVALID; }
     *n_out = 0;
     theta_n3_state* s = pl->n3;
-    const double near_thr = global_min + 2.5 * THETA_TIE_MARGIN;
-    std::vector<uint32_t> list;
-    std::vector<double> prior;
-    double P = prior_min;
-    for (uint64_t i = 0; i < s->h_item_min.size(); ++i) {
-        const double v = s->h_item_min[i];
-        const bool rec = v < P, near = v <= near_thr;
-        if (rec || near || s->nan_nll) {
-            list.push_back((uint32_t)(s->p1_begin + i));
-            prior.push_back(rec ? P : -INFINITY);
-        }
-        if (v < P) P = v;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(window > 0.0)) window = s->window;
+    if (window > s->window) { set_error("window %g exceeds the searched one (%g)", window, s->window); return THETA_ERR_INVALID; }
+    const size_t m = (size_t)pl->m;
+    const size_t cnt = (size_t)std::min<uint64_t>(s->q_count, s->q_cap);
+    if (cnt == 0) return THETA_OK;
+    std::vector<theta_cand> all(cnt);
+    THETA_CUDA(cudaMemcpyAsync(all.data(), s->d_q_res, sizeof(theta_cand) * cnt, cudaMemcpyDeviceToHost, st));
+    THETA_CUDA(cudaStreamSynchronize(st));
+    const double thr = global_min + window;
+    std::vector<theta_cand> sel;
+    for (const theta_cand& c : all)
+        if (c.status >= 0 && c.status < THETA_ST_NONE_SIGN && (c.nll != c.nll || c.nll <= thr)) sel.push_back(c);
+    std::sort(sel.begin(), sel.end(), [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; });
+    sel.erase(std::unique(sel.begin(), sel.end(), [](const theta_cand& a, const theta_cand& b) { return a.rank == b.rank; }), sel.end());
+    *n_out = sel.size();
+    if (sel.empty()) return THETA_OK;
+    if (sel.size() > cap) { set_error("window holds %zu records, buffer holds %llu", sel.size(), (unsigned long long)cap); return THETA_ERR_OVERFLOW; }
+    // gather the paths on the device, re-solve in reference order
+    const int64_t k = (int64_t)sel.size();
+    uint8_t* d_p = nullptr; double *d_mu = nullptr, *d_mh = nullptr, *d_nll = nullptr; int32_t* d_st = nullptr;
+    cudaError_t e = theta::dmalloc(&d_p, (size_t)k * m);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_mu, sizeof(double) * 3 * k);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_mh, sizeof(double) * 3 * k);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_nll, sizeof(double) * k);
+    if (e == cudaSuccess) e = theta::dmalloc(&d_st, sizeof(int32_t) * k);
+    for (int64_t i = 0; e == cudaSuccess && i < k; ++i)
+        e = cudaMemcpyAsync(d_p + (size_t)i * m, s->d_q_path + (size_t)sel[i].flags * m, m, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "n3 window setup", __FILE__, __LINE__);
+    if (!rc) rc = solve_rows_dev(pl, d_p, k, d_mu, d_mh, d_nll, d_st, nullptr, THETA_N3_MODE_REF, st);
+    std::vector<double> mu(3 * k), nll(k);
+    std::vector<int32_t> stt(k);
+    std::vector<uint8_t> paths((size_t)k * m);
+    if (!rc) {
+        e = cudaMemcpyAsync(mu.data(), d_mu, sizeof(double) * 3 * k, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nll.data(), d_nll, sizeof(double) * k, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(stt.data(), d_st, sizeof(int32_t) * k, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(paths.data(), d_p, (size_t)k * m, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "n3 window D2H", __FILE__, __LINE__);
     }
-    pl->stats.n_rescanned = list.size();
-    std::vector<theta_cand> recs;
-    std::vector<uint8_t> paths;
-    rc = run_emit(pl, list, prior, near_thr, 0, &recs, &paths, (cudaStream_t)stream);
+    theta::dfree(d_p); theta::dfree(d_mu); theta::dfree(d_mh); theta::dfree(d_nll); theta::dfree(d_st);
     if (rc) return rc;
-    {   // the device emits a superset (every sub-item restarts its running minimum): keep exactly the NaN values,
-        // the strict prefix minima w.r.t. everything before this shard, and the near-minimum set
-        const size_t m = (size_t)pl->m;
-        size_t w = 0;
-        double run = prior_min;
-        for (size_t i = 0; i < recs.size(); ++i) {
-            const double v = recs[i].nll;
-            const bool keep = (v != v) || v < run || v <= near_thr;
-            if (v < run) run = v;
-            if (keep) {
-                if (w != i) { recs[w] = recs[i]; std::memmove(paths.data() + w * m, paths.data() + i * m, m); }
-                recs[w].flags = (int32_t)w;
-                ++w;
-            }
-        }
-        recs.resize(w);
-        paths.resize(w * m);
+    for (int64_t i = 0; i < k; ++i) {
+        sel[i].nll = nll[i]; sel[i].mu[0] = mu[3 * i]; sel[i].mu[1] = mu[3 * i + 1]; sel[i].mu[2] = mu[3 * i + 2];
+        sel[i].status = stt[i]; sel[i].flags = (int32_t)i;
     }
-    *n_out = recs.size();
-    if (recs.size() > cap) { set_error("pass2 produced %zu records, buffer holds %llu", recs.size(), (unsigned long long)cap); return THETA_ERR_OVERFLOW; }
-    if (out_host && !recs.empty()) std::memcpy(out_host, recs.data(), sizeof(theta_cand) * recs.size());
-    if (paths_host && !paths.empty()) std::memcpy(paths_host, paths.data(), paths.size());
+    if (out_host) std::memcpy(out_host, sel.data(), sizeof(theta_cand) * sel.size());
+    if (paths_host) std::memcpy(paths_host, paths.data(), paths.size());
     return THETA_OK;
 }
 
@@ -916,17 +1222,71 @@ extern "C" int theta_enumerate_n3(theta_plan* pl, uint64_t item_begin, uint64_t 
     if (s->off.empty()) { set_error("theta_n3_prepare has not been called"); return THETA_ERR_INVALID; }
     const uint64_t ni = s->off.size() - 1;
     if (item_end > ni) item_end = ni;
-    std::vector<uint32_t> list;
-    std::vector<double> prior;
-    for (uint64_t i = item_begin; i < item_end; ++i) { list.push_back((uint32_t)i); prior.push_back(-INFINITY); }
-    std::vector<theta_cand> recs;
-    std::vector<uint8_t> paths;
-    rc = run_emit(pl, list, prior, -INFINITY, 1, &recs, &paths, nullptr);
+    *n_out = 0;
+    if (item_begin >= item_end) return THETA_OK;
+    double wtot = 0.0;
+    for (uint64_t i = item_begin; i < item_end; ++i) wtot += s->weight[i];
+    const size_t m = (size_t)pl->m;
+    size_t qcap = (size_t)wtot + 1024;
+    rc = ensure_queue(s, pl->m, qcap);
     if (rc) return rc;
-    *n_out = recs.size();
-    if (recs.size() > cap) { set_error("enumeration produced %zu candidates, buffer holds %llu", recs.size(), (unsigned long long)cap); return THETA_ERR_OVERFLOW; }
-    if (paths_host && !paths.empty()) std::memcpy(paths_host, paths.data(), paths.size());
+    s->q_count = 0; s->list_begin = s->list_end = 0;
+    unsigned long long init[kCtrWords] = {0};
+    THETA_CUDA(cudaMemcpy(s->d_ctr, init, sizeof(init), cudaMemcpyHostToDevice));
+    WalkArgs a;
+    a.item_begin = (uint32_t)item_begin; a.n_work = (uint32_t)(item_end - item_begin); a.enumerate_only = 1;
+    rc = run_walk(pl, a, nullptr);
+    if (rc) return rc;
+    unsigned long long ctr[kCtrWords];
+    THETA_CUDA(cudaMemcpy(ctr, s->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost));
+    const size_t cnt = (size_t)ctr[kCtrQueue];
+    if (cnt > s->q_cap) { set_error("enumeration produced more candidates than the item weights allow"); return THETA_ERR_OVERFLOW; }
+    *n_out = cnt;
+    if (cnt > cap) { set_error("enumeration produced %zu candidates, buffer holds %llu", cnt, (unsigned long long)cap); return THETA_ERR_OVERFLOW; }
+    if (cnt == 0 || !paths_host) return THETA_OK;
+    std::vector<uint32_t> meta(2 * cnt);
+    std::vector<uint8_t> raw(cnt * m);
+    THETA_CUDA(cudaMemcpy(meta.data(), s->d_q_meta, sizeof(uint32_t) * 2 * cnt, cudaMemcpyDeviceToHost));
+    THETA_CUDA(cudaMemcpy(raw.data(), s->d_q_path, cnt * m, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> idx(cnt);
+    for (size_t i = 0; i < cnt; ++i) idx[i] = (uint32_t)i;
+    std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
+        return meta[2 * x] != meta[2 * y] ? meta[2 * x] < meta[2 * y] : meta[2 * x + 1] < meta[2 * y + 1];
+    });
+    for (size_t i = 0; i < cnt; ++i) std::memcpy(paths_host + i * m, raw.data() + (size_t)idx[i] * m, m);
     return THETA_OK;
+}
+
+static int solve_rows_dev(theta_plan* pl, const uint8_t* d_p, int64_t count, double* d_mu, double* d_mh, double* d_nll,
+                          int32_t* d_st, double* d_vals, int mode, cudaStream_t st) {
+    theta_n3_state* s = pl->n3;
+    N3Dev D;
+    fill_dev(pl, &D);
+    uint32_t* d_ref = nullptr;
+    THETA_CUDA(theta::dmalloc(&d_ref, sizeof(uint32_t) * (size_t)count));
+    cudaError_t e = cudaMemsetAsync(s->d_ctr_rows, 0, sizeof(unsigned long long) * kCtrWords, st);
+    int rc = THETA_OK;
+    if (e != cudaSuccess) rc = cuda_fail(e, "solve_rows counters", __FILE__, __LINE__);
+    if (!rc) {
+        const int grid = (int)((count + kBlock3 - 1) / kBlock3);
+        n3_solve_rows_kernel<<<grid, kBlock3, 0, st>>>(D, d_p, count, d_mu, d_mh, d_nll, d_st, d_vals, mode, s->d_ctr_rows, d_ref);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cuda_fail(e, "n3_solve_rows_kernel", __FILE__, __LINE__);
+    }
+    if (!rc && mode != THETA_N3_MODE_GROUPED) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+        RefParams rp{};
+        rp.D = D; rp.ctr = s->d_ctr_rows; rp.ref_list = d_ref; rp.paths = d_p;
+        rp.mu = d_mu; rp.muhat = d_mh; rp.nll = d_nll; rp.status = d_st; rp.vals = d_vals;
+        rc = launch_ref(pl, rp, (int)std::min<int64_t>(sms * 2, count), st);
+    }
+    if (!rc) {
+        e = cudaStreamSynchronize(st);  // d_ref is released below
+        if (e != cudaSuccess) rc = cuda_fail(e, "solve_rows", __FILE__, __LINE__);
+    }
+    theta::dfree(d_ref);
+    return rc;
 }
 
 extern "C" int theta_solve_rows_n3(theta_plan* pl, const uint8_t* paths_host, int64_t count, double* mu_host,
@@ -945,12 +1305,11 @@ extern "C" int theta_solve_rows_n3(theta_plan* pl, const uint8_t* paths_host, in
     if (e == cudaSuccess && vals_host) e = theta::dmalloc(&d_vals, sizeof(double) * (size_t)count * m);
     if (e == cudaSuccess) e = cudaMemcpy(d_p, paths_host, (size_t)count * m, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && vals_host) e = cudaMemset(d_vals, 0, sizeof(double) * (size_t)count * m);
-    if (e == cudaSuccess) {
-        N3Dev D;
-        fill_dev(pl, &D);
-        const int grid = (int)((count + kBlock3 - 1) / kBlock3);
-        n3_solve_rows_kernel<<<grid, kBlock3>>>(D, d_p, count, d_mu, d_mh, d_nll, d_st, d_vals, (int)mode);
-        e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "solve_rows_n3 setup", __FILE__, __LINE__);
+    if (!rc) rc = solve_rows_dev(pl, d_p, count, d_mu, d_mh, d_nll, d_st, d_vals, (int)mode, nullptr);
+    if (rc) {
+        theta::dfree(d_p); theta::dfree(d_mu); theta::dfree(d_mh); theta::dfree(d_nll); theta::dfree(d_st); theta::dfree(d_vals);
+        return rc;
     }
     if (e == cudaSuccess) e = cudaMemcpy(mu_host, d_mu, sizeof(double) * 3 * count, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && muhat_host) e = cudaMemcpy(muhat_host, d_mh, sizeof(double) * 3 * count, cudaMemcpyDeviceToHost);

@@ -309,7 +309,8 @@ THETA_HDN void n3_solve_auto(const Groups3& g, double S1, double S2, const N3Con
     }
     const ref3::StatusCodes sc{THETA_ST_OK, THETA_ST_FALLBACK_X0, THETA_ST_FALLBACK_MOVED, THETA_ST_NONE_RANGE};
     ref3::Out r;
-    ref3::solve(c, sc, r);
+    ref3::SerialExec ex;
+    ref3::solve(c, sc, ex, r);
     for (int j = 0; j < 3; ++j) { o.mu[j] = r.mu[j]; o.muhat[j] = r.muhat[j]; }
     o.nll = r.nll;
     o.status = r.status;

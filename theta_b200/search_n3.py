@@ -1,9 +1,9 @@
 """n = 3 host side: do_optimization* for two tumour populations (python/RunTHetA.py:124-220 with
 Enumerator._generate_next_C_3 and Optimizer._solve_n3plus), on the GPU through the C ABI.
 
-The search runs as for n=2: items (DFS sub-trees in enumeration order) are sharded contiguously
-over the ranks of a torch.distributed group, pass 1 reduces per item, one all-reduce(min) gives the
-global minimum, pass 2 emits the records the reference's fold can keep, the fold is replayed.
+Items (DFS sub-trees in enumeration order) are sharded contiguously by estimated weight over the ranks of a
+torch.distributed group; every shard finds its exact minimum NLL, one all-reduce(min) gives the global one, every
+shard returns its candidates inside the tie window, and the reference's fold is replayed over their union.
 """
 import sys
 
@@ -52,30 +52,62 @@ class SearchResultN3(object):
     pass
 
 
-def search_n3(plan, leaf_cap=256, stream=None):
-    """Sharded two-pass n=3 search.  Returns a SearchResultN3 with `best` = list of
-    (path or None for the bogus first matrix, mu[3], nll, status) in fold order."""
+def cluster_top(values, g):
+    """Top of the 1e-3-connected cluster of NLL values that contains the global minimum g: walk the sorted values
+    upwards from g and stop at the first gap that Misc.isClose would call "not close"."""
+    h = g
+    for v in sorted(float(x) for x in values if x == x):
+        if v < g:
+            continue
+        if abs(v - h) > _lib.TIE_MARGIN:
+            break
+        h = v
+    return h
+
+
+def search_n3(plan, leaf_cap=0, stream=None, window=0.0):
+    """Sharded n=3 search.  Returns a SearchResultN3 with `best` = list of
+    (path or None for the bogus first matrix, mu[3], nll, status) in fold order.
+
+    The fold of RunTHetA.py:198-206 is decided by the candidates inside the 1e-3-connected cluster of NLL values
+    around the global minimum g, in enumeration order (any reset outside the cluster is undone by the first cluster
+    member that follows).  So: every shard finds its exact minimum (theta_search_n3_min), one
+    all-reduce(min) gives g, every shard returns its candidates within `window` of g, and the fold is replayed over
+    their union -- after checking that the cluster really ends inside the window; if not, search again with a
+    wider one."""
     rank, world, dist = _dist_state()
     n_items = plan.prepare(leaf_cap)
+    if getattr(plan, "truncated", False) and not getattr(plan, "allow_truncated", False):
+        raise _lib.ThetaError("the n=3 candidate space exceeds %d work items: theta_n3_prepare would cover only a "
+                              "lexicographic prefix of it (pass an explicit item budget to search a prefix)" % n_items)
     w = plan.item_weights()
     b, e = shard_items(w, rank, world)
-    local_min = plan.pass1_n3(b, e, stream)
-    st = plan.stats()
     # the reference's first "candidate" is the all-[tau,0,0] matrix built from iter = [0]*m, bounds ignored
     # (RunTHetA.py:148,188, Enumerator.py:54,154-160 -- Q2); Optimizer.solve returns garbage mu and (usually) the
     # all-normal likelihood for it: row index 0 is (0, 0), and the reference-order solver reproduces both
     bmu, _, bnll, bst, _ = plan.solve_rows(np.zeros((1, plan.m), dtype=np.uint8), mode=1)
     has_bogus = int(bst[0]) < _lib.ST_NONE_SIGN
     null_nll = float(bnll[0]) if has_bogus else INF
-    g, prior = exchange_minima(local_min, dist, rank, world)
-    recs, paths = plan.pass2_n3(g, prior, stream)
-    st.update({k: v for k, v in plan.stats().items() if k in ("n_rescanned", "ms_pass2")})
-    allrecs, extras = gather_records(recs, dist, world, extra=[st["n_solved"], st["n_candidates"]])
-    allpaths = gather_paths(paths, dist, world)
-    n_solved = sum(e[0] for e in extras)
-    n_cand = sum(e[1] for e in extras)
-    # the stream the reference folds: the all-[tau,0,0] matrix first (RunTHetA.py:148,188 -- Q2), whose
-    # NLL is the all-normal likelihood, then the candidates in enumeration order
+    window = float(window) if window > 0 else 4.0 * _lib.TIE_MARGIN
+    while True:
+        local_min = plan.search_min_n3(b, e, INF, window, stream)
+        st = plan.stats()
+        g, _ = exchange_minima(local_min, dist, rank, world)
+        g_all = min(g, null_nll) if null_nll == null_nll else g
+        recs, paths = plan.window_n3(g_all, window, stream)
+        allrecs, extras = gather_records(recs, dist, world, extra=[st["n_solved"], st["n_candidates"]])
+        allpaths = gather_paths(paths, dist, world)
+        vals = list(allrecs["nll"]) + ([null_nll] if has_bogus else [])
+        fin = [v for v in vals if v == v]
+        if not fin:
+            break
+        g_ref = min(fin)  # the reference-order values of the records (the search minimum is the grouped value)
+        if cluster_top(fin, g_ref) + _lib.TIE_MARGIN < g_all + window - 1e-6:
+            break
+        window *= 8.0  # the tie cluster reaches the edge of the window: look further
+    n_solved = sum(x[0] for x in extras)
+    n_cand = sum(x[1] for x in extras)
+    # the stream the reference folds: the all-[tau,0,0] matrix first, then the candidates in enumeration order
     nb = 1 if has_bogus else 0
     keys = np.concatenate([[0] * nb, allrecs["rank"].astype(np.uint64) + np.uint64(1)]).astype(np.uint64)
     nlls = np.concatenate([[null_nll] * nb, allrecs["nll"]])
@@ -91,7 +123,8 @@ def search_n3(plan, leaf_cap=256, stream=None):
     res.records, res.paths = allrecs, allpaths
     res.count = n_cand + 1
     res.n_solved = n_solved + 1
-    res.min_nll = min(g, null_nll)
+    res.min_nll = g_all
+    res.window = window
     res.stats = st
     res.n_items = n_items
     return res

@@ -16,9 +16,9 @@ for (m, k, F, tb, cap, maxit) in [(150, 5, 12, False, c, 1 << 22) for c in CAPS]
     print("m", m, "items", ni, "truncated", plan.truncated, "est leaves %.3g" % w.sum(), "prepare %.2fs" % (t1 - t0), flush=True)
     for rep in range(2):
         t0 = time.perf_counter()
-        g = plan.pass1_n3(0, ni)
+        g = plan.search_min_n3(0, ni)
         t1 = time.perf_counter()
-        recs, paths = plan.pass2_n3(g)
+        recs, paths = plan.window_n3(g)
         t2 = time.perf_counter()
         st = plan.stats()
         print("  pass1 %.1f ms (kernel %.1f) pass2 %.1f ms (kernel %.1f) leaves %d solved %d cand/s %.3e nfev %.2f rescanned %d recs %d min %.6f"
