@@ -168,6 +168,8 @@ int theta_search_n2(theta_plan* plan, uint64_t rank_begin, uint64_t rank_end, th
 int theta_optimize_n2(const theta_problem* p, uint64_t rank_limit, int32_t* lower_out, int32_t* upper_out,
                       uint64_t cap_best, uint64_t* n_best, theta_cand* best, int8_t* cols, double* vals,
                       theta_search_stats* stats, uint64_t* n_candidates);
+/* Tumour columns [count][m] of given ranks (host-side unranking, no launch). */
+int theta_columns_of_ranks(const theta_plan* plan, const uint64_t* ranks, int64_t count, int8_t* cols);
 /* (mu, NLL, status, vals[m]) of given ranks -- Optimizer.solve's return for the winners (Optimizer.py:123-126). */
 int theta_eval_ranks_n2(theta_plan* plan, const uint64_t* ranks_host, int64_t count, theta_cand* out_host,
                         double* vals_host /* [count][m] or NULL */);
@@ -198,6 +200,7 @@ int theta_n3_rows(const theta_plan* plan, int32_t* a, int32_t* b, int32_t* n_row
  * candidates (count DP of TimeEstimate.count_number_matrices_3, TimeEstimate.py:113-142, per sub-tree).
  * leaf_cap <= 0: 256, or less for small spaces so that there are enough items to fill the GPU. */
 int theta_n3_prepare(theta_plan* plan, int64_t leaf_cap, int64_t max_items, uint64_t* n_items);
+int theta_n3_item_count(const theta_plan* plan, uint64_t* n_items);
 int theta_n3_item_weights(const theta_plan* plan, double* weights /* [n_items] estimated leaves */);
 /* 1 if theta_n3_prepare stopped at max_items: the items then cover only a lexicographic prefix of the space. */
 int theta_n3_truncated(const theta_plan* plan, int32_t* truncated);
@@ -227,6 +230,44 @@ int theta_enumerate_n3(theta_plan* plan, uint64_t item_begin, uint64_t item_end,
 int theta_solve_rows_n3(theta_plan* plan, const uint8_t* paths_host, int64_t count, double* mu_host /* [count][3] */,
                         double* muhat_host /* [count][3] or NULL */, double* nll_host, int32_t* status_host,
                         double* vals_host /* [count][m] or NULL */, int32_t mode);
+
+/* ---- the search across GPUs: replaces the multiprocessing farm of do_optimization (RunTHetA.py:96-171:
+ * start_processes / process_loop / returnQueue / find_mins).  Per GPU, in stream order: pass 1 on its shard, ONE
+ * ncclAllReduce(min) on a device double, pass 2 / window records, ncclAllGather of the few records, one host
+ * synchronisation; then the reference's fold on the host.  NCCL is bound at run time (dlopen libnccl.so.2). ---- */
+typedef struct theta_comm theta_comm; /* one rank's communicator + exchange buffers (current device) */
+/* One process per GPU (torchrun): rank 0 makes the id, it travels through the launcher's own transport. */
+int theta_nccl_unique_id(uint8_t* id128 /* [128] */);
+int theta_comm_create(int32_t rank, int32_t world, const uint8_t* id128 /* NULL iff world == 1 */, theta_comm** out);
+void theta_comm_destroy(theta_comm* comm);
+/* One sharded search step on this rank; every rank receives the union of the records, in enumeration order.
+ * n=2: records = what the fold replay needs (theta_filter_records).  n=3: every candidate within `window` of the
+ * global minimum (extra_min: NLL of the all-[tau,0,0] pseudo candidate, folded into the minimum), flags index
+ * paths_host; totals = {solved, candidates} summed over all shards. */
+int theta_search_n2_dist(theta_plan* plan, theta_comm* comm, uint64_t rank_begin, uint64_t rank_end, theta_cand* out_host,
+                         uint64_t cap, uint64_t* n_out, double* global_min, uint64_t* n_solved_total, void* stream);
+int theta_search_n3_dist(theta_plan* plan, theta_comm* comm, uint64_t item_begin, uint64_t item_end, double window,
+                         double extra_min, theta_cand* out_host, uint8_t* paths_host, uint64_t cap, uint64_t* n_out,
+                         double* global_min, uint64_t* totals, void* stream);
+/* ONE process, n_devices GPUs: do_optimization(max_processes) (RunTHetA.py:124-171) behind one blocking call
+ * (ncclCommInitAll + one persistent host thread and stream per GPU).  devices NULL: 0..n_devices-1.
+ *   budget  n=2: rank limit (0 = whole space); n=3: work-item budget (0 = whole space; a space that exceeds the item
+ *           limit is an error unless a budget is given)
+ *   rows    [cap_best][m]: n=2 tumour column / n=3 row indices (theta_n3_rows) of each solution, in the reference's
+ *           fold order; rank == UINT64_MAX marks the all-[tau,0,0] pseudo candidate of n=3 (Q2)
+ *   vals    [cap_best][m]: Optimizer.solve's third return value.   *n_best may exceed cap_best (THETA_ERR_OVERFLOW). */
+typedef struct theta_mgpu theta_mgpu;
+int theta_mgpu_create(const theta_problem* p, int32_t n_devices, const int32_t* devices, theta_mgpu** out);
+void theta_mgpu_destroy(theta_mgpu* h);
+int theta_mgpu_devices(const theta_mgpu* h);
+int theta_mgpu_optimize(theta_mgpu* h, uint64_t budget, int32_t* lower_out, int32_t* upper_out, uint64_t cap_best,
+                        uint64_t* n_best, theta_cand* best, uint8_t* rows, double* vals, theta_search_stats* stats,
+                        uint64_t* n_candidates);
+int theta_mgpu_last_ms(const theta_mgpu* h, float* ms /* [n_devices] device time of the last search */);
+/* One-shot: create + optimize + destroy. */
+int theta_optimize(const theta_problem* p, int32_t n_devices, const int32_t* devices, uint64_t budget, int32_t* lower_out,
+                   int32_t* upper_out, uint64_t cap_best, uint64_t* n_best, theta_cand* best, uint8_t* rows, double* vals,
+                   theta_search_stats* stats, uint64_t* n_candidates);
 
 /* ---- CalcAllC.L2 / L3 (CalcAllC.py:44-76): masked NLL of one weighted matrix at a given mu ---- */
 /* Cw is [m][n] row-major fp64 (already weighted by rN); valid_i = Cw[i][0] != 0 (L2 with mu==0: Cw[i][1] != 0).

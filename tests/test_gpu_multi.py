@@ -20,3 +20,15 @@ def test_two_gpu_search_equals_single_gpu():
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "DIST_CHECK OK %d" % world in out.stdout
+
+
+def test_single_process_driver_equals_single_gpu():
+    """theta_mgpu_optimize (one process, host thread + stream per GPU, ncclAllReduce(min)) == do_optimization_single, on
+    every device count the box offers -- including 1, so the driver path is exercised on a one-GPU box too."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mgpu_check.py")], capture_output=True, text=True,
+                         timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "MGPU_CHECK OK 1" in out.stdout
+    import torch
+    if torch.cuda.device_count() >= 2:
+        assert "MGPU_CHECK OK 2" in out.stdout

@@ -67,6 +67,7 @@ SYMBOLS = {
     "theta_plan_null_nll": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "theta_n3_rows": (C.c_int, [_VP, _VP, _VP, C.POINTER(C.c_int32)]),
     "theta_n3_prepare": (C.c_int, [_VP, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
+    "theta_n3_item_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "theta_n3_item_weights": (C.c_int, [_VP, _VP]),
     "theta_n3_truncated": (C.c_int, [_VP, C.POINTER(C.c_int32)]),
     "theta_search_n3_min": (C.c_int, [_VP, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.POINTER(C.c_double), _VP]),
@@ -90,6 +91,22 @@ SYMBOLS = {
     "theta_optimize_n2": (C.c_int, [C.POINTER(Problem), C.c_uint64, _VP, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP, _VP, _VP,
                                     C.POINTER(SearchStats), C.POINTER(C.c_uint64)]),
     "theta_eval_ranks_n2": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
+    "theta_columns_of_ranks": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
+    "theta_nccl_unique_id": (C.c_int, [_VP]),
+    "theta_comm_create": (C.c_int, [C.c_int32, C.c_int32, _VP, C.POINTER(_VP)]),
+    "theta_comm_destroy": (None, [_VP]),
+    "theta_search_n2_dist": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_uint64), _VP]),
+    "theta_search_n3_dist": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint64, C.c_double, C.c_double, _VP, _VP, C.c_uint64,
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_double), _VP, _VP]),
+    "theta_mgpu_create": (C.c_int, [C.POINTER(Problem), C.c_int32, _VP, C.POINTER(_VP)]),
+    "theta_mgpu_destroy": (None, [_VP]),
+    "theta_mgpu_devices": (C.c_int, [_VP]),
+    "theta_mgpu_optimize": (C.c_int, [_VP, C.c_uint64, _VP, _VP, C.c_uint64, C.POINTER(C.c_uint64), _VP, _VP, _VP,
+                                      C.POINTER(SearchStats), C.POINTER(C.c_uint64)]),
+    "theta_mgpu_last_ms": (C.c_int, [_VP, _VP]),
+    "theta_optimize": (C.c_int, [C.POINTER(Problem), C.c_int32, _VP, C.c_uint64, _VP, _VP, C.c_uint64, C.POINTER(C.c_uint64),
+                                 _VP, _VP, _VP, C.POINTER(SearchStats), C.POINTER(C.c_uint64)]),
     "theta_solve_tiles_n2_dev": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP, _VP]),
     "theta_solve_tiles_n2": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP]),
     "theta_nll_tiles_n2_dev": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, _VP, _VP]),
@@ -232,6 +249,13 @@ class Plan(object):
         check(load().theta_n3_truncated(self._h, C.byref(t)))
         self.truncated = bool(t.value)
         return self.n_items
+
+    def columns_of_ranks(self, ranks):
+        ranks = np.ascontiguousarray(np.asarray(ranks, dtype=np.uint64))
+        cols = np.zeros((len(ranks), self.m), dtype=np.int8)
+        if len(ranks):
+            check(load().theta_columns_of_ranks(self._h, ptr(ranks), len(ranks), ptr(cols)))
+        return cols
 
     def item_weights(self):
         w = np.zeros(self.n_items, dtype=np.float64)
@@ -430,6 +454,153 @@ def optimize_n2(r, rN, lower, upper, tau=2, max_normal=1.0, rank_limit=None, cap
         k = int(n.value)
         return (lo_out, up_out, best[:k], cols[:k], vals[:k], {f: getattr(st, f) for f, _ in SearchStats._fields_},
                 int(nc.value))
+
+
+def device_count():
+    return int(load().theta_device_count())
+
+
+class Comm(object):
+    """theta_comm: this rank's NCCL communicator + exchange buffers for the sharded search steps
+    (theta_search_n2_dist / theta_search_n3_dist).  Under torch.distributed the NCCL id made on rank 0 travels
+    through torch's own broadcast; world == 1 needs no id and no NCCL."""
+
+    def __init__(self, rank=0, world=1, nccl_id=None, device=None):
+        init(device)
+        self.rank, self.world = int(rank), int(world)
+        h = C.c_void_p()
+        idbuf = None
+        if self.world > 1:
+            idbuf = np.ascontiguousarray(np.frombuffer(bytes(nccl_id), dtype=np.uint8))
+            assert idbuf.size == 128
+        check(load().theta_comm_create(self.rank, self.world, ptr(idbuf) if idbuf is not None else None, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(128, dtype=np.uint8)
+        check(load().theta_nccl_unique_id(ptr(buf)))
+        return buf.tobytes()
+
+    @classmethod
+    def from_torch(cls, dist):
+        """Communicator over the ranks of an initialised torch.distributed NCCL group."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        return cls(rank, world, bytes(t.cpu().numpy().tobytes()), device=torch.cuda.current_device())
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            try:
+                _lib.theta_comm_destroy(h)
+            except Exception:
+                pass
+
+    __del__ = close
+
+    def search_n2(self, plan, rank_begin, rank_end, stream=None):
+        """One sharded n=2 step in a single C call: pass 1, all-reduce(min), pass 2, record all-gather.
+        Returns (records of all shards as the fold replay needs them, global_min, solved candidates of all shards)."""
+        cap = 1 << 10
+        while True:
+            buf = np.empty(cap, dtype=CAND_DTYPE)
+            n = C.c_uint64()
+            g = C.c_double()
+            ns = C.c_uint64()
+            rc = load().theta_search_n2_dist(plan.handle, self._h, int(rank_begin), int(rank_end), ptr(buf), cap, C.byref(n),
+                                             C.byref(g), C.byref(ns), stream)
+            if rc == ERR_OVERFLOW and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            check(rc)
+            return buf[:int(n.value)], float(g.value), int(ns.value)
+
+    def search_n3(self, plan, item_begin, item_end, window, extra_min=float("inf"), stream=None):
+        """One sharded n=3 step: returns (records, paths, global_min, (solved, candidates) over all shards)."""
+        cap = 1 << 10
+        while True:
+            buf = np.empty(cap, dtype=CAND_DTYPE)
+            paths = np.zeros((cap, plan.m), dtype=np.uint8)
+            n = C.c_uint64()
+            g = C.c_double()
+            tot = np.zeros(2, dtype=np.uint64)
+            rc = load().theta_search_n3_dist(plan.handle, self._h, int(item_begin), int(item_end), float(window),
+                                             float(extra_min), ptr(buf), ptr(paths), cap, C.byref(n), C.byref(g), ptr(tot),
+                                             stream)
+            if rc == ERR_OVERFLOW and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            check(rc)
+            k = int(n.value)
+            return buf[:k], paths[:k], float(g.value), (int(tot[0]), int(tot[1]))
+
+
+class MultiGpu(object):
+    """theta_mgpu: do_optimization on several GPUs from ONE process (one host thread + stream per GPU, NCCL
+    all-reduce(min) in between) -- what RunTHetA's max_processes / --NUM_PROCESSES maps to."""
+
+    def __init__(self, n, r, rN, lower, upper, tau=2, max_normal=1.0, n_devices=None, devices=None):
+        load()
+        self.n = int(n)
+        self.m = len(r)
+        self._r, self._rN = _int_array(r, np.int64), _int_array(rN, np.int64)
+        self._lo, self._up = _int_array(lower, np.int32), _int_array(upper, np.int32)
+        if devices is not None:
+            devs = np.ascontiguousarray(np.asarray(devices, dtype=np.int32))
+            n_devices = len(devs)
+        else:
+            devs = None
+            n_devices = int(n_devices or device_count())
+        prob = Problem(self.n, self.m, int(tau), 0, self._r.ctypes.data_as(C.POINTER(C.c_int64)),
+                       self._rN.ctypes.data_as(C.POINTER(C.c_int64)), self._lo.ctypes.data_as(C.POINTER(C.c_int32)),
+                       self._up.ctypes.data_as(C.POINTER(C.c_int32)), float(max_normal))
+        h = C.c_void_p()
+        check(load().theta_mgpu_create(C.byref(prob), n_devices, ptr(devs) if devs is not None else None, C.byref(h)))
+        self._h = h
+        self.n_devices = n_devices
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            try:
+                _lib.theta_mgpu_destroy(h)
+            except Exception:
+                pass
+
+    __del__ = close
+
+    def optimize(self, budget=0, cap_best=64):
+        """Returns (lower, upper, best records [fold order], rows [n_best, m] uint8, vals [n_best, m], stats, n_candidates)."""
+        m = self.m
+        lo_out = np.empty(m, dtype=np.int32)
+        up_out = np.empty(m, dtype=np.int32)
+        while True:
+            best = np.empty(cap_best, dtype=CAND_DTYPE)
+            rows = np.empty((cap_best, m), dtype=np.uint8)
+            vals = np.empty((cap_best, m), dtype=np.float64)
+            n = C.c_uint64()
+            nc = C.c_uint64()
+            st = SearchStats()
+            rc = load().theta_mgpu_optimize(self._h, int(budget or 0), ptr(lo_out), ptr(up_out), cap_best, C.byref(n),
+                                            ptr(best), ptr(rows), ptr(vals), C.byref(st), C.byref(nc))
+            if rc == ERR_OVERFLOW and n.value > cap_best:
+                cap_best = int(n.value) + 8
+                continue
+            check(rc)
+            k = int(n.value)
+            return (lo_out, up_out, best[:k], rows[:k], vals[:k], {f: getattr(st, f) for f, _ in SearchStats._fields_},
+                    int(nc.value))
+
+    def last_ms(self):
+        ms = np.zeros(self.n_devices, dtype=np.float32)
+        check(load().theta_mgpu_last_ms(self._h, ptr(ms)))
+        return ms
 
 
 STATUS_WORDS = 32          # uint64 words of the device status block (theta_n2.cu)

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtheta_b200.so")
-SOURCES = ["theta_rt.cu", "theta_n2.cu", "theta_tiles.cu", "theta_n3.cu"]
+SOURCES = ["theta_rt.cu", "theta_n2.cu", "theta_tiles.cu", "theta_n3.cu", "theta_mgpu.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-Wno-unknown-pragmas", "--expt-relaxed-constexpr",
               "-Xptxas", "-v", "-cudart", "static"] + os.environ.get("THETA_NVCC_EXTRA", "").split()

@@ -981,6 +981,17 @@ static void host_column_of_rank(const theta_plan* pl, uint64_t rank, int8_t* col
     }
 }
 
+// tumour columns [count][m] of given ranks (host-side unranking from the plan's count tables; no kernel launch)
+extern "C" int theta_columns_of_ranks(const theta_plan* pl, const uint64_t* ranks, int64_t count, int8_t* cols) {
+    if (!pl || (count > 0 && (!ranks || !cols))) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (pl->n != 2) { set_error("plan is not n=2"); return THETA_ERR_INVALID; }
+    for (int64_t i = 0; i < count; ++i) {
+        if (ranks[i] >= pl->count) { set_error("rank %llu out of range", (unsigned long long)ranks[i]); return THETA_ERR_INVALID; }
+        host_column_of_rank(pl, ranks[i], cols + i * (size_t)pl->m);
+    }
+    return THETA_OK;
+}
+
 // do_optimization_single (python/RunTHetA.py:173-220) for n=2 in ONE call: plan, both passes, the reference's
 // running-min fold (RunTHetA.py:198-206 with Misc.isClose, the first matrix evaluated twice -- Q1, NaN counts as
 // close -- Q6) over the emitted records, and for each survivor its tumour column and Optimizer.solve's `vals`.

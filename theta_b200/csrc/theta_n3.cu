@@ -906,6 +906,13 @@ extern "C" int theta_n3_prepare(theta_plan* pl, int64_t leaf_cap, int64_t max_it
     return THETA_OK;
 }
 
+extern "C" int theta_n3_item_count(const theta_plan* pl, uint64_t* n_items) {
+    int rc = check_n3(pl);
+    if (rc) return rc;
+    if (n_items) *n_items = pl->n3->off.empty() ? 0 : pl->n3->off.size() - 1;
+    return THETA_OK;
+}
+
 extern "C" int theta_n3_truncated(const theta_plan* pl, int32_t* truncated) {
     int rc = check_n3(pl);
     if (rc) return rc;

@@ -112,75 +112,44 @@ def pass1_allreduce(plan, begin, end, dist, world, stream=None):
 
 
 def search_shard(plan, begin, end, dist, world, stream=None):
-    """Both passes on this shard with the one all-reduce(min) in between.  Returns (records, global_min).
-
-    On a GPU nothing returns to the host in between: pass 1 and its min reduction are enqueued, the NCCL
-    all-reduce(min) runs on the device double right behind them (stream order), the device-side stripe scan and
-    pass 2 follow, and the host waits once for the records."""
+    """Both passes on this shard with the one all-reduce(min) in between (host values: single GPU, gloo, host models
+    of the tests).  Returns (records, global_min)."""
     if not hasattr(plan, "pass1_begin"):  # host model of the plan (tests/test_dist_gloo.py)
         g, _ = pass1_allreduce(plan, begin, end, dist, world, stream)
         return plan.pass2(g, INF, stream), g
     if dist is None:
         plan.pass1_begin(begin, end, None, stream)
         return plan.pass2_dev(None, INF, stream)
-    if dist.get_backend() != "nccl":
-        g, _ = pass1_allreduce(plan, begin, end, dist, world, stream)
-        return plan.pass2(g, INF, stream), g
-    import torch
-    cur = torch.cuda.current_stream()
-    if stream is not None and int(stream) != int(cur.cuda_stream):
-        raise ValueError("with NCCL the search must run on torch's current stream")
-    t = _bufs(dist, world, _GATHER_BYTES)["min"]
-    plan.pass1_begin(begin, end, t.data_ptr(), cur.cuda_stream)
-    dist.all_reduce(t, op=dist.ReduceOp.MIN)   # ordered behind the kernel; the current stream then waits for it
-    return plan.pass2_dev(t.data_ptr(), INF, cur.cuda_stream)
+    g, _ = pass1_allreduce(plan, begin, end, dist, world, stream)
+    return plan.pass2(g, INF, stream), g
 
 
-_XCAP = 1024  # raw records per shard carried by the stream-ordered exchange
+_COMM = {}
+
+
+def comm_for(dist):
+    """The process's theta_comm over the ranks of `dist` (NCCL backend), made once: the NCCL id of rank 0 travels
+    through torch's own broadcast, everything after that is C (theta_b200/csrc/theta_mgpu.cu)."""
+    key = (dist.get_rank(), dist.get_world_size())
+    c = _COMM.get(key)
+    if c is None:
+        c = _lib.Comm.from_torch(dist)
+        _COMM[key] = c
+    return c
 
 
 def search_sharded(plan, begin, end, dist, world, stream=None):
     """The whole sharded search of one step.  Returns (records, global_min, n_solved): the records of all shards
     sorted by rank (a superset of what the fold replay needs), identical on every rank.
 
-    Default: search_shard (pass 1 -> all-reduce(min) on the device double -> stripe scan + pass 2, one host wait)
-    followed by the fixed-size record all-gather (a second wait).  With THETA_ASYNC_EXCHANGE=1 everything is
-    enqueued in stream order and the host waits once: ... -> device-to-device copy of the status block and the
-    raw records into the exchange buffer -> all-gather -> one D2H copy."""
-    # The fully stream-ordered exchange below (one host wait per step) measured SLOWER than pass 2 + a separate
-    # record gather on 2 x B200 (1.39 vs 1.24 ms per step: the raw-record all-gather is 4x larger and the second
-    # wait is cheap), so it is opt-in (THETA_ASYNC_EXCHANGE=1) until it is tuned at 8 GPUs.
-    if (dist is None or not hasattr(plan, "pass2_enqueue") or dist.get_backend() != "nccl"
-            or os.environ.get("THETA_ASYNC_EXCHANGE") != "1"):
-        recs, g = search_shard(plan, begin, end, dist, world, stream)
-        allrecs, extras = gather_records(recs, dist, world, extra=[plan.stats()["n_solved"]])
-        return allrecs, g, sum(e[0] for e in extras)
-    import torch
-    cur = torch.cuda.current_stream()
-    if stream is not None and int(stream) != int(cur.cuda_stream):
-        raise ValueError("with NCCL the search must run on torch's current stream")
-    item = _lib.CAND_DTYPE.itemsize
-    head = 8 * _lib.STATUS_WORDS
-    nbytes = head + _XCAP * item
-    b = _bufs(dist, world, nbytes)
-    plan.pass1_begin(begin, end, b["min"].data_ptr(), cur.cuda_stream)
-    dist.all_reduce(b["min"], op=dist.ReduceOp.MIN)
-    plan.pass2_enqueue(b["min"].data_ptr(), b["send_d"].data_ptr(), _XCAP, INF, cur.cuda_stream)
-    dist.all_gather_into_tensor(b["recv_d"], b["send_d"])
-    b["recv_h"].copy_(b["recv_d"], non_blocking=True)
-    cur.synchronize()
-    raw = b["recv_h"].numpy().reshape(world, nbytes)
-    status = raw[:, :head].copy().view(np.uint64)  # [world, STATUS_WORDS]
-    plan.async_done(status[dist.get_rank()])
-    g = float(status[0, _lib.ST_GLOBAL_MIN:_lib.ST_GLOBAL_MIN + 1].view(np.float64)[0])
-    n_solved = int(status[:, _lib.ST_SOLVED].sum())
-    emitted = [int(v) for v in status[:, _lib.ST_EMITTED]]
-    if max(emitted) > _XCAP:  # a shard overflowed the exchange buffer (every rank sees it): synchronous path
-        recs, _ = plan.pass2_dev(b["min"].data_ptr(), INF, cur.cuda_stream)
-        return gather_records(recs, dist, world), g, n_solved
-    parts = [raw[r, head:head + emitted[r] * item].copy().view(_lib.CAND_DTYPE) for r in range(world)]
-    allraw = np.concatenate(parts) if parts else np.zeros(0, dtype=_lib.CAND_DTYPE)
-    return _lib.filter_records(allraw, g + 2.5 * TIE_MARGIN), g, n_solved
+    On GPUs (NCCL) the step is ONE C call per rank (theta_search_n2_dist): pass 1 -> ncclAllReduce(min) on the device
+    double -> stripe scan + pass 2 -> ncclAllGather of the status blocks and raw records -> one host wait.  The host
+    models of the tests and the gloo backend take the two-pass Python path below."""
+    if dist is not None and hasattr(plan, "handle") and dist.get_backend() == "nccl":
+        return comm_for(dist).search_n2(plan, begin, end, stream)
+    recs, g = search_shard(plan, begin, end, dist, world, stream)
+    allrecs, extras = gather_records(recs, dist, world, extra=[plan.stats()["n_solved"]])
+    return allrecs, g, sum(e[0] for e in extras)
 
 
 _GATHER_CAP = 256  # records per shard carried by the fixed-size exchange
@@ -370,13 +339,69 @@ def do_optimization(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_normal,
                     multi_event, get_values, prefix=None):
     """RunTHetA.do_optimization (python/RunTHetA.py:124-171).
 
-    The reference farms candidates out to `max_processes - 1` worker processes and merges
-    their tie lists in scheduling order (Q13); parity is defined against the single-process
-    fold, which is what the GPU path reproduces.  `max_processes` is accepted and ignored:
-    parallelism comes from the GPU(s) -- one process per GPU under torch.distributed.
+    The reference farms candidates out to `max_processes - 1` worker processes and merges their tie lists in
+    scheduling order (Q13); parity is defined against the single-process fold, which is what the GPU path reproduces
+    on any number of GPUs.  `max_processes` maps to the number of GPUs: from a plain process (no torch.distributed
+    group) the search runs on min(max_processes, visible GPUs) devices through ONE blocking C call (theta_mgpu_*: one
+    host thread + stream per GPU, a single ncclAllReduce(min) between the passes).  Under torchrun every rank drives
+    its own GPU and `max_processes` is ignored.
     """
-    return do_optimization_single(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_normal, sorted_index,
-                                  multi_event, get_values, prefix)
+    n_gpus = 1
+    if _dist_state()[2] is None and not get_values and max_processes and int(max_processes) > 1:
+        n_gpus = max(1, min(int(max_processes), _lib.device_count()))
+    if n_gpus <= 1:
+        return do_optimization_single(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_normal, sorted_index,
+                                      multi_event, get_values, prefix)
+    if n not in (2, 3):
+        raise ValueError("n must be 2 or 3 (FileIO.py:42)")
+    try:
+        mg = _lib.MultiGpu(n, r, rN, lower_bounds, upper_bounds, tau=tau, max_normal=max_normal, n_devices=n_gpus)
+    except _lib.EmptySpaceError:
+        print(_NO_PROFILES)
+        sys.exit(1)
+    try:
+        try:
+            lo, up, recs, rows, vals, _st, _nc = mg.optimize()
+        except _lib.EmptySpaceError:
+            print(_NO_PROFILES)
+            sys.exit(1)
+        lower_bounds[:] = lo.tolist()  # Q16
+        upper_bounds[:] = up.tolist()
+        return best_from_records(n, m, tau, recs, rows, vals, sorted_index, mg)
+    finally:
+        mg.close()
+
+
+def best_from_records(n, m, tau, recs, rows, vals, sorted_index, mg=None):
+    """theta_mgpu_optimize's output -> the reference's `best` tuples (C_new, mu, likelihood, vals), original interval order."""
+    best = []
+    si = np.asarray(sorted_index, dtype=np.int64)
+    table = None
+    for j in range(len(recs)):
+        C = np.zeros((m, n))
+        C[si, 0] = tau
+        v = [0] * m
+        for i, x in zip(sorted_index, vals[j].tolist()):
+            v[i] = np.float64(x)
+        if n == 2:
+            C[si, 1] = rows[j].view(np.int8)
+            mu0 = np.float64(recs["mu"][j][0])
+            best.append((C, (mu0, 1 - mu0), np.float64(recs["nll"][j]), v))
+        else:
+            if table is None:
+                table = n3_row_table(tau, int(max(int(x) for x in mg._up))) if mg is not None else None
+            if int(recs["rank"][j]) != 0xFFFFFFFFFFFFFFFF:
+                ab = np.array([table[int(g)] for g in rows[j]], dtype=np.float64)
+                C[si, 1] = ab[:, 0]
+                C[si, 2] = ab[:, 1]
+            best.append((C, np.array(recs["mu"][j], dtype=np.float64), np.float64(recs["nll"][j]), v))
+    return best
+
+
+def n3_row_table(tau, K):
+    """Enumerator._create_graph's row list (python/Enumerator.py:272-298): first component fastest, rows with
+    (tau - a)(tau - b) >= 0 -- the order theta_n3_rows reports."""
+    return [(a, b) for b in range(K + 1) for a in range(K + 1) if (tau - a) * (tau - b) >= 0]
 
 
 def dump_values_n2(plan, path, chunk=1 << 18):

@@ -89,14 +89,21 @@ def search_n3(plan, leaf_cap=0, stream=None, window=0.0):
     has_bogus = int(bst[0]) < _lib.ST_NONE_SIGN
     null_nll = float(bnll[0]) if has_bogus else INF
     window = float(window) if window > 0 else 4.0 * _lib.TIE_MARGIN
+    use_comm = dist is not None and hasattr(plan, "handle") and dist.get_backend() == "nccl"
     while True:
-        local_min = plan.search_min_n3(b, e, INF, window, stream)
-        st = plan.stats()
-        g, _ = exchange_minima(local_min, dist, rank, world)
-        g_all = min(g, null_nll) if null_nll == null_nll else g
-        recs, paths = plan.window_n3(g_all, window, stream)
-        allrecs, extras = gather_records(recs, dist, world, extra=[st["n_solved"], st["n_candidates"]])
-        allpaths = gather_paths(paths, dist, world)
+        if use_comm:  # one C call per rank: minimum, ncclAllReduce(min), window records, ncclAllGather
+            from .search import comm_for
+            allrecs, allpaths, g_all, tot = comm_for(dist).search_n3(plan, b, e, window, null_nll, stream)
+            st = plan.stats()
+            extras = [list(tot)]
+        else:
+            local_min = plan.search_min_n3(b, e, INF, window, stream)
+            st = plan.stats()
+            g, _ = exchange_minima(local_min, dist, rank, world)
+            g_all = min(g, null_nll) if null_nll == null_nll else g
+            recs, paths = plan.window_n3(g_all, window, stream)
+            allrecs, extras = gather_records(recs, dist, world, extra=[st["n_solved"], st["n_candidates"]])
+            allpaths = gather_paths(paths, dist, world)
         vals = list(allrecs["nll"]) + ([null_nll] if has_bogus else [])
         fin = [v for v in vals if v == v]
         if not fin:
@@ -154,19 +161,13 @@ def do_optimization_n3(m, k, tau, lower_bounds, upper_bounds, r, rN, sorted_inde
         rows = plan.rows()
         res = search_n3(plan)
         best = []
-        real = [b for b in res.best if b[0] is not None]
-        vals = None
-        if real:
-            _, _, _, _, vals = plan.solve_rows(np.stack([b[0] for b in real]), want_vals=True)
-        j = 0
-        A = float(sum(int(v) for v in rN))
-        for path, mu, nll, st in res.best:
+        # Optimizer.solve's third return value for the winners: L3's numer_i / denom in reference order (mode 1); the
+        # all-[tau,0,0] pseudo candidate is row 0 everywhere
+        wp = [np.zeros(m, dtype=np.uint8) if b[0] is None else np.asarray(b[0], dtype=np.uint8) for b in res.best]
+        vals = plan.solve_rows(np.stack(wp), want_vals=True, mode=1)[4] if wp else None
+        for j, (path, mu, nll, st) in enumerate(res.best):
             C = _matrix(path, rows, tau, m)
-            if path is None:
-                v = [np.float64(int(x) / A) for x in rN]  # all-normal model: p_i = rN_i / sum rN
-            else:
-                v = [np.float64(x) for x in vals[j]]
-                j += 1
+            v = [np.float64(x) for x in vals[j]]
             best.append((_reverse_sort_rows(C, sorted_index), np.array(mu, dtype=np.float64), np.float64(nll),
                          _reverse_sort_list(v, sorted_index)))
         if get_values:
