@@ -6,16 +6,19 @@
 One "step" = one complete search (enumerate every admissible C, solve mu, NLL, keep the
 best with the reference's tie fold) of the workload's candidate space.  At N=1 the workload is
 BASELINE.json configs[1]: synthetic m=150, n=2, k=5 (seed 1) -> 25,251,156 candidates.
-For N>1 (torchrun, one rank per GPU) the scaling is WEAK: every GPU keeps the same 25,251,156
-candidates per step; the job is the first N x 25,251,156 ranks of the same data's search with the
-upper bounds widened by two copies (same r, rN, m, K=5 -> same cost per candidate; 4.196e8 candidates),
-cut into contiguous rank ranges.  The only communication is the min exchange + the record gather.
+The scaling series is WEAK and uses ONE workload family at every N (including N=1): the data of configs[1] with the
+upper bounds widened by two copies (same r, rN, m, K=5 -> same cost per candidate; 4.196e8 candidates), first
+N x 25,251,156 ranks, cut into contiguous rank ranges -- 25,251,156 candidates (configs[1]'s count) per GPU per
+step.  The exact configs[1] space, the >=100x target shape and configs[2..4] are measured at every N too (`extra`,
+strong scaling).  The only communication is one ncclAllReduce(min) + one ncclAllGather of the records per step.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      the streaming NLL kernel (theta_nll_tiles_n2) on tiles larger than L2, HBM-bound
-  search_kernel the fused search kernel's own device time / fp64 utilisation
-  cpu_baseline  the oracle's Python port of the reference path on the host cores (bounded sample)
-  extra         the >=100x target shape (m=150, k=7) searched once
+  roofline         the streaming NLL kernel (theta_nll_tiles_n2) on tiles larger than L2, HBM-bound
+  roofline_search  the kernel that binds the timed step (n2_search_kernel): fp64 flops executed / DFMA peak
+  dist_check       N > 1: the sharded answers equal the unsharded ones (rank 0 re-runs them on one GPU)
+  cpu_baseline     the reference's own multiprocessing path on the host cores (oracle/_ref snapshot; else the port)
+  extra            configs[1] exact, the >=100x target shape (m=150, k=7), configs[2], [3], [4] at this N; the
+                   single-process multi-GPU driver (theta_mgpu_*) on the same GPUs
 """
 import argparse
 import json
@@ -158,39 +161,114 @@ def cpu_reference_rate(name, per_core, cores=None):
                       % (total, per_core, wall)}
 
 
+def reference_available():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refshim
+    return os.path.isdir(refshim.REF), refshim.REF
+
+
+def live_reference_rate(name, seconds=15.0, cores=None):
+    """The reference's OWN multiprocessing path -- RunTHetA.do_optimization (python/RunTHetA.py:124-171: one producer,
+    NUM_PROCESSES-1 forked workers, pickled matrices through a Queue), unmodified arithmetic, imported through
+    oracle/refshim.py from /root/reference/python or the oracle/_ref snapshot -- on the first P candidates of the
+    workload in enumeration order (the Enumerator it instantiates is wrapped to stop after P; nothing else is touched).
+    P is sized from a short calibration run so that the timed run takes about `seconds`."""
+    import contextlib
+    import io
+    import warnings
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refshim
+    warnings.simplefilter("ignore")
+    R = refshim.modules()
+    P = problem(name)
+    cores = cores or os.cpu_count() or 1
+    base = R.Enumerator.Enumerator
+
+    def run(limit):
+        class Bounded(base):
+            def __init__(self, *a, **k):
+                base.__init__(self, *a, **k)
+                self._left = limit
+
+            def generate_next_C(self):
+                if self._left <= 0:
+                    return False
+                self._left -= 1
+                return base.generate_next_C(self)
+        R.RunTHetA.Enumerator = Bounded
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            best = R.RunTHetA.do_optimization(2, P["m"], P["k"], 2, list(P["lower"]), list(P["upper"]), P["r"], P["rN"], 1.0,
+                                              P["sorted_index"], cores, True, False)
+        dt = time.perf_counter() - t0
+        R.RunTHetA.Enumerator = base
+        return (limit + 1) / dt, dt, float(best[0][2])
+
+    rate0, _, _ = run(40 * cores)
+    limit = max(200, int(rate0 * seconds))
+    rate, dt, nll = run(limit)
+    return {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "reference",
+            "sample": "first %d candidates of the workload in enumeration order through the reference's own "
+                      "RunTHetA.do_optimization with NUM_PROCESSES=%d (%d workers + producer), %.1f s wall; modules from %s"
+                      % (limit + 1, cores, cores - 1, dt, refshim.REF), "best_nll_of_sample": nll}
+
+
+def cpu_arm(name, seconds=15.0):
+    """cpu_baseline: the live reference when its modules are present (build container: /root/reference; GPU box: the
+    oracle/_ref snapshot), else the oracle port -- and says which."""
+    ok, _ = reference_available()
+    if ok and os.environ.get("THETA_CPU_ARM", "reference") != "port":
+        try:
+            return live_reference_rate(name, seconds)
+        except Exception as exc:  # fall back to the port, keep the reason
+            res = cpu_reference_rate(name, 40000)
+            res["sample"] += " [live reference failed: %s]" % (str(exc)[:120],)
+            return res
+    return cpu_reference_rate(name, 40000)
+
+
+def headline(world):
+    """The workload of `value` at every N: BASELINE configs[1]'s data (m=150, n=2, k=5, seed 1), upper bounds widened by
+    two copies, the first world x 25,251,156 ranks -- 25,251,156 candidates (configs[1]'s count) per GPU per step."""
+    P = problem("cfg2w")
+    P["window"] = PER_GPU * world
+    return P
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.workload == "cfg2":
-        args.workload = "cfg2w"  # same config as our arm at this N
-    per_core = 40000
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    name = "cfg2w" if args.workload == "cfg2" else args.workload
     vals = []
-    for _ in range(args.warmup and 1 or 0):
-        cpu_reference_rate(args.workload, 100)
     res = None
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = cpu_reference_rate(args.workload, per_core)
+    for _ in range(max(1, args.steps)):
+        res = cpu_arm(name, seconds=12.0)
         vals.append(res["value"])
     wall = time.perf_counter() - t0
     v = sum(vals) / len(vals)
     res["value"] = v
-    P = problem(args.workload)
+    P = headline(world) if name == "cfg2w" else problem(name)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import theta_oracle as O
     total = O.count_n2(P["lower"], P["upper"])
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.workload == "cfg2w":
-        total = min(total, PER_GPU * world)
+    if P.get("window"):
+        total = min(total, P["window"])
     line = {"impl": "reference", "metric": "C-candidates/sec", "value": v, "unit": "candidates/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": P["desc"], "n": 2, "m": P["m"], "k": P["k"], "candidates": int(total)},
+            "config": config_of(P, total, world),
             "cpu_baseline": res,
             "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def config_of(P, total, world):
+    return {"workload": P["desc"], "n": 2, "m": P["m"], "k": P["k"], "candidates": int(total),
+            "candidates_per_gpu": PER_GPU}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -211,7 +289,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from theta_b200 import _lib, search
+    from theta_b200 import _lib, search, search_n3
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,14 +303,12 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.current_stream().cuda_stream
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import theta_oracle as O  # input generators only
 
-    if world > 1 and args.workload == "cfg2":
-        args.workload = "cfg2w"  # weak scaling: same data and K, wider bounds, PER_GPU ranks per GPU
-    P = problem(args.workload)
+    P = headline(world) if args.workload == "cfg2" else problem(args.workload)
     plan = _lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"])
     total = plan.count()
-    if args.workload == "cfg2w":
-        total = min(total, PER_GPU * world)
     if P["window"]:
         total = min(total, P["window"])
     begin, end = search.shard_range(total, rank, world)
@@ -241,7 +317,8 @@ def main():
     launches = [0]
 
     def step():
-        # search kernel, min reduction [, NCCL all-reduce], stripe scan, emit kernel -- one host synchronisation
+        # per rank: search kernel, min reduction [, ncclAllReduce(min)], stripe scan, emit kernel [, ncclAllGather],
+        # one host synchronisation; at N > 1 all of it inside ONE C call (theta_search_n2_dist)
         recs, g, _ = search.search_sharded(plan, begin, end, D, world, stream)
         launches[0] += 4
         return recs, g
@@ -276,7 +353,8 @@ def main():
 
     # ---- e2e: the public call (host lists in, the reference-shaped Python `best` list out), every step from
     # scratch: one C-ABI call at N=1 (theta_optimize_n2: tables built on the host, staged in pinned memory, one H2D;
-    # both passes; D2H of the status block and records; the fold; winners' columns and vals).
+    # both passes; D2H of the status block and records; the fold; winners' columns and vals); at N>1 every rank builds
+    # its plan and runs the one-call sharded step.
     def e2e_step():
         return search.do_optimization_single(2, P["m"], P["k"], 2, list(P["lower"]), list(P["upper"]), P["r"], P["rN"],
                                              1.0, P["sorted_index"], True, False, rank_limit=total)
@@ -291,21 +369,40 @@ def main():
     tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-    # bytes that cross PCIe per call: H2D = the plan arena (count tables, r, rN, their prefix sums, status block);
-    # D2H = the status block + the speculative record window of pass 2 (theta_n2.cu: 1024 x 48 B)
+    # bytes that cross PCIe per call and rank: H2D = the plan arena (count tables, r, rN, their prefix sums, status
+    # block); D2H = the status block + the record window (N=1: 1024 x 48 B speculative; N>1: world x (256 B + 256 x 48 B))
     up256 = lambda v: (v + 255) & ~255
     h2d = (up256(plan.table_bytes()) + 2 * up256(8 * plan.m) + 2 * up256(8 * (plan.pitch + 1)) + up256(4 * (plan.pitch + 1))
            + up256(8 * 32))
-    d2h = 8 * 32 + 48 * 1024
+    d2h = 8 * 32 + 48 * 1024 if world == 1 else world * (8 * 32 + 48 * 256)
     e2e = {"value": total * args.steps / float(tdt.item()), "unit": "candidates/s",
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(tdt.item()) / args.steps,
+           "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+           "ms_per_step": 1e3 * float(tdt.item()) / args.steps,
            "api": "theta_b200.search.do_optimization_single (RunTHetA.py:173 signature), host lists in / best list out",
            "best_nll": float(best[0][2]), "best_mu0": float(best[0][1][0]), "n_best": len(best)}
 
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- dist_check: the N-shard answer == the unsharded answer on the same window (rank 0 re-runs it on its GPU)
+    dist_check = None
+    sharded_best = search.fold_replay(recs["rank"], recs["nll"], dup_first=True)
+    sharded_key = [(int(recs["rank"][i]), float(recs["mu"][i][0]), float(recs["nll"][i])) for i in sharded_best]
+    if world > 1:
+        ok = True
+        if rank == 0:
+            plan.pass1_begin(0, total, None, stream)
+            r1, g1 = plan.pass2_dev(None, float("inf"), stream)
+            one = search.fold_replay(r1["rank"], r1["nll"], dup_first=True)
+            one_key = [(int(r1["rank"][i]), float(r1["mu"][i][0]), float(r1["nll"][i])) for i in one]
+            ok = (one_key == sharded_key) and (g1 == g)
+            dist_check = {"ok": bool(ok), "what": "n=2 headline window: best list (rank, mu, NLL) and minimum of the %d-shard "
+                                                  "search identical to the unsharded search on one GPU" % world,
+                          "n_best": len(one_key)}
+        barrier()
+
     # ---- roofline of the streaming NLL kernel (rank 0 only; tiles > L2 so every launch streams from HBM)
     roof = None
+    roof_search = None
     extra = {}
     if rank == 0:
         lib = _lib.load()
@@ -353,11 +450,29 @@ def main():
         roof = {"kernel": "nll_tiles_kernel (theta_nll_tiles_n2_dev: Optimizer.L2 over int8 C tiles, TMA-staged)",
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_candidate": plan.m + 16, "candidates_per_launch": cnt,
-                "ms_per_launch": t_nll, "tile_bytes": cnt * pitch, "check_max_rel_err_vs_solve": maxrel}
+                "ms_per_launch": t_nll, "tile_bytes": cnt * pitch, "check_max_rel_err_vs_solve": maxrel,
+                "note": "the north-star's NLL kernel; the kernel that binds the timed step is in roofline_search"}
         del tiles, mu, nll, stt
-        # fused search kernel: device time and fp64 rate
+        # ---- the kernel that binds the timed step: n2_search_kernel, FP64 pipe.  flops per candidate = 2 DFMA + DMUL +
+        # DADD executed (ncu smsp__sass_thread_inst_executed_op_d*_pred_on of the committed capture, profiles/
+        # search_flops.json) ; peak = DFMA microbenchmark on this GPU (theta_fp64_peak)
         fp64 = _lib.fp64_peak_gflops(stream)
         extra["fp64_peak_gflops_measured"] = fp64
+        try:
+            with open(os.path.join(ROOT, "profiles", "search_flops.json")) as f:
+                sf = json.load(f)
+            fl = float(sf["flops_per_candidate"])
+            t_k = sum(p1_ms) / len(p1_ms) * 1e-3
+            ach_f = fl * (end - begin) / t_k / 1e9
+            roof_search = {"kernel": "n2_search_kernel<KT,false> (pass 1 of the timed step: %.0f %% of the step)"
+                                     % (100.0 * (sum(p1_ms) / len(p1_ms)) / (ms_total / args.steps)),
+                           "bound": "fp64", "achieved": ach_f, "peak": fp64, "unit": "GFLOP/s", "frac": ach_f / fp64,
+                           "flops_per_candidate": fl, "flops_source": sf.get("source"),
+                           "ncu_sm__pipe_fp64_cycles_active_pct": sf.get("pipe_fp64_cycles_active_pct"),
+                           "candidates_per_launch": int(end - begin), "ms_per_launch": t_k * 1e3,
+                           "peak_source": "theta_fp64_peak: dependent-free DFMA streams, measured in this process"}
+        except Exception:
+            roof_search = None
     # search kernel own numbers (all ranks ran it; report rank 0's)
     search_kernel = {"kernel": "n2_search_kernel<KT,false>", "ms_pass1_mean": sum(p1_ms) / len(p1_ms),
                      "ms_pass2_last": st["ms_pass2"], "candidates_per_launch": int(end - begin),
@@ -365,72 +480,97 @@ def main():
                      "newton_iters_mean": st["newton_iters"], "stripes": int(st["n_stripes"]),
                      "rescanned_stripes": int(st["n_rescanned"])}
 
-    if not args.no_extra and args.workload == "cfg2" and world == 1:
-        # (a) the >=100x target shape of BASELINE.json (m=150, k=7, 6.07e8 candidates), sharded over all ranks
-        P7 = problem("m150k7")
-        plan7 = _lib.Plan(2, P7["r"], P7["rN"], P7["lower"], P7["upper"])
-        n7 = plan7.count()
-        b7, e7 = search.shard_range(n7, rank, world)
+    if not args.no_extra and args.workload == "cfg2":
+        def timed(fn, warm=1):
+            for _ in range(warm):
+                fn()
+            barrier()
+            t0_ = time.perf_counter()
+            out = fn()
+            barrier()
+            d = torch.tensor([time.perf_counter() - t0_], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(d, op=dist.ReduceOp.MAX)
+            return out, float(d.item())
 
-        def step7():
-            r_, g_, _ = search.search_sharded(plan7, b7, e7, D, world, stream)
-            return r_, g_
-        for _ in range(2):
-            step7()
+        def n2_strong(name):
+            Pn = problem(name)
+            pl = _lib.Plan(2, Pn["r"], Pn["rN"], Pn["lower"], Pn["upper"])
+            n_ = pl.count()
+            b_, e_ = search.shard_range(n_, rank, world)
+            (r_, g_, _s), dt_ = timed(lambda: search.search_sharded(pl, b_, e_, D, world, stream), warm=0 if n_ > 1e10 else 2)
+            out = {"workload": Pn["desc"], "candidates": n_, "seconds": dt_, "cand_per_s": n_ / dt_, "min_nll": g_,
+                   "ms_pass1_rank0": pl.stats()["ms_pass1"], "n_records": int(len(r_)), "n_gpus": world, "scaling": "strong"}
+            pl.close()
+            return out
+        # BASELINE configs[1] exactly (the 25,251,156-candidate space of the unwidened bounds), the >=100x target shape
+        # (m=150, k=7, 6.07e8 candidates) and configs[2] (m=300, k=7: the WHOLE 1.698e11-candidate space), each cut into
+        # `world` contiguous rank ranges: strong scaling
+        extra["cfg2_exact_space"] = n2_strong("cfg2")
+        extra["m150_k7_full_space"] = n2_strong("m150k7")
+        extra["cfg3_strong"] = n2_strong("cfg3")
+
+        # n = 3: BASELINE configs[3] (m=150, k=5, explicit bounds, F=12: whole space) and configs[4] (m=500, k=7,
+        # TAU-style bounds: a 200,000-item prefix of the enumeration order), sharded by item weight, one
+        # ncclAllReduce(min) between the minimum search and the window records
+        def n3_case(m_, k_, F_, tb_, budget):
+            P3 = O.synthetic_problem_n3(m_, k_, 1, F_, tb_)
+            pl = _lib.Plan(3, P3["r"], P3["rN"], P3["lower"], P3["upper"])
+            tp = time.perf_counter()
+            pl.prepare(4096 if budget else 0, budget or (1 << 22))  # host: cut the DFS forest into work items (once per plan)
+            tp = time.perf_counter() - tp
+            res3, dt3 = timed(lambda: search_n3.search_n3(pl, leaf_cap=4096 if budget else 0, max_items=budget or None), warm=1)
+            out = {"candidates": res3.count, "seconds": dt3, "prepare_seconds": tp, "cand_per_s": res3.count / dt3, "min_nll": res3.min_nll,
+                   "items": res3.n_items, "n_gpus": world, "ms_search_rank0": res3.stats["ms_pass1"],
+                   "survivors_solved_rank0": int(res3.stats["n_exact"]), "n_best": len(res3.best), "scaling": "strong",
+                   "truncated_to_item_budget": bool(getattr(pl, "truncated", False))}
+            key3 = [(None if b[0] is None else tuple(int(x) for x in b[0]), b[2]) for b in res3.best]
+            if world > 1 and rank == 0:  # G == 1 check on this space too
+                saved = search_n3._dist_state
+                search_n3._dist_state = lambda: (0, 1, None)
+                try:
+                    one3 = search_n3.search_n3(pl, leaf_cap=4096 if budget else 0, max_items=budget or None)
+                finally:
+                    search_n3._dist_state = saved
+                out["equals_single_gpu"] = [(None if b[0] is None else tuple(int(x) for x in b[0]), b[2]) for b in one3.best] == key3
+            barrier()
+            pl.close()
+            return out
+        extra["cfg4_n3_m150_k5"] = n3_case(150, 5, 12, False, 0)
+        extra["cfg5_n3_m500_k7_tau_bounds"] = n3_case(500, 7, 12, True, 200000)
+        if dist_check is not None:
+            dist_check["n3_cfg4_equals_single_gpu"] = extra["cfg4_n3_m150_k5"].get("equals_single_gpu")
+            dist_check["n3_cfg5_equals_single_gpu"] = extra["cfg5_n3_m500_k7_tau_bounds"].get("equals_single_gpu")
+            dist_check["ok"] = bool(dist_check["ok"] and dist_check["n3_cfg4_equals_single_gpu"]
+                                    and dist_check["n3_cfg5_equals_single_gpu"])
+
+        # ONE process driving all `world` GPUs (theta_mgpu_*: what do_optimization(max_processes) maps to), measured by
+        # rank 0 in a child process while the other ranks wait: the headline workload and configs[2]
+        if rank == 0:
+            try:
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mgpu_bench.py"), "--gpus", str(world),
+                                      "--steps", str(args.steps)], capture_output=True, text=True, timeout=300)
+                extra["single_process_driver"] = json.loads(out.stdout.strip().split("\n")[-1])
+            except Exception as exc:
+                extra["single_process_driver"] = {"error": str(exc)[:200]}
         barrier()
-        t0 = time.perf_counter()
-        r7, g7 = step7()
-        barrier()
-        dt7 = time.perf_counter() - t0
-        extra["m150_k7_full_space"] = {"candidates": n7, "seconds": dt7, "cand_per_s": n7 / dt7, "min_nll": g7,
-                                       "ms_pass1_rank0": plan7.stats()["ms_pass1"], "n_gpus": world}
-        plan7.close()
-        # (a2) BASELINE configs[2]: m=300, k=7, the whole 1.698e11-candidate space (SURVEY 8d allowed a rank budget;
-        # at this rate the full space takes seconds)
-        P3f = problem("cfg3")
-        plan3f = _lib.Plan(2, P3f["r"], P3f["rN"], P3f["lower"], P3f["upper"])
-        n3f = plan3f.count()
-        b3f, e3f = search.shard_range(n3f, rank, world)
-        barrier()
-        t0 = time.perf_counter()
-        r3f, g3f, _ = search.search_sharded(plan3f, b3f, e3f, D, world, stream)
-        barrier()
-        dt3f = time.perf_counter() - t0
-        extra["m300_k7_full_space"] = {"candidates": n3f, "seconds": dt3f, "cand_per_s": n3f / dt3f, "min_nll": g3f,
-                                       "ms_pass1_rank0": plan3f.stats()["ms_pass1"], "n_records": int(len(r3f)), "n_gpus": world}
-        plan3f.close()
-        # (b) n = 3: BASELINE configs[3] shape (m=150, k=5, explicit bounds, F=12), whole space, sharded by items
-        import theta_oracle as O
-        from theta_b200 import search_n3
-        P3 = O.synthetic_problem_n3(150, 5, 1, 12, False)
-        plan3 = _lib.Plan(3, P3["r"], P3["rN"], P3["lower"], P3["upper"])
-        search_n3.search_n3(plan3, leaf_cap=512)
-        barrier()
-        t0 = time.perf_counter()
-        res3 = search_n3.search_n3(plan3, leaf_cap=512)
-        barrier()
-        dt3 = time.perf_counter() - t0
-        extra["n3_m150_k5_full_space"] = {"candidates": res3.count, "seconds": dt3, "cand_per_s": res3.count / dt3,
-                                          "min_nll": res3.min_nll, "items": res3.n_items, "n_gpus": world,
-                                          "ms_pass1_rank0": res3.stats["ms_pass1"], "hybrj_fevals_mean": res3.stats["newton_iters"]}
-        plan3.close()
 
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:
-        cpu = cpu_reference_rate(args.workload, 40000)
+        cpu = cpu_arm("cfg2w" if args.workload == "cfg2" else args.workload)
 
     if rank == 0:
+        cfg = config_of(P, total, world)
+        cfg["sharding"] = ("contiguous rank ranges, %d per GPU; one ncclAllReduce(min) + one ncclAllGather of the records per step"
+                           % ((total + world - 1) // world))
+        cfg["l2_policy"] = ("search kernel streams nothing from HBM (tables in shared memory); the roofline kernel uses "
+                            "tiles of %d MiB > L2" % (roof["tile_bytes"] >> 20 if roof else 0))
         line = {"metric": "C-candidates/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": P["desc"], "n": 2, "m": P["m"], "k": P["k"], "candidates": int(total),
-                           "sharding": "contiguous rank ranges, %d per GPU; one all-reduce(min) + record gather per step"
-                                       % ((total + world - 1) // world),
-                           "l2_policy": "search kernel streams nothing from HBM (tables in shared memory); the "
-                                        "roofline kernel uses tiles of %d MiB > L2" % (roof["tile_bytes"] >> 20 if roof else 0)},
+                "data": "synthetic", "config": cfg,
                 "e2e": e2e, "time_to_best_nll_ms": e2e["ms_per_step"], "gpu_launches": launches[0], "clocks": clocks,
-                "roofline": roof,
+                "roofline": roof, "roofline_search": roof_search, "dist_check": dist_check,
                 "search_kernel": search_kernel, "cpu_baseline": cpu, "extra": extra,
                 "result": {"min_nll": g, "n_records": int(len(recs)), "n_solved": int(st["n_solved"])}}
         print(json.dumps(line))

@@ -2,9 +2,11 @@
 
 TEST INFRASTRUCTURE ONLY.  This module exists to (a) validate the restatement
 in oracle/theta_oracle.py against the reference's own code and (b) generate the
-golden vectors committed under tests/golden/ (see oracle/make_golden.py).  It
-only works in the build container: /root/reference does not exist on the GPU
-box, so nothing under tests/ -m gpu, bench.py or __graft_entry__ may import it.
+golden vectors committed under tests/golden/ (see oracle/make_golden.py), and
+(c) time the reference's own multiprocessing path as the CPU arm of bench.py.
+/root/reference exists only in the build container; on the GPU box the modules
+come from oracle/_ref/python, a git-ignored snapshot made by oracle/build_ref.sh
+that travels with the working tree.  Only bench.py's CPU arm uses it there.
 
 No reference source is copied: each module's text is read from the read-only
 tree at import time and executed after the minimal py2->py3 syntax rewrites
@@ -18,7 +20,8 @@ import re
 import sys
 import types
 
-REF = os.environ.get("THETA_REFERENCE", "/root/reference/python")
+_SNAP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "python")  # oracle/build_ref.sh (git-ignored)
+REF = os.environ.get("THETA_REFERENCE") or ("/root/reference/python" if os.path.isdir("/root/reference/python") else _SNAP)
 
 _PRINT = re.compile(r"^(\s*(?:[^#'\"]*?:\s*)?)print\s+(?!\()(.*)$")
 _BARE_PRINT = re.compile(r"^(\s*(?:[^#'\"]*?:\s*)?)print\s*$")

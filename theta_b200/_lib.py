@@ -242,12 +242,17 @@ class Plan(object):
         return [(int(x), int(y)) for x, y in zip(a[:n.value], b[:n.value])]
 
     def prepare(self, leaf_cap=0, max_items=1 << 22):
+        """Cut the DFS forest into work items (theta_n3_prepare).  The list is a function of the plan and the two
+        arguments only, so a repeated call with the same arguments keeps the list that is already on the device."""
+        if getattr(self, "_prepared", None) == (int(leaf_cap), int(max_items)):
+            return self.n_items
         n = C.c_uint64()
         check(load().theta_n3_prepare(self._h, int(leaf_cap), int(max_items), C.byref(n)))
         self.n_items = int(n.value)
         t = C.c_int32()
         check(load().theta_n3_truncated(self._h, C.byref(t)))
         self.truncated = bool(t.value)
+        self._prepared = (int(leaf_cap), int(max_items))
         return self.n_items
 
     def columns_of_ranks(self, ranks):

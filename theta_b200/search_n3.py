@@ -65,7 +65,7 @@ def cluster_top(values, g):
     return h
 
 
-def search_n3(plan, leaf_cap=0, stream=None, window=0.0):
+def search_n3(plan, leaf_cap=0, stream=None, window=0.0, max_items=None):
     """Sharded n=3 search.  Returns a SearchResultN3 with `best` = list of
     (path or None for the bogus first matrix, mu[3], nll, status) in fold order.
 
@@ -74,10 +74,14 @@ def search_n3(plan, leaf_cap=0, stream=None, window=0.0):
     member that follows).  So: every shard finds its exact minimum (theta_search_n3_min), one
     all-reduce(min) gives g, every shard returns its candidates within `window` of g, and the fold is replayed over
     their union -- after checking that the cluster really ends inside the window; if not, search again with a
-    wider one."""
+    wider one.
+
+    max_items (not in the reference): an explicit work-item budget -- search only the lexicographic prefix of the space
+    that fits (the rank-budget runs of SURVEY 8d).  Without it a space that exceeds the item limit is an error, never a
+    silent prefix."""
     rank, world, dist = _dist_state()
-    n_items = plan.prepare(leaf_cap)
-    if getattr(plan, "truncated", False) and not getattr(plan, "allow_truncated", False):
+    n_items = plan.prepare(leaf_cap, max_items) if max_items else plan.prepare(leaf_cap)
+    if getattr(plan, "truncated", False) and not max_items:
         raise _lib.ThetaError("the n=3 candidate space exceeds %d work items: theta_n3_prepare would cover only a "
                               "lexicographic prefix of it (pass an explicit item budget to search a prefix)" % n_items)
     w = plan.item_weights()
