@@ -300,7 +300,8 @@ def main():
     _lib.init(local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.current_stream().cuda_stream
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -546,6 +547,10 @@ def main():
 
         # ONE process driving all `world` GPUs (theta_mgpu_*: what do_optimization(max_processes) maps to), measured by
         # rank 0 in a child process while the other ranks wait: the headline workload and configs[2]
+        # (the other ranks wait on the rendezvous store, i.e. on the CPU: an NCCL barrier would keep a spinning kernel on
+        # their GPUs and time-slice them with the child process)
+        torch.cuda.synchronize()
+        store = dist.distributed_c10d._get_default_store() if world > 1 else None
         if rank == 0:
             try:
                 out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mgpu_bench.py"), "--gpus", str(world),
@@ -553,6 +558,10 @@ def main():
                 extra["single_process_driver"] = json.loads(out.stdout.strip().split("\n")[-1])
             except Exception as exc:
                 extra["single_process_driver"] = {"error": str(exc)[:200]}
+            if store is not None:
+                store.set("theta_mgpu_done", "1")
+        elif store is not None:
+            store.wait(["theta_mgpu_done"])
         barrier()
 
     cpu = None

@@ -9,6 +9,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
