@@ -58,13 +58,18 @@ typedef struct theta_problem {
     int32_t n;            /* populations: 2 or 3 */
     int32_t m;            /* intervals */
     int32_t tau;          /* copies in the normal genome */
-    int32_t reserved;
+    int32_t reserved;     /* flags: THETA_PLAN_TILES_ONLY */
     const int64_t* r;     /* [m] tumour read counts  (host) */
     const int64_t* rN;    /* [m] normal read counts  (host) */
     const int32_t* lower; /* [m] per-interval lower copy bound (host) */
     const int32_t* upper; /* [m] per-interval upper copy bound (host) */
     double max_normal;    /* Optimizer upper_bound (Optimizer.py:43); 1.0 = unconstrained */
+    double min_normal;    /* Optimizer lower_bound (Optimizer.py:43,109-110); 0.0 = unconstrained.  RunTHetA never sets it:
+                             honoured by the explicit-column solve (theta_solve_tiles_n2), not by the search kernels */
 } theta_problem;
+/* theta_problem.reserved flag: the plan only serves explicit columns (theta_solve_tiles_* / theta_nll_tiles_*): a space
+ * whose candidate count exceeds 2^63 is accepted (count reported as 0, searches refused) */
+#define THETA_PLAN_TILES_ONLY 1
 
 /* One candidate record.  `rank` is the 0-based position in the reference's
  * enumeration order (Enumerator.py:119-152: ascending colex). */

@@ -93,3 +93,84 @@ def test_cli_default_flow_matches_reference_outputs(tmp_path):
     ref_n = 3 if ref_best == open(os.path.join(GOLD, "cli_flow.n3.results")).read() else 2
     with open(os.path.join(out, "flow.BEST.results")) as f, open(os.path.join(out, "flow.n%d.results" % ref_n)) as g:
         assert f.read() == g.read()
+
+
+def _dump_lines(path):
+    with open(path) as f:
+        return [ln.rstrip("\n").split("\t") for ln in f]
+
+
+def test_get_values_dump_matches_reference(tmp_path, golden):
+    """--GET_VALUES (RunTHetA.py:210-215): the .likelihoods dump, line for line, against the reference's own dumps of
+    the whole small n=2 spaces (first matrix twice: Q1) and against the live reference's per-candidate results for the
+    n=3 spaces (all-[tau,0,0] matrix first: Q2): same column strings in the same order, mu within 1e-9, NLL within 1e-10."""
+    from theta_b200 import _lib
+    from theta_b200.search import dump_values_n2
+    from theta_b200.search_n3 import dump_values_n3
+    _lib.init(0)
+    for case in golden("n2_small_full.json"):
+        plan = _lib.Plan(2, case["r"], case["rN"], case["lower"], case["upper"], max_normal=case["max_normal"])
+        out = str(tmp_path / "n2.likelihoods")
+        dump_values_n2(plan, out)
+        want = [s for s in case["stream"] if s[1] is not None]
+        if case["stream"][0][1] is not None:
+            want = [want[0]] + want
+        got = _dump_lines(out)
+        assert [g[0] for g in got] == [w[0] for w in want]
+        for g, w in zip(got, want):
+            assert abs(float(g[1]) - w[1]) <= 1e-9 and abs(float(g[2]) - w[2]) <= 1e-10 * abs(w[2]), (g, w)
+        plan.close()
+    for case in golden("n3_small_full.json.gz"):
+        plan = _lib.Plan(3, case["r"], case["rN"], case["lower"], case["upper"])
+        plan.prepare()
+        out = str(tmp_path / "n3.likelihoods")
+        dump_values_n3(plan, plan.rows(), out)
+        want = []
+        for s in case["stream"]:
+            if s[2] is None:
+                continue
+            col1 = "0" * case["m"] if s[0] == "bogus" else s[0][0::2]
+            want.append((col1, s[1][0], s[2]))
+        got = _dump_lines(out)
+        assert [g[0] for g in got] == [w[0] for w in want]
+        for g, w in zip(got, want):
+            assert abs(float(g[1]) - w[1]) <= 1e-9, (g, w)
+            assert (float(g[2]) != float(g[2])) if w[2] != w[2] else abs(float(g[2]) - w[2]) <= 1e-10 * abs(w[2]), (g, w)
+        plan.close()
+
+
+def test_time_estimate_counts_messages_and_aborts(capsys, golden):
+    """TimeEstimate.time_estimate (TimeEstimate.py:40-89): exact n=2 count, the reference's n=3 estimate, the printed
+    ETA, the n=3 / m > 30 guard and the > 200 h abort without --FORCE."""
+    import gzip, json
+    from theta_b200.time_estimate import count_number_matrices_2, count_number_matrices_3, time_estimate
+    with open(os.path.join(GOLD, "config1_search.json")) as f:
+        inp = json.load(f)["inputs"]
+    m = len(inp["r"])
+    res = time_estimate(2, m, 3, 2, list(inp["lower"]), list(inp["upper"]), inp["r"], inp["rN"], 1.0, list(range(m)), 1, True, False)
+    assert res["count"] == 142560 and res["rate"] > 1e8 and res["seconds"] < 1
+    text = capsys.readouterr().out
+    assert "Estimating time..." in text and "Estimated Total Time: 0 second(s)" in text
+    # values of the live reference's count_number_matrices_3 (Python 2 integer division) on the golden spaces
+    cases = golden("n3_small_full.json.gz")
+    assert [count_number_matrices_3(c["m"], c["upper"], c["lower"]) for c in cases] == [2600, 6190, 33535]
+    c = cases[0]
+    res = time_estimate(3, c["m"], 3, 2, list(c["lower"]), list(c["upper"]), c["r"], c["rN"], 1.0, c["sorted_index"], 1, True, False)
+    assert res["count"] == 2600
+    capsys.readouterr()
+    # n = 3 with more than 30 intervals needs --FORCE (TimeEstimate.py:48-50)
+    big = 31
+    with pytest.raises(SystemExit) as ex:
+        time_estimate(3, big, 3, 2, [1] * big, [2] * big, [1000] * big, [1000] * big, 1.0, list(range(big)), 1, True, False)
+    assert ex.value.code == 1 and "Run with --FORCE to continue" in capsys.readouterr().out
+    # C(1007, 7) ~ 2e17 candidates: hundreds of hours even at 1e10 candidates/s -> abort unless forced (:74-85)
+    mm = 1000
+    rr = [1000 + 3 * i for i in range(mm)]
+    rn = [1000] * mm
+    assert count_number_matrices_2(mm, [7] * mm, [0] * mm) == 204032533091695451  # C(1007, 7)
+    with pytest.raises(SystemExit) as ex:
+        time_estimate(2, mm, 7, 2, [0] * mm, [7] * mm, rr, rn, 1.0, list(range(mm)), 1, True, False)
+    out = capsys.readouterr().out
+    assert ex.value.code == 1 and "hour(s)" in out and "the runtime is likely excessive" in out
+    res = time_estimate(2, mm, 7, 2, [0] * mm, [7] * mm, rr, rn, 1.0, list(range(mm)), 1, True, True)
+    assert res["seconds"] > 200 * 3600 and "hour(s)" in capsys.readouterr().out

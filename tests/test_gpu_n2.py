@@ -339,3 +339,58 @@ def test_sharded_on_one_gpu_equals_unsharded(lib, golden):
             for sp in shard_plans:
                 sp.close()
         plan.close()
+
+
+def test_optimizer_mirror_large_m_lower_bound_and_legacy_tile_kernel(lib):
+    """Optimizer.solve(C) (python/Optimizer.py:68-126) through the explicit-column plans: (a) at m = 150 and 300, where a
+    [0,15]^m space cannot be counted in 63 bits (the mirror used to fail for m >~ 110); (b) with a non-zero
+    lower_bound, mapped through M2_Rev like the reference (Optimizer.py:109-110); (c) at m = 1000, where the shared-memory
+    state of the warp-granular solve kernel no longer fits and the CTA-granular tile kernel takes over."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import theta_oracle as O
+    from theta_b200.optimizer import Optimizer
+    rng = np.random.default_rng(3)
+    for m, k in ((150, 5), (300, 7)):
+        P = O.synthetic_problem_n2(m, k, 1)
+        opt = Optimizer(P["r"], P["rN"], m, 2, 2)
+        for _ in range(6):
+            col = np.sort(rng.integers(0, k + 1, m))
+            C = O.column_to_matrix(col)
+            ref = O.solve_n2(C, P["r"], P["rN"])
+            got = opt.solve(C)
+            assert (ref is None) == (got is None)
+            if ref is not None:
+                assert abs(got[0][0] - ref[0][0]) <= 1e-9 and abs(got[1] - ref[1]) <= 1e-10 * abs(ref[1])
+                assert np.allclose(got[2], ref[2], rtol=1e-12, atol=0)
+    # (b) lower_bound: candidates whose root lies below / above the lower bracket end
+    P = O.synthetic_problem_n2(40, 4, 2)
+    n_none = n_ok = 0
+    for lb_ in (0.2, 0.5, 0.65, 0.8):
+        opt = Optimizer(P["r"], P["rN"], 40, 2, 2, lower_bound=lb_, upper_bound=0.9)
+        for _ in range(40):
+            col = np.sort(rng.integers(0, 5, 40))
+            C = O.column_to_matrix(col)
+            ref = O.solve_n2(C, P["r"], P["rN"], 0.9, lb_)
+            got = opt.solve(C)
+            assert (ref is None) == (got is None), (lb_, col)
+            if ref is None:
+                n_none += 1
+            else:
+                n_ok += 1
+                assert abs(got[0][0] - ref[0][0]) <= 1e-9 and abs(got[1] - ref[1]) <= 1e-10 * abs(ref[1])
+    assert n_none > 0 and n_ok > 0
+    # (c) m = 1000: solve_tiles and nll_tiles on the legacy path
+    m = 1000
+    P = O.synthetic_problem_n2(m, 6, 4)
+    plan = lib.Plan(2, P["r"], P["rN"], [0] * m, [6] * m, tiles_only=True)
+    cols = np.sort(rng.integers(0, 7, (40, m)), axis=1).astype(np.int8)
+    mu, nll, st = plan.solve_tiles(cols)
+    for i in range(0, 40, 5):
+        ref = O.solve_n2(O.column_to_matrix(cols[i]), P["r"], P["rN"])
+        assert (ref is None) == (st[i] >= 8)
+        if ref is not None:
+            assert abs(mu[i] - ref[0][0]) <= 1e-9 and abs(nll[i] - ref[1]) <= 1e-10 * abs(ref[1])
+    ok = st < 8
+    assert np.allclose(plan.nll_tiles(cols[ok], mu[ok]), nll[ok], rtol=1e-13, atol=0)
+    plan.close()

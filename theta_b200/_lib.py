@@ -31,7 +31,7 @@ class Problem(C.Structure):
     _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("tau", C.c_int32), ("reserved", C.c_int32),
                 ("r", C.POINTER(C.c_int64)), ("rN", C.POINTER(C.c_int64)),
                 ("lower", C.POINTER(C.c_int32)), ("upper", C.POINTER(C.c_int32)),
-                ("max_normal", C.c_double)]
+                ("max_normal", C.c_double), ("min_normal", C.c_double)]
 
 
 class Cand(C.Structure):
@@ -175,7 +175,7 @@ def _int_array(v, dtype):
 class Plan(object):
     """Owns a theta_plan: device tables of one problem at the do_optimization* boundary."""
 
-    def __init__(self, n, r, rN, lower, upper, tau=2, max_normal=1.0, device=None):
+    def __init__(self, n, r, rN, lower, upper, tau=2, max_normal=1.0, device=None, min_normal=0.0, tiles_only=False):
         init(device)
         self.n = int(n)
         self.m = len(r)
@@ -187,10 +187,10 @@ class Plan(object):
         self._up = _int_array(upper, np.int32)
         if not (len(self._rN) == len(self._lo) == len(self._up) == self.m):
             raise ValueError("r, rN, lower, upper must have the same length")
-        prob = Problem(self.n, self.m, self.tau, 0,
+        prob = Problem(self.n, self.m, self.tau, 1 if tiles_only else 0,
                        self._r.ctypes.data_as(C.POINTER(C.c_int64)), self._rN.ctypes.data_as(C.POINTER(C.c_int64)),
                        self._lo.ctypes.data_as(C.POINTER(C.c_int32)), self._up.ctypes.data_as(C.POINTER(C.c_int32)),
-                       self.max_normal)
+                       self.max_normal, float(min_normal))
         h = C.c_void_p()
         check(load().theta_plan_create(C.byref(prob), C.byref(h)))
         self._h = h
@@ -440,7 +440,7 @@ def optimize_n2(r, rN, lower, upper, tau=2, max_normal=1.0, rank_limit=None, cap
     if not (len(rNa) == len(lo) == len(up) == m):
         raise ValueError("r, rN, lower, upper must have the same length")
     prob = Problem(2, m, int(tau), 0, ra.ctypes.data_as(C.POINTER(C.c_int64)), rNa.ctypes.data_as(C.POINTER(C.c_int64)),
-                   lo.ctypes.data_as(C.POINTER(C.c_int32)), up.ctypes.data_as(C.POINTER(C.c_int32)), float(max_normal))
+                   lo.ctypes.data_as(C.POINTER(C.c_int32)), up.ctypes.data_as(C.POINTER(C.c_int32)), float(max_normal), 0.0)
     lo_out = np.empty(m, dtype=np.int32)
     up_out = np.empty(m, dtype=np.int32)
     while True:
@@ -564,7 +564,7 @@ class MultiGpu(object):
             n_devices = int(n_devices or device_count())
         prob = Problem(self.n, self.m, int(tau), 0, self._r.ctypes.data_as(C.POINTER(C.c_int64)),
                        self._rN.ctypes.data_as(C.POINTER(C.c_int64)), self._lo.ctypes.data_as(C.POINTER(C.c_int32)),
-                       self._up.ctypes.data_as(C.POINTER(C.c_int32)), float(max_normal))
+                       self._up.ctypes.data_as(C.POINTER(C.c_int32)), float(max_normal), 0.0)
         h = C.c_void_p()
         check(load().theta_mgpu_create(C.byref(prob), n_devices, ptr(devs) if devs is not None else None, C.byref(h)))
         self._h = h

@@ -26,6 +26,7 @@ struct N2Const {
     double K0;       // -sum r_i log(rN_i / A)
     double tau;
     double max_normal;  // 1.0 => uB = 1
+    double min_normal;  // 0.0 => lB = 0 (Optimizer's lower_bound; only the explicit-column solve honours it)
     int any_zero_rN;    // some rN_i == 0 -> every candidate is NaN/None
     int m;
 };
@@ -148,7 +149,9 @@ __device__ __forceinline__ double n2_f(const double (&nv)[KV], double S1, double
 //   zero_r_c0 : some interval with c_i == 0 has r_i == 0 (0/0 at x = lB = 0 -> NaN -> None)
 //   x0        : warm start for the root (<= 0: none)
 // n2_root: everything up to mu (brenth + M2); returns false when the reference returns None.
-template <int KV>
+// LB: honour k.min_normal (Optimizer's lower_bound -> lB = M2_Rev(C_w, lower_bound), Optimizer.py:109-110).  RunTHetA
+// never sets it, so the search kernels instantiate LB = false and keep lB = 0 hard-wired.
+template <int KV, bool LB = false>
 __device__ __forceinline__ bool n2_root(const double (&R)[KV], double S1, bool zero_r_c0, const N2Const& k, double x0,
                                         SolveOut& o) {
     o.x = 0.0;
@@ -168,10 +171,15 @@ __device__ __forceinline__ bool n2_root(const double (&R)[KV], double S1, bool z
         nv[v] = R[v] * ev[v];
     }
     // bracket [lB, uB] = [0, 1] or [0, M2_Rev(max_normal)] (Optimizer.py:109-112, 228-231)
-    double uB = 1.0;
+    double uB = 1.0, lB = 0.0;
     // f(lB = 0) up to the positive factor 1/A: the v = 0 group has denominator 0 -> -inf when it carries reads
     double f0;
-    if (nv[0] != 0.0) {
+    if (LB && k.min_normal != 0.0) {
+        const double numer = -k.min_normal * k.S0;
+        const double denom = (k.min_normal - 1.0) * S1 + numer;
+        lB = numer / denom;
+        f0 = n2_f<KV>(nv, S1, k.A, lB);
+    } else if (nv[0] != 0.0) {
         f0 = -INFINITY;
     } else {
         double s = 0.0;
@@ -199,7 +207,7 @@ __device__ __forceinline__ bool n2_root(const double (&R)[KV], double S1, bool z
     double x;
     int status = THETA_ST_OK;
     if (f0 == 0.0) {  // scipy brenth: f(a)==0 -> return a (flat likelihood, Q17)
-        x = 0.0;
+        x = lB;
         status = THETA_ST_ROOT_LB;
     } else if (fU == 0.0) {
         x = uB;
@@ -214,7 +222,7 @@ __device__ __forceinline__ bool n2_root(const double (&R)[KV], double S1, bool z
         // below THETA_NEWTON_PRED * |x|  (the reference's own brenth stops at 2e-12 absolute, Optimizer.py:118).
         // Cubic convergence makes two evaluations enough from a warm start within ~1e-2, which keeps the lanes
         // of a warp in step.
-        double lo = 0.0, hi = uB;
+        double lo = lB, hi = uB;
         const bool rising = f0 < 0.0;
         x = (x0 > lo && x0 < hi) ? x0 : 0.5 * (lo + hi);
         int it = 0;
@@ -295,10 +303,10 @@ __device__ __forceinline__ double n2_l2_approx(const double (&R)[KV], double S1,
     return fma(-0.6931471805599453094, acc, k.K0);
 }
 
-template <int KV>
+template <int KV, bool LB = false>
 __device__ __forceinline__ void n2_solve(const double (&R)[KV], double S1, bool zero_r_c0, const N2Const& k, double x0,
                                          SolveOut& o, const double2* __restrict__ LT = nullptr) {
-    if (n2_root<KV>(R, S1, zero_r_c0, k, x0, o)) o.nll = n2_l2<KV>(R, S1, o.mu, k, LT);
+    if (n2_root<KV, LB>(R, S1, zero_r_c0, k, x0, o)) o.nll = n2_l2<KV>(R, S1, o.mu, k, LT);
 }
 
 }  // namespace theta

@@ -404,7 +404,7 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
     for (int i = 0; i < m; ++i)
         if (pl->r[i] > 0 && pl->rN[i] > 0) K0 -= (long double)pl->r[i] * logl((long double)pl->rN[i] / A);
     pl->kc.A = (double)A; pl->kc.S0 = (double)(A * p->tau); pl->kc.Rtot = (double)Rt; pl->kc.K0 = (double)K0;
-    pl->kc.tau = (double)p->tau; pl->kc.max_normal = p->max_normal; pl->kc.any_zero_rN = zero_rN; pl->kc.m = m;
+    pl->kc.tau = (double)p->tau; pl->kc.max_normal = p->max_normal; pl->kc.min_normal = p->min_normal; pl->kc.any_zero_rN = zero_rN; pl->kc.m = m;
     // tables
     pl->layout = TableLayout(m, KT);
     pl->h_tables.assign(pl->layout.bytes, 0);
@@ -447,8 +447,12 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
             sw[q] = (uint64_t)acc;
         }
     }
-    if (overflow) { set_error("candidate count exceeds 2^63"); delete pl; return THETA_ERR_OVERFLOW; }
-    {
+    // THETA_PLAN_TILES_ONLY: the plan serves explicit columns only (Optimizer.solve / CalcAllC): it needs r, rN, the
+    // prefix tables and KT, not the count tables -- so a space too large to count (m >~ 110 with bounds [0, 15]) is fine
+    const bool tiles_only = (p->reserved & THETA_PLAN_TILES_ONLY) != 0;
+    if (overflow && !tiles_only) { set_error("candidate count exceeds 2^63"); delete pl; return THETA_ERR_OVERFLOW; }
+    if (overflow) { pl->count = 0; }
+    else {
         const uint64_t* swK = SW + (size_t)(KT - 1) * (m + 2);
         pl->count = (empty || qlo[KT - 1] > qhi[KT - 1]) ? 0 : swK[qlo[KT - 1]];
         if (empty) pl->count = 0;

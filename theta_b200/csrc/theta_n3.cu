@@ -749,7 +749,7 @@ int theta_n3_tile_info(const theta_plan* pl, uint8_t* ra, uint8_t* rb, int* n_ro
     *n_rows = s->NR;
     *kc = theta::N2Const{};
     kc->A = s->kc.A; kc->S0 = s->kc.tau * s->kc.A; kc->Rtot = s->kc.Rtot; kc->K0 = s->kc.K0; kc->tau = s->kc.tau;
-    kc->max_normal = 1.0; kc->any_zero_rN = s->kc.any_zero_rN; kc->m = s->kc.m;
+    kc->max_normal = 1.0; kc->min_normal = 0.0; kc->any_zero_rN = s->kc.any_zero_rN; kc->m = s->kc.m;
     return THETA_OK;
 }
 

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kRows) tiles_n2_kernel(const TileParams p) {
 #pragma unroll
                 for (int v = 0; v <= KT; ++v) R[v] = h[v * kRows];
                 SolveOut o;
-                n2_solve<KT + 1>(R, s1, z0, kc, -1.0, o);
+                n2_solve<KT + 1, true>(R, s1, z0, kc, -1.0, o);
                 if (bad) { o.status = THETA_ST_NONE_NAN; o.mu = 0.0; o.nll = 0.0; }
                 p.mu_out[row] = o.mu;
                 p.nll_out[row] = o.nll;
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) solve_tiles_kernel(const Til
         }
         if (live) {
             SolveOut so;
-            n2_solve<KT + 1>(R, s1, z0, kc, -1.0, so);
+            n2_solve<KT + 1, true>(R, s1, z0, kc, -1.0, so);
             if (bad) { so.status = THETA_ST_NONE_NAN; so.mu = 0.0; so.nll = 0.0; }
             p.mu_out[row] = so.mu;
             p.nll_out[row] = so.nll;

@@ -7,17 +7,29 @@ import numpy as np
 
 from . import _lib
 
+_KT = (2, 3, 4, 5, 6, 7, 8, 10, 12, 15)  # level-count templates of the solve kernels (theta_n2.cu::pick_KT)
+
 
 class Optimizer(object):
     def __init__(self, r, rN, m, n, tau, lower_bound=0, upper_bound=1):
-        if lower_bound != 0:
-            raise NotImplementedError("lower_bound != 0 is never used by RunTHetA (RunTHetA.py:133,183)")
         self.r, self.rN, self.m, self.n, self.tau = r, rN, m, n, tau
-        self.lB, self.uB = lower_bound, upper_bound
-        self._plan = None
-        if n == 2:
-            # bounds only size the kernels' level tables; solve() accepts any column within [0, THETA_MAX_COPY]
-            self._plan = _lib.Plan(2, r, rN, [0] * m, [15] * m, tau=tau, max_normal=float(upper_bound))
+        self.lB, self.uB = lower_bound, upper_bound  # normal-admixture bracket (Optimizer.py:43,109-112); n=2 only (Q15)
+        self._plan = None    # n = 3
+        self._plans = {}     # n = 2: one explicit-column plan per level-count template, made when first needed
+        _lib.init()
+
+    def _plan_for(self, kmax):
+        kt = next((o for o in _KT if kmax <= o), None)
+        if kt is None:
+            raise ValueError("tumour copy numbers must be integers in [0, 15]")
+        pl = self._plans.get(kt)
+        if pl is None:
+            # explicit-column plan: only sizes the kernels' tables, so it works for any m (the number of monotone
+            # columns in [0, kt]^m is never counted -- THETA_PLAN_TILES_ONLY)
+            pl = _lib.Plan(2, self.r, self.rN, [0] * self.m, [kt] * self.m, tau=self.tau, max_normal=float(self.uB),
+                           min_normal=float(self.lB), tiles_only=True)
+            self._plans[kt] = pl
+        return pl
 
     def solve(self, C):
         C = np.asarray(C, dtype=np.float64)
@@ -32,7 +44,7 @@ class Optimizer(object):
         col = C[:, 1]
         if np.any(col != np.floor(col)) or col.min() < 0 or col.max() > 15:
             raise ValueError("tumour copy numbers must be integers in [0, 15]")
-        mu, nll, st = self._plan.solve_tiles(col.astype(np.int8)[None, :])
+        mu, nll, st = self._plan_for(int(col.max())).solve_tiles(col.astype(np.int8)[None, :])
         if st[0] >= _lib.ST_NONE_SIGN:
             return None  # Optimizer.py:119-121
         mu0 = np.float64(mu[0])

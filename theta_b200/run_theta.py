@@ -18,6 +18,7 @@ import sys
 
 from . import _lib, pipeline
 from .search import do_optimization, do_optimization_single
+from .time_estimate import time_estimate
 
 
 def parse_arguments(argv=None):
@@ -115,18 +116,12 @@ def run_fixed_N(n, a, intervals, resultsfile=None, argv=None):
     boundsfile = pipeline.write_out_bounds(directory, prefix, a.QUERY_FILE, ub_out, lb_out, n, order if choose else None)
     if a.BOUNDS_ONLY:
         sys.exit(0)
-    # TimeEstimate.time_estimate (python/TimeEstimate.py:40-89): the exact count replaces the CPU timing loop
-    print("Estimating time...")
-    if n == 3 and m > 30 and not a.FORCE:
-        print("\tWARNING: With n=3 and", m, "intervals, the runtime would likely be excessive. Try reducing the number of "
-              "intervals below 25. Run with --FORCE to continue.")
-        sys.exit(1)
-    if n == 2:
-        plan = _lib.Plan(2, r, rN, lower_bounds, upper_bounds, tau=tau, max_normal=max_normal)
-        print("\tCandidate copy number profiles:", plan.count())
-        plan.close()
+    # TimeEstimate.time_estimate (python/TimeEstimate.py:40-89): same counts, messages and aborts; the per-candidate
+    # time is measured on the GPU instead of on 100 / 20 CPU solves
+    time_estimate(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_normal, sorted_index, a.NUM_PROCESSES,
+                  not a.NO_MULTI_EVENT, a.FORCE)
     print("Performing optimization...")
-    pre = os.path.join(directory, prefix)
+    pre = prefix  # RunTHetA.py:307-308: --GET_VALUES writes <prefix>.likelihoods in the working directory
     if a.NUM_PROCESSES == 1:
         best = do_optimization_single(n, m, k, tau, lower_bounds, upper_bounds, r, rN, max_normal, sorted_index,
                                       not a.NO_MULTI_EVENT, a.GET_VALUES, prefix=pre)

@@ -182,9 +182,11 @@ def do_optimization_n3(m, k, tau, lower_bounds, upper_bounds, r, rN, sorted_inde
 
 
 def dump_values_n3(plan, rows, path):
-    """--GET_VALUES for n=3 (RunTHetA.py:210-215 writes column 1 of C, mu[0], likelihood)."""
+    """--GET_VALUES for n=3 (RunTHetA.py:188-215): one line per solved candidate of the stream the driver folds -- the
+    all-[tau,0,0] first matrix (Q2), then the candidates in enumeration order -- with column 1 of C, mu[0], likelihood."""
     paths = plan.enumerate_n3()
-    mu, _, nll, st, _ = plan.solve_rows(paths)
+    paths = np.concatenate([np.zeros((1, plan.m), dtype=np.uint8), paths]) if len(paths) else np.zeros((1, plan.m), dtype=np.uint8)
+    mu, _, nll, st, _ = plan.solve_rows(paths, mode=1)
     with open(path, "w") as f:
         for i in range(len(paths)):
             if st[i] >= _lib.ST_NONE_SIGN:
