@@ -380,6 +380,32 @@ def gen_edge(R):
     _dump("edge_n2.json", out)
 
 
+def gen_bounds_edge(R):
+    """n=2 spaces whose lower bound exceeds the upper bound at some intervals: the reference never checks its
+    start vector against the upper bounds -- Enumerator._generate_next_C_2 (Enumerator.py:119-152) starts from the lower
+    bounds and simply never increments a position that is already at or above its upper bound -- so such a space is NOT
+    empty.  Whole streams + best lists through the live do_optimization_single."""
+    cases = []
+    for m, lb, ub, seed in ((6, [0, 0, 2, 2, 3, 3], [2, 2, 1, 3, 2, 4], 1), (5, [1, 1, 1, 3, 3], [0, 2, 2, 2, 3], 2),
+                            (4, [2, 2, 2, 2], [1, 1, 1, 1], 3)):
+        r, rN, _ = O.synthetic(m, 2, 4, seed)
+        r, rN, si = O.sort_r(rN, r)
+        R.RunTHetA.pre = "/tmp/theta_golden_bedge"
+        lb_in, ub_in = lb[:], ub[:]
+        with _quiet():
+            best = R.RunTHetA.do_optimization_single(2, m, 4, 2, lb_in, ub_in, r, rN, 1.0, si, True, True)
+        lines = []
+        with open("/tmp/theta_golden_bedge.likelihoods") as f:
+            for line in f:
+                cs, mu0, nll = line.rstrip("\n").split("\t")
+                lines.append([cs, float(mu0), float(nll)])
+        cases.append(dict(m=m, r=r, rN=rN, lower=lb, upper=ub, lower_after=lb_in, upper_after=ub_in, sorted_index=si,
+                          dump=lines, best=[dict(C=np.asarray(b[0]).tolist(), mu=[float(b[1][0]), float(b[1][1])],
+                                                 nll=float(b[2]), vals=[float(v) for v in b[3]]) for b in best]))
+        print("bounds edge", lb, ub, "dump lines", len(lines), "best", len(best))
+    _dump("bounds_edge_n2.json", cases)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="kat,edge,n2_small,synth_n2,n3_small,synth_n3,config1")
@@ -402,6 +428,8 @@ def main():
         gen_synth_n3(R)
     if "n3_rankdef" in todo:
         gen_n3_rankdef(R)
+    if "bounds_edge" in todo:
+        gen_bounds_edge(R)
     if "config1" in todo:
         gen_config1(R)
     if "config1_cli" in todo:

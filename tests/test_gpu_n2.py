@@ -394,3 +394,27 @@ def test_optimizer_mirror_large_m_lower_bound_and_legacy_tile_kernel(lib):
     ok = st < 8
     assert np.allclose(plan.nll_tiles(cols[ok], mu[ok]), nll[ok], rtol=1e-13, atol=0)
     plan.close()
+
+
+def test_lower_bound_above_upper_bound_follows_the_reference(lib, golden, tmp_path):
+    """Spaces with lower > upper at some intervals are not empty in the reference (its odometer starts at the lower
+    bounds and never checks them against the upper ones): same candidate stream (--GET_VALUES dump of the live
+    reference, first matrix twice) and the same best list."""
+    from theta_b200.search import do_optimization_single, dump_values_n2
+    for case in golden("bounds_edge_n2.json"):
+        plan = lib.Plan(2, case["r"], case["rN"], case["lower"], case["upper"])
+        out = str(tmp_path / "be.likelihoods")
+        dump_values_n2(plan, out)
+        with open(out) as f:
+            got = [ln.rstrip("\n").split("\t") for ln in f]
+        assert [g[0] for g in got] == [d[0] for d in case["dump"]]
+        for g, d in zip(got, case["dump"]):
+            assert abs(float(g[1]) - d[1]) <= 1e-9 and abs(float(g[2]) - d[2]) <= 1e-10 * abs(d[2])
+        plan.close()
+        lo, up = list(case["lower"]), list(case["upper"])
+        best = do_optimization_single(2, case["m"], 4, 2, lo, up, case["r"], case["rN"], 1.0, case["sorted_index"], True, False)
+        assert lo == case["lower_after"] and up == case["upper_after"]  # Q16: monotonised in place, nothing else
+        assert len(best) == len(case["best"])
+        for b, g in zip(best, case["best"]):
+            assert np.array_equal(b[0], np.array(g["C"]))
+            assert abs(b[1][0] - g["mu"][0]) <= 1e-9 and abs(b[2] - g["nll"]) <= 1e-10 * g["nll"]

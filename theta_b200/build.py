@@ -58,10 +58,13 @@ def build(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs
+    # link to a temporary name and rename into place: several ranks calling build() at once never see a half-written .so
+    tmp = "%s.%d.tmp" % (LIB, os.getpid())
+    cmd = [nvcc, "-shared", "-cudart", "static", "-o", tmp] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    os.replace(tmp, LIB)
     return LIB
 
 

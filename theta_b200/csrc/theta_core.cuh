@@ -335,6 +335,19 @@ void cache_release();  // returns every cached block to the driver
 cudaError_t logtab_device(double2** out);
 }  // namespace theta
 
+// scope guards: blocks and events are returned on every exit path (THETA_CUDA returns early)
+struct DevBlock {
+    void* p = nullptr;
+    ~DevBlock() { dfree(p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+    cudaError_t alloc(size_t bytes) { return dmalloc_bytes(&p, bytes); }
+};
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    cudaError_t create() { cudaError_t e = cudaEventCreate(&a); return e == cudaSuccess ? cudaEventCreate(&b) : e; }
+};
+
 #define THETA_CUDA(expr)                                                        \
     do {                                                                        \
         cudaError_t _e = (expr);                                                \

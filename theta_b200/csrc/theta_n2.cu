@@ -378,13 +378,25 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
     for (int i = m - 2; i >= 0; --i) if (pl->upper[i] > pl->upper[i + 1]) pl->upper[i] = pl->upper[i + 1];
     int K = 0;
     bool empty = false;
+    // n=2: the reference never checks its start vector (the lower bounds) against the upper bounds --
+    // Enumerator._generate_next_C_2 (Enumerator.py:119-152) just never increments a position that is already at or
+    // above its upper bound -- so where lower > upper the position is pinned to its lower bound: effective upper =
+    // max(upper, lower) (golden: tests/golden/bounds_edge_n2.json).  The bounds reported back stay the monotonised ones.
+    std::vector<int32_t> ue(pl->upper);
     for (int i = 0; i < m; ++i) {
         if (pl->lower[i] < 0) { set_error("negative lower bound"); delete pl; return THETA_ERR_INVALID; }
-        if (pl->lower[i] > pl->upper[i]) empty = true;
-        K = std::max(K, pl->upper[i]);
+        if (pl->lower[i] > pl->upper[i]) {
+            if (p->n == 2) ue[i] = pl->lower[i];
+            else empty = true;
+        }
+        K = std::max(K, ue[i]);
         if (pl->r[i] < 0 || pl->rN[i] < 0) { set_error("negative read count"); delete pl; return THETA_ERR_INVALID; }
     }
-    if (K > THETA_MAX_COPY) { set_error("copy number bound %d exceeds THETA_MAX_COPY=%d", K, THETA_MAX_COPY); delete pl; return THETA_ERR_UNSUPPORTED; }
+    if (K > THETA_MAX_COPY) {
+        set_error("copy number bound %d exceeds THETA_MAX_COPY=%d (n=3: 7): tighten the bounds (--MAX_K, interval selection)", K, THETA_MAX_COPY);
+        delete pl;
+        return THETA_ERR_UNSUPPORTED;
+    }
     pl->K = K;
     if (p->n == 3) {
         if (empty) { set_error("No valid Copy Number Profiles exist for these intervals within the bounds specified"); delete pl; return THETA_ERR_EMPTY; }
@@ -427,7 +439,7 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
     }
     for (int v = 1; v <= KT; ++v) {
         int lo = 0, hi = 0;
-        for (int i = 0; i < m; ++i) { if (pl->lower[i] >= v) ++lo; if (pl->upper[i] >= v) ++hi; }
+        for (int i = 0; i < m; ++i) { if (pl->lower[i] >= v) ++lo; if (ue[i] >= v) ++hi; }
         qlo[v - 1] = lo; qhi[v - 1] = hi;
     }
     // W_1(q) = 1;  W_v(q) = SW_{v-1}[max(q, qlo_{v-1})]   (0 beyond qhi_{v-1})
@@ -1072,11 +1084,12 @@ extern "C" int theta_eval_ranks_n2(theta_plan* pl, const uint64_t* ranks_host, i
     if (count <= 0) return THETA_OK;
     for (int64_t i = 0; i < count; ++i)
         if (ranks_host[i] >= pl->count) { set_error("rank %llu out of range", (unsigned long long)ranks_host[i]); return THETA_ERR_INVALID; }
-    uint64_t* d_ranks = nullptr; theta_cand* d_out = nullptr; double* d_vals = nullptr;
     const int m = pl->m;
-    THETA_CUDA(theta::dmalloc(&d_ranks, sizeof(uint64_t) * count));
-    THETA_CUDA(theta::dmalloc(&d_out, sizeof(theta_cand) * count));
-    if (vals_host) THETA_CUDA(theta::dmalloc(&d_vals, sizeof(double) * count * m));
+    theta::DevBlock b_ranks, b_out, b_vals;
+    THETA_CUDA(b_ranks.alloc(sizeof(uint64_t) * count));
+    THETA_CUDA(b_out.alloc(sizeof(theta_cand) * count));
+    if (vals_host) THETA_CUDA(b_vals.alloc(sizeof(double) * count * m));
+    uint64_t* d_ranks = b_ranks.as<uint64_t>(); theta_cand* d_out = b_out.as<theta_cand>(); double* d_vals = b_vals.as<double>();
     THETA_CUDA(cudaMemcpy(d_ranks, ranks_host, sizeof(uint64_t) * count, cudaMemcpyHostToDevice));
     const int grid = (int)((count + kBlock - 1) / kBlock);
     THETA_KT_DISPATCH(pl->KT, {
@@ -1087,6 +1100,5 @@ extern "C" int theta_eval_ranks_n2(theta_plan* pl, const uint64_t* ranks_host, i
     THETA_CUDA(cudaGetLastError());
     THETA_CUDA(cudaMemcpy(out_host, d_out, sizeof(theta_cand) * count, cudaMemcpyDeviceToHost));
     if (vals_host) THETA_CUDA(cudaMemcpy(vals_host, d_vals, sizeof(double) * count * m, cudaMemcpyDeviceToHost));
-    theta::dfree(d_ranks); theta::dfree(d_out); theta::dfree(d_vals);
     return THETA_OK;
 }

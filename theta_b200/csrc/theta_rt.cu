@@ -198,11 +198,12 @@ extern "C" int theta_fp64_peak(double* gflops, void* stream) {
     THETA_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int block = 256, grid = sms * 8, iters = 1 << 14;
-    double* d = nullptr;
-    THETA_CUDA(theta::dmalloc(&d, sizeof(double) * (size_t)grid * block));
-    cudaEvent_t e0, e1;
-    THETA_CUDA(cudaEventCreate(&e0));
-    THETA_CUDA(cudaEventCreate(&e1));
+    theta::DevBlock blk;
+    THETA_CUDA(blk.alloc(sizeof(double) * (size_t)grid * block));
+    double* d = blk.as<double>();
+    theta::EventPair ev;
+    THETA_CUDA(ev.create());
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         THETA_CUDA(cudaEventRecord(e0, st));
@@ -214,9 +215,6 @@ extern "C" int theta_fp64_peak(double* gflops, void* stream) {
         const double fl = 2.0 * 8.0 * (double)iters * (double)grid * block;
         if (rep > 0 && ms > 0) best = fmax(best, fl / (ms * 1e-3) / 1e9);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    theta::dfree(d);
     THETA_CUDA(cudaGetLastError());
     *gflops = best;
     return THETA_OK;
