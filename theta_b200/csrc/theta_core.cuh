@@ -333,7 +333,6 @@ inline cudaError_t hmalloc(T** p, size_t bytes) { return hmalloc_bytes(reinterpr
 void cache_release();  // returns every cached block to the driver
 // the fast_log table of the current device (uploaded on first use, kept until theta_shutdown)
 cudaError_t logtab_device(double2** out);
-}  // namespace theta
 
 // scope guards: blocks and events are returned on every exit path (THETA_CUDA returns early)
 struct DevBlock {
@@ -347,6 +346,7 @@ struct EventPair {
     ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
     cudaError_t create() { cudaError_t e = cudaEventCreate(&a); return e == cudaSuccess ? cudaEventCreate(&b) : e; }
 };
+}  // namespace theta
 
 #define THETA_CUDA(expr)                                                        \
     do {                                                                        \
