@@ -161,6 +161,9 @@ int theta_search_n2_pass2_dev(theta_plan* plan, const double* global_min_dev, do
 int theta_search_n2_pass2_enqueue(theta_plan* plan, const double* global_min_dev, double prior_min, void* out_dev,
                                   uint64_t cap, void* stream);
 int theta_search_n2_async_done(theta_plan* plan, const unsigned long long* status_host);
+/* Host-side bookkeeping of theta_search_n2_pass1_begin for a step whose device work is replayed from a CUDA graph
+ * captured from the very same call sequence (theta_search_n2_dist does this from the second identical step on). */
+int theta_search_n2_graph_replay(theta_plan* plan, uint64_t rank_begin, uint64_t rank_end, void* stream);
 int theta_filter_records(theta_cand* recs, uint64_t n, double prior_min, double near_thr, uint64_t* n_out);
 int theta_search_stats_get(const theta_plan* plan, theta_search_stats* stats);
 /* Single-shard convenience: pass1 + pass2 with global_min = local_min, prior_min = +inf. */
@@ -245,6 +248,12 @@ typedef struct theta_comm theta_comm; /* one rank's communicator + exchange buff
 int theta_nccl_unique_id(uint8_t* id128 /* [128] */);
 int theta_comm_create(int32_t rank, int32_t world, const uint8_t* id128 /* NULL iff world == 1 */, theta_comm** out);
 void theta_comm_destroy(theta_comm* comm);
+/* One process per GPU, optional: share the ranks' exchange areas through CUDA IPC so that the two collectives of an n=2
+ * step run as remote stores over NVLink peer memory inside our own kernels instead of NCCL calls.  Every rank publishes
+ * theta_comm_ipc_handle (128 bytes), the launcher all-gathers them, every rank calls theta_comm_open_peers.  Without this
+ * (or with THETA_EXCHANGE=nccl, or when the GPUs cannot map each other) the step uses ncclAllReduce / ncclAllGather. */
+int theta_comm_ipc_handle(theta_comm* comm, uint8_t* handle128);
+int theta_comm_open_peers(theta_comm* comm, const uint8_t* handles /* [world][128] */);
 /* One sharded search step on this rank; every rank receives the union of the records, in enumeration order.
  * n=2: records = what the fold replay needs (theta_filter_records).  n=3: every candidate within `window` of the
  * global minimum (extra_min: NLL of the all-[tau,0,0] pseudo candidate, folded into the minimum), flags index

@@ -85,6 +85,7 @@ SYMBOLS = {
                                             C.POINTER(C.c_double), _VP]),
     "theta_search_n2_pass2_enqueue": (C.c_int, [_VP, _VP, C.c_double, _VP, C.c_uint64, _VP]),
     "theta_search_n2_async_done": (C.c_int, [_VP, _VP]),
+    "theta_search_n2_graph_replay": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP]),
     "theta_filter_records": (C.c_int, [_VP, C.c_uint64, C.c_double, C.c_double, C.POINTER(C.c_uint64)]),
     "theta_search_stats_get": (C.c_int, [_VP, C.POINTER(SearchStats)]),
     "theta_search_n2": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
@@ -95,6 +96,8 @@ SYMBOLS = {
     "theta_nccl_unique_id": (C.c_int, [_VP]),
     "theta_comm_create": (C.c_int, [C.c_int32, C.c_int32, _VP, C.POINTER(_VP)]),
     "theta_comm_destroy": (None, [_VP]),
+    "theta_comm_ipc_handle": (C.c_int, [_VP, _VP]),
+    "theta_comm_open_peers": (C.c_int, [_VP, _VP]),
     "theta_search_n2_dist": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_double), C.POINTER(C.c_uint64), _VP]),
     "theta_search_n3_dist": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint64, C.c_double, C.c_double, _VP, _VP, C.c_uint64,
@@ -497,7 +500,15 @@ class Comm(object):
         if rank == 0:
             t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
         dist.broadcast(t, src=0)
-        return cls(rank, world, bytes(t.cpu().numpy().tobytes()), device=torch.cuda.current_device())
+        c = cls(rank, world, bytes(t.cpu().numpy().tobytes()), device=torch.cuda.current_device())
+        # exchange areas over NVLink peer memory (CUDA IPC): handles all-gathered once through torch
+        mine = np.zeros(128, dtype=np.uint8)
+        check(load().theta_comm_ipc_handle(c._h, ptr(mine)))
+        hs = torch.zeros(world * 128, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(hs, torch.from_numpy(mine).to(dev))
+        allh = np.ascontiguousarray(hs.cpu().numpy())
+        check(load().theta_comm_open_peers(c._h, ptr(allh)))
+        return c
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None

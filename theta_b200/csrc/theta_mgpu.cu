@@ -16,8 +16,11 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -79,6 +82,80 @@ constexpr int kStatusWordsX = 32;  // theta_n2.cu: status block of the asynchron
 constexpr int kStEmitted = 8 + 3;
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Exchange over NVLink peer memory (the default when every GPU can map every other): the two collectives of a step are
+// 8 bytes and ~12 KB per rank, i.e. pure latency, and as NCCL calls they were most of what an 8-GPU step added to a
+// 1-GPU step (two kernel launches with their protocol set-up per rank, completion visible to the host only after NCCL's
+// own bookkeeping).  Here each is ONE tiny kernel of ours: every rank stores its value / its record block straight into
+// every peer's exchange area (remote stores through NVSwitch), publishes a step tag with release semantics, and spins on
+// the tags the peers publish in its own area.  Tags are the step number (monotone), so nothing is ever reset; a spin that
+// exceeds ~10 s sets an error word instead of hanging the GPU.  ncclAllReduce / ncclAllGather remain the fallback
+// (THETA_EXCHANGE=nccl, no peer access, or a record block that outgrows the fixed peer slot).
+constexpr int kMaxPeers = 16;
+constexpr size_t kPeerRecs = 1024;  // records per rank that fit the fixed peer slot
+struct XArea {                      // one per rank, device memory, zero-initialised
+    struct { double val; unsigned long long tag; } mins[kMaxPeers];
+    unsigned long long rtag[kMaxPeers];
+    unsigned long long cur;         // step number of the exchange in flight (written by peer_min_kernel only)
+    unsigned long long err;
+};
+struct PeerTable {
+    XArea* area[kMaxPeers];
+    unsigned char* recv[kMaxPeers];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want, unsigned long long* err) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < want) {
+        if (clock64() - t0 > 20000000000LL) { *err = 1ULL; return false; }
+    }
+    return true;
+}
+
+// all-reduce(min) of one double per rank: in place on *val
+__global__ void peer_min_kernel(PeerTable T, int G, int rank, double* val) {
+    const int lane = threadIdx.x;
+    XArea* mine = T.area[rank];
+    const unsigned long long seq = mine->cur + 1ULL;
+    __syncwarp();
+    if (lane == 0) mine->cur = seq;
+    const double v = *val;
+    if (lane < G) {
+        XArea* peer = T.area[lane];
+        peer->mins[rank].val = v;
+        __threadfence_system();
+        st_release_sys(&peer->mins[rank].tag, seq);
+    }
+    double x = INFINITY;
+    if (lane < G && spin_until(&mine->mins[lane].tag, seq, &mine->err)) x = mine->mins[lane].val;
+    for (int o = 16; o; o >>= 1) x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
+    if (lane == 0) *val = x;
+}
+
+// all-gather of one block of `bytes` per rank: block b of the grid serves peer b
+__global__ void peer_gather_kernel(PeerTable T, int G, int rank, const unsigned char* send, size_t bytes, size_t slot) {
+    const int b = blockIdx.x;
+    XArea* mine = T.area[rank];
+    const unsigned long long seq = mine->cur;
+    const uint4* src = reinterpret_cast<const uint4*>(send);
+    uint4* dst = reinterpret_cast<uint4*>(T.recv[b] + (size_t)rank * slot);
+    for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys(&T.area[b]->rtag[rank], seq);
+        spin_until(&mine->rtag[b], seq, &mine->err);  // ... and peer b's block has arrived here
+    }
+}
+
 struct theta_comm {
     ncclComm_t comm = nullptr;  // NULL: a single shard, no collective
     int rank = 0, world = 1, device = 0;
@@ -89,6 +166,22 @@ struct theta_comm {
     unsigned char* h_recv = nullptr;      // pinned copy of d_recv
     size_t block_bytes = 0;
     uint64_t xcap = 0;                    // n=2: records per exchange block
+    cudaEvent_t dbg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // THETA_DEBUG=1: phase times of a step
+    // CUDA graph of the n=2 step (pass 1, min reduction, all-reduce, scan, pass 2, all-gather, D2H): a repeated search of
+    // the same plan and range costs one graph launch instead of ~20 driver calls per rank -- with 8 host threads (or 8
+    // ranks) issuing them, those calls and their jitter were half of a 1-ms step
+    cudaGraphExec_t g_exec = nullptr;
+    uint64_t g_key[5] = {0, 0, 0, 0, 0};
+    int g_seen = 0;
+    bool g_disabled = false;              // a capture failed once: stay on the eager path
+    // peer-memory exchange (see above)
+    XArea* x_area = nullptr;
+    unsigned char* x_recv = nullptr;      // [world] slots of x_slot bytes
+    size_t x_slot = 0;
+    PeerTable peers{};
+    bool peer_ok = false;
+    unsigned long long* h_err = nullptr;  // pinned
+    cudaStream_t st_own = nullptr;        // used when the caller passes the legacy default stream (which cannot be captured)
 };
 
 static int comm_buffers(theta_comm* c, size_t block_bytes) {
@@ -108,7 +201,52 @@ static int comm_init_common(theta_comm* c) {
     THETA_CUDA(theta::dmalloc(&c->d_min, sizeof(double) * 2));
     THETA_CUDA(theta::hmalloc(&c->h_min, sizeof(double) * 2));
     c->xcap = 256;
+    if (c->world > 1 && c->world <= kMaxPeers) {
+        c->x_slot = sizeof(unsigned long long) * kStatusWordsX + sizeof(theta_cand) * kPeerRecs;
+        THETA_CUDA(theta::dmalloc(&c->x_area, sizeof(XArea)));
+        THETA_CUDA(theta::dmalloc(&c->x_recv, c->x_slot * c->world));
+        THETA_CUDA(theta::hmalloc(&c->h_err, sizeof(unsigned long long)));
+        THETA_CUDA(cudaMemset(c->x_area, 0, sizeof(XArea)));
+    }
     return comm_buffers(c, sizeof(unsigned long long) * kStatusWordsX + sizeof(theta_cand) * c->xcap);
+}
+
+static bool peer_exchange_wanted() {
+    const char* e = getenv("THETA_EXCHANGE");
+    return !(e && (e[0] == 'n' || e[0] == 'N'));  // "nccl" forces the NCCL collectives
+}
+
+// One process per GPU: the exchange areas are shared through CUDA IPC.  handle128 = {area handle (64 B), recv handle (64 B)}.
+extern "C" int theta_comm_ipc_handle(theta_comm* c, uint8_t* handle128) {
+    if (!c || !handle128) { set_error("null argument"); return THETA_ERR_INVALID; }
+    std::memset(handle128, 0, 128);
+    if (!c->x_area) return THETA_OK;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t ha, hr;
+    THETA_CUDA(cudaIpcGetMemHandle(&ha, c->x_area));
+    THETA_CUDA(cudaIpcGetMemHandle(&hr, c->x_recv));
+    std::memcpy(handle128, &ha, 64);
+    std::memcpy(handle128 + 64, &hr, 64);
+    return THETA_OK;
+}
+
+extern "C" int theta_comm_open_peers(theta_comm* c, const uint8_t* handles /* [world][128] */) {
+    if (!c || !handles) { set_error("null argument"); return THETA_ERR_INVALID; }
+    if (!c->x_area || !peer_exchange_wanted()) return THETA_OK;
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) { c->peers.area[r] = c->x_area; c->peers.recv[r] = c->x_recv; continue; }
+        cudaIpcMemHandle_t ha, hr;
+        std::memcpy(&ha, handles + (size_t)r * 128, 64);
+        std::memcpy(&hr, handles + (size_t)r * 128 + 64, 64);
+        void *pa = nullptr, *pr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&pa, ha, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pr, hr, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); c->peer_ok = false; return THETA_OK; }  // no peer mapping: NCCL path
+        c->peers.area[r] = static_cast<XArea*>(pa);
+        c->peers.recv[r] = static_cast<unsigned char*>(pr);
+    }
+    c->peer_ok = true;
+    return THETA_OK;
 }
 
 extern "C" int theta_nccl_unique_id(uint8_t* id128) {
@@ -143,8 +281,11 @@ extern "C" int theta_comm_create(int32_t rank, int32_t world, const uint8_t* id1
 
 extern "C" void theta_comm_destroy(theta_comm* c) {
     if (!c) return;
+    if (c->g_exec) cudaGraphExecDestroy(c->g_exec);
+    if (c->st_own) cudaStreamDestroy(c->st_own);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     theta::dfree(c->d_min); theta::hfree(c->h_min); theta::dfree(c->d_send); theta::dfree(c->d_recv); theta::hfree(c->h_recv);
+    theta::dfree(c->x_area); theta::dfree(c->x_recv); theta::hfree(c->h_err);  // (IPC mappings of the peers end with the process)
     delete c;
 }
 
@@ -155,24 +296,96 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
                                     uint64_t* n_solved_total, void* stream) {
     if (!pl || !c || !n_out) { set_error("null argument"); return THETA_ERR_INVALID; }
     *n_out = 0;
+    if (!stream) {  // the step is self-contained and ends with a host wait: run it on the communicator's own stream
+        if (!c->st_own) THETA_CUDA(cudaStreamCreateWithFlags(&c->st_own, cudaStreamNonBlocking));
+        stream = c->st_own;
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = theta_search_n2_pass1_begin(pl, rank_begin, rank_end, c->d_min, stream);
-    if (rc) return rc;
-    if (c->comm) THETA_NCCL(nccl().AllReduce(c->d_min, c->d_min, 1, ncclDouble, ncclMin, c->comm, st));
+    static const bool debug = getenv("THETA_DEBUG") != nullptr;
+    static const bool graph_env = !debug && !(getenv("THETA_NO_GRAPH") && getenv("THETA_NO_GRAPH")[0] == '1');
+    const bool use_graph = graph_env && !c->g_disabled;
+    if (debug && !c->dbg[0]) for (int i = 0; i < 5; ++i) cudaEventCreate(&c->dbg[i]);
     const size_t head = sizeof(unsigned long long) * kStatusWordsX;
-    for (int attempt = 0;; ++attempt) {
-        const size_t bytes = head + sizeof(theta_cand) * c->xcap;
-        rc = comm_buffers(c, bytes);
-        if (rc) return rc;
-        rc = theta_search_n2_pass2_enqueue(pl, c->d_min, INFINITY, c->d_send, c->xcap, stream);
-        if (rc) return rc;
-        if (c->comm) {
+    int rc = THETA_OK;
+    // everything one step enqueues on the stream (also what the graph captures)
+    auto enqueue = [&](size_t bytes) -> int {
+        if (debug) cudaEventRecord(c->dbg[0], st);
+        int r = theta_search_n2_pass1_begin(pl, rank_begin, rank_end, c->d_min, stream);
+        if (r) return r;
+        if (debug) cudaEventRecord(c->dbg[1], st);
+        const bool peer = c->world > 1 && c->peer_ok && c->xcap <= kPeerRecs;
+        if (peer) peer_min_kernel<<<1, 32, 0, st>>>(c->peers, c->world, c->rank, c->d_min);
+        else if (c->comm) THETA_NCCL(nccl().AllReduce(c->d_min, c->d_min, 1, ncclDouble, ncclMin, c->comm, st));
+        if (debug) cudaEventRecord(c->dbg[2], st);
+        r = theta_search_n2_pass2_enqueue(pl, c->d_min, INFINITY, c->d_send, c->xcap, stream);
+        if (r) return r;
+        if (debug) cudaEventRecord(c->dbg[3], st);
+        if (peer) {
+            peer_gather_kernel<<<c->world, 256, 0, st>>>(c->peers, c->world, c->rank, c->d_send, bytes, c->x_slot);
+            THETA_CUDA(cudaGetLastError());
+            THETA_CUDA(cudaMemcpy2DAsync(c->h_recv, bytes, c->x_recv, c->x_slot, bytes, c->world, cudaMemcpyDeviceToHost, st));
+            THETA_CUDA(cudaMemcpyAsync(c->h_err, &c->x_area->err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        } else if (c->comm) {
             THETA_NCCL(nccl().AllGather(c->d_send, c->d_recv, bytes, ncclUint8, c->comm, st));
             THETA_CUDA(cudaMemcpyAsync(c->h_recv, c->d_recv, bytes * c->world, cudaMemcpyDeviceToHost, st));
         } else {
             THETA_CUDA(cudaMemcpyAsync(c->h_recv, c->d_send, bytes, cudaMemcpyDeviceToHost, st));
         }
+        if (debug) cudaEventRecord(c->dbg[4], st);
+        return THETA_OK;
+    };
+    for (int attempt = 0;; ++attempt) {
+        const size_t bytes = head + sizeof(theta_cand) * c->xcap;
+        rc = comm_buffers(c, bytes);
+        if (rc) return rc;
+        const uint64_t key[5] = {pl->uid, rank_begin, rank_end, c->xcap, (uint64_t)(uintptr_t)st};
+        const bool same = std::memcmp(key, c->g_key, sizeof(key)) == 0;
+        if (use_graph && same && c->g_exec) {
+            theta_search_n2_graph_replay(pl, rank_begin, rank_end, stream);  // host-side bookkeeping of pass1_begin
+            THETA_CUDA(cudaGraphLaunch(c->g_exec, st));
+        } else {
+            if (!same) {
+                if (c->g_exec) { cudaGraphExecDestroy(c->g_exec); c->g_exec = nullptr; }
+                std::memcpy(c->g_key, key, sizeof(key));
+                c->g_seen = 0;
+            }
+            if (use_graph && same && ++c->g_seen >= 1) {
+                // second identical step: capture it (the first ran eagerly and sized every buffer)
+                // (anything going wrong here just means: no graph for this communicator)
+                cudaGraph_t graph = nullptr;
+                cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+                bool ok = e == cudaSuccess;
+                if (ok) {
+                    const int rcc = enqueue(bytes);
+                    e = cudaStreamEndCapture(st, &graph);
+                    ok = rcc == THETA_OK && e == cudaSuccess && graph;
+                }
+                if (ok) {
+                    e = cudaGraphInstantiate(&c->g_exec, graph, 0);
+                    ok = e == cudaSuccess;
+                }
+                if (graph) cudaGraphDestroy(graph);
+                if (ok) ok = cudaGraphLaunch(c->g_exec, st) == cudaSuccess;
+                if (!ok) {
+                    cudaGetLastError();
+                    if (c->g_exec) { cudaGraphExecDestroy(c->g_exec); c->g_exec = nullptr; }
+                    c->g_disabled = true;
+                    rc = enqueue(bytes);
+                    if (rc) return rc;
+                }
+            } else {
+                rc = enqueue(bytes);
+                if (rc) return rc;
+            }
+        }
         THETA_CUDA(cudaStreamSynchronize(st));
+        if (c->h_err && c->peer_ok && *c->h_err) { set_error("peer exchange timed out (a rank did not reach the step)"); return THETA_ERR_CUDA; }
+        if (debug) {
+            float t[4];
+            for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], c->dbg[i], c->dbg[i + 1]);
+            fprintf(stderr, "[theta dist rank %d/%d] pass1+reduce %.3f  allreduce %.3f  scan+pass2 %.3f  allgather+D2H %.3f ms\n",
+                    c->rank, c->world, t[0], t[1], t[2], t[3]);
+        }
         uint64_t worst = 0;
         for (int r = 0; r < c->world; ++r) {
             const unsigned long long* stw = reinterpret_cast<const unsigned long long*>(c->h_recv + (size_t)r * bytes);
@@ -437,6 +650,28 @@ extern "C" int theta_mgpu_create(const theta_problem* p, int32_t n_devices, cons
         x.comm->rank = x.index; x.comm->world = n_devices; x.comm->comm = comms[x.index];
         return comm_init_common(x.comm);
     });
+    if (!rc && n_devices > 1 && n_devices <= kMaxPeers && peer_exchange_wanted()) {
+        // every GPU maps every other one (NVSwitch); without that the NCCL collectives stay
+        std::vector<theta_comm*> cs;
+        for (Worker* w : h->w) cs.push_back(w->comm);
+        int rcp = run_all(h, [&cs, n_devices](Worker& x) {
+            for (int j = 0; j < n_devices; ++j) {
+                if (j == x.index) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, x.device, cs[j]->device) != cudaSuccess || !can) return THETA_ERR_UNSUPPORTED;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(cs[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return THETA_ERR_UNSUPPORTED; }
+                cudaGetLastError();
+            }
+            return THETA_OK;
+        });
+        if (rcp == THETA_OK) {
+            for (theta_comm* c : cs) {
+                for (int j = 0; j < n_devices; ++j) { c->peers.area[j] = cs[j]->x_area; c->peers.recv[j] = cs[j]->x_recv; }
+                c->peer_ok = true;
+            }
+        }
+    }
     if (rc) { const std::string keep = theta_last_error(); theta_mgpu_destroy(h); set_error("%s", keep.c_str()); return rc; }
     *out = h;
     return THETA_OK;
@@ -482,7 +717,10 @@ extern "C" int theta_mgpu_optimize(theta_mgpu* h, uint64_t budget, int32_t* lowe
         const uint64_t total = budget ? std::min<uint64_t>(p0->count, budget) : p0->count;
         if (n_candidates) *n_candidates = total;
         if (total == 0) { set_error("No valid Copy Number Profiles exist for these intervals within the bounds specified"); return THETA_ERR_EMPTY; }
-        rc = run_all(h, [total, G](Worker& x) {
+        static const bool tdbg = getenv("THETA_DEBUG_HOST") != nullptr;
+        const auto t_main0 = std::chrono::steady_clock::now();
+        rc = run_all(h, [total, G, t_main0](Worker& x) {
+            const auto tw0 = std::chrono::steady_clock::now();
             const uint64_t b = (uint64_t)(((unsigned __int128)total * x.index) / G), e = (uint64_t)(((unsigned __int128)total * (x.index + 1)) / G);
             if (x.recs.size() < 1024) x.recs.resize(1024);
             cudaEventRecord(x.e0, x.st);
@@ -495,8 +733,16 @@ extern "C" int theta_mgpu_optimize(theta_mgpu* h, uint64_t budget, int32_t* lowe
             cudaEventSynchronize(x.e1);
             cudaEventElapsedTime(&x.ms, x.e0, x.e1);
             theta_search_stats_get(x.plan, &x.stats);
+            if (tdbg) {
+                const auto tw1 = std::chrono::steady_clock::now();
+                fprintf(stderr, "[theta mgpu worker %d] wake %.1f us after post, job %.1f us (device %.1f us)\n", x.index,
+                        std::chrono::duration<double, std::micro>(tw0 - t_main0).count(),
+                        std::chrono::duration<double, std::micro>(tw1 - tw0).count(), x.ms * 1e3);
+            }
             return rc2;
         });
+        if (tdbg) fprintf(stderr, "[theta mgpu main] run_all %.1f us\n",
+                          std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_main0).count());
         if (rc) return rc;
         Worker& w0 = *h->w[0];
         if (stats) {

@@ -4,6 +4,7 @@
 // (python/Optimizer.py:90-126) and the enumerate->solve->keep-best loop of
 // do_optimization_single / process_loop (python/RunTHetA.py:53-93,173-220).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -366,6 +367,8 @@ extern "C" int theta_plan_create(const theta_problem* p, theta_plan** out) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError())); return THETA_ERR_CUDA; }
     theta_plan* pl = new theta_plan();
+    static std::atomic<uint64_t> next_uid{1};
+    pl->uid = next_uid.fetch_add(1);
     pl->device = dev;
     pl->n = p->n; pl->m = p->m; pl->tau = p->tau; pl->max_normal = p->max_normal;
     const int m = p->m;
@@ -670,6 +673,15 @@ __global__ void __launch_bounds__(1024) stripe_scan_kernel(const double* __restr
 }
 }  // namespace theta
 
+// timing events of the plan: inside a stream capture they are recorded as external event nodes, so that they can
+// still be read with cudaEventElapsedTime after the graph has run
+static cudaError_t record_event(cudaEvent_t ev, cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+        return cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal);
+    return cudaEventRecord(ev, st);
+}
+
 static int plan_events(theta_plan* pl) {
     if (!pl->ev0) {
         THETA_CUDA(cudaEventCreate(&pl->ev0)); THETA_CUDA(cudaEventCreate(&pl->ev1));
@@ -713,7 +725,7 @@ extern "C" int theta_search_n2_pass1_begin(theta_plan* pl, uint64_t rank_begin, 
         pl->stripe_cap = stripes + 1;
     }
     THETA_CUDA(cudaMemsetAsync(pl->d_counters, 0, sizeof(unsigned long long) * kStatusWords, st));
-    THETA_CUDA(cudaEventRecord(pl->ev0, st));
+    THETA_CUDA(record_event(pl->ev0, st));
     if (N) {
         SearchParams sp{};
         sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
@@ -726,9 +738,21 @@ extern "C" int theta_search_n2_pass1_begin(theta_plan* pl, uint64_t rank_begin, 
         }
         THETA_KT_DISPATCH(pl->KT, { int rc2 = launch_search<KT, false>(pl, sp, st); if (rc2) return rc2; });
     }
-    THETA_CUDA(cudaEventRecord(pl->ev1, st));
+    THETA_CUDA(record_event(pl->ev1, st));
     stripe_min_reduce_kernel<<<1, 1024, 0, st>>>(pl->d_stripe_min, stripes, pl->d_counters, local_min_dev);
     THETA_CUDA(cudaGetLastError());
+    return THETA_OK;
+}
+
+// The host-side part of theta_search_n2_pass1_begin when the device work is replayed from a captured graph of the very
+// same call (theta_mgpu.cu): per-search bookkeeping only, nothing is enqueued.
+extern "C" int theta_search_n2_graph_replay(theta_plan* pl, uint64_t rank_begin, uint64_t rank_end, void* stream) {
+    if (!pl || pl->n != 2) { set_error("plan is not n=2"); return THETA_ERR_INVALID; }
+    if (rank_end > pl->count) rank_end = pl->count;
+    pl->p1_begin = rank_begin; pl->p1_end = rank_end; pl->p1_stream = stream; pl->p1_pending = true;
+    pl->stats = theta_search_stats{};
+    pl->stats.n_candidates = rank_end - rank_begin;
+    pl->stats.min_nll = INFINITY;
     return THETA_OK;
 }
 
@@ -796,7 +820,7 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
             if (e != cudaSuccess) { rc = cuda_fail(e, "emit staging", __FILE__, __LINE__); break; }
             pl->h_emit_cap = std::max(spec, want);
         }
-        cudaEventRecord(pl->ev2, st);
+        record_event(pl->ev2, st);
         // (re)builds the list and zeroes the pass-2 counters
         stripe_scan_kernel<<<1, 1024, 0, st>>>(pl->d_stripe_min, stripes, global_min_dev, prior_min, margin, pl->d_counters,
                                                pl->d_list, pl->d_prior);
@@ -818,7 +842,7 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
             }
             if (rc) break;
         }
-        cudaEventRecord(pl->ev3, st);
+        record_event(pl->ev3, st);
         cudaError_t e = cudaMemcpyAsync(pl->h_ctr, pl->d_counters, sizeof(unsigned long long) * kStatusWords, cudaMemcpyDeviceToHost, st);
         const size_t n_spec = std::min(spec, pl->emit_cap);
         if (e == cudaSuccess) e = cudaMemcpyAsync(pl->h_emit, pl->d_emit, sizeof(theta_cand) * n_spec, cudaMemcpyDeviceToHost, st);
@@ -884,7 +908,7 @@ extern "C" int theta_search_n2_pass2_enqueue(theta_plan* pl, const double* globa
         THETA_CUDA(theta::dmalloc(&pl->d_emit, sizeof(theta_cand) * want));
         pl->emit_cap = want;
     }
-    THETA_CUDA(cudaEventRecord(pl->ev2, st));
+    THETA_CUDA(record_event(pl->ev2, st));
     stripe_scan_kernel<<<1, 1024, 0, st>>>(pl->d_stripe_min, stripes, global_min_dev, prior_min, margin, pl->d_counters,
                                            pl->d_list, pl->d_prior);
     int rc = THETA_OK;
@@ -906,7 +930,7 @@ extern "C" int theta_search_n2_pass2_enqueue(theta_plan* pl, const double* globa
         }
         if (rc) return rc;
     }
-    THETA_CUDA(cudaEventRecord(pl->ev3, st));
+    THETA_CUDA(record_event(pl->ev3, st));
     unsigned char* out = static_cast<unsigned char*>(out_dev);
     THETA_CUDA(cudaMemcpyAsync(out, pl->d_counters, sizeof(unsigned long long) * kStatusWords, cudaMemcpyDeviceToDevice, st));
     THETA_CUDA(cudaMemcpyAsync(out + sizeof(unsigned long long) * kStatusWords, pl->d_emit, sizeof(theta_cand) * cap,

@@ -123,6 +123,7 @@ int theta_n3_tile_info(const theta_plan* pl, uint8_t* ra, uint8_t* rb, int* n_ro
 
 // Host-side plan (opaque to C callers)
 struct theta_plan {
+    uint64_t uid = 0;  // unique per plan instance (a destroyed plan's address can be reused): keys cached CUDA graphs
     theta_n3_state* n3 = nullptr;
     int device = 0;
     int n = 2, m = 0, tau = 2, K = 0, KT = 0;
