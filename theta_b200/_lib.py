@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtheta_b200.so")
+# THETA_LIB: a differently built copy of the same library (kernel variants during development, tools/build_variants.py)
+LIB_PATH = os.environ.get("THETA_LIB") or os.path.join(HERE, "libtheta_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_EMPTY, ERR_OVERFLOW, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 ST_OK, ST_ROOT_LB, ST_ROOT_UB, ST_FALLBACK_X0, ST_DEGENERATE, ST_FALLBACK_MOVED = 0, 1, 2, 3, 4, 5

@@ -39,6 +39,9 @@ struct SolveOut {
     int iters;
 };
 
+#ifndef THETA_P1_FASTM2
+#define THETA_P1_FASTM2 1
+#endif
 #define THETA_NEWTON_MAXIT 100
 #define THETA_NEWTON_PRED 2e-11   // stop when the error predicted after the step, |f''/(2f')| dN^2, is below this (relative)
 #define THETA_NEWTON_RTOL 1e-9    // a converged step that leaves the bracket by rounding is accepted if it is this small (relative)
@@ -143,6 +146,48 @@ __device__ __forceinline__ double n2_f(const double (&nv)[KV], double S1, double
     return -s;
 }
 
+// One safeguarded Halley step of the root-finder on the bracket [lo, hi] (f increasing: f' = sum R_v e_v^2 / den^2 > 0).
+// With c2 = f''/(2f') the error left after a *Newton* step dN is |c2| dN^2 to leading order (and less after the
+// Halley step actually taken), so the stopping test needs no history: stop once that bound is below
+// THETA_NEWTON_PRED * |x|  (the reference's own brenth stops at 2e-12 absolute, Optimizer.py:118).
+// Returns true when x is final.
+//
+// P1 (pass 1 of the search, whose start is already good to ~1e-6): the bound for the Halley step itself.  With
+// w_v = e_v/den_v, f''/(2f') and f'''/(6f') are weighted means of -w_v and w_v^2 (weights R_v e_v^2/den_v^2 >= 0), w_v is
+// monotone in v between 1/x and -1/(1-x), hence |w_v| <= W = 1/min(x, 1-x), and the error left after a Halley step is
+// |(f''/(2f'))^2 - f'''/(6f')| dN^3 <= 2 W^2 |dN|^3 to leading order.  The test  dN^2 <= 1e-9 x min(x,1-x)  and
+// |dN| <= 1e-2 min(x,1-x)  implies  2 W^2 |dN|^3 <= THETA_NEWTON_PRED |x|: the same accuracy contract as the Newton bound,
+// reached one evaluation earlier.
+template <int KV, bool P1 = false>
+__device__ __forceinline__ bool n2_halley_step(const double (&nv)[KV], const double (&ev)[KV], double S1, double A, bool rising,
+                                               double& x, double& lo, double& hi) {
+    double f, fp, fpp2;
+    n2_f_df_d2<KV>(nv, ev, S1, A, x, f, fp, fpp2);
+    if (f == 0.0) return true;
+    if ((f < 0.0) == rising) lo = x; else hi = x;
+    const double rfp = fast_rcp(fp);
+    const double dN = -f * rfp;          // Newton step
+    const double c2 = fpp2 * rfp;         // f'' / (2 f')
+    const double den = fma(dN, c2, 1.0);  // Halley: dH = dN / (1 + dN c2)
+    const double dx = (den > 0.5 && den < 2.0) ? dN * fast_rcp(den) : dN;
+    const double xn = x + dx;
+    const bool inside = (xn > lo && xn < hi);
+    bool conv;
+    if (P1) {
+        const double mx = fmin(x, 1.0 - x);  // (P1: the bracket is [0, 1])
+        conv = (dN * dN <= (50.0 * THETA_NEWTON_PRED) * x * mx) && (fabs(dN) <= 1e-2 * mx);
+    } else {
+        conv = fabs(c2) * dN * dN <= THETA_NEWTON_PRED * fabs(x);
+    }
+    // (a converged step can round onto the bracket end it started from: then x itself is the root)
+    if (conv && (inside || fabs(dN) <= THETA_NEWTON_RTOL * fabs(x))) {
+        if (inside) x = xn;
+        return true;
+    }
+    x = inside ? xn : 0.5 * (lo + hi);
+    return false;
+}
+
 // Optimizer._solve_n2 (python/Optimizer.py:90-126) on grouped statistics.
 //   R[v]      : sum of r_i over intervals with c_i == v
 //   S1        : sum rN_i c_i
@@ -226,26 +271,8 @@ __device__ __forceinline__ bool n2_root(const double (&R)[KV], double S1, bool z
         const bool rising = f0 < 0.0;
         x = (x0 > lo && x0 < hi) ? x0 : 0.5 * (lo + hi);
         int it = 0;
-        for (; it < THETA_NEWTON_MAXIT; ++it) {
-            double f, fp, fpp2;
-            n2_f_df_d2<KV>(nv, ev, S1, k.A, x, f, fp, fpp2);
-            if (f == 0.0) break;
-            if ((f < 0.0) == rising) lo = x; else hi = x;
-            const double rfp = fast_rcp(fp);
-            const double dN = -f * rfp;          // Newton step
-            const double c2 = fpp2 * rfp;         // f'' / (2 f')
-            const double den = fma(dN, c2, 1.0);  // Halley: dH = dN / (1 + dN c2)
-            const double dx = (den > 0.5 && den < 2.0) ? dN * fast_rcp(den) : dN;
-            const double xn = x + dx;
-            const bool inside = (xn > lo && xn < hi);
-            const bool conv = fabs(c2) * dN * dN <= THETA_NEWTON_PRED * fabs(x);
-            // (a converged step can round onto the bracket end it started from: then x itself is the root)
-            if (conv && (inside || fabs(dN) <= THETA_NEWTON_RTOL * fabs(x))) {
-                if (inside) x = xn;
-                break;
-            }
-            x = inside ? xn : 0.5 * (lo + hi);
-        }
+        for (; it < THETA_NEWTON_MAXIT; ++it)
+            if (n2_halley_step<KV>(nv, ev, S1, k.A, rising, x, lo, hi)) break;
         o.iters = it + 1;
         if (it >= THETA_NEWTON_MAXIT) {
             o.status = THETA_ST_NONE_NOCONV;
@@ -258,6 +285,100 @@ __device__ __forceinline__ bool n2_root(const double (&R)[KV], double S1, bool z
     o.x = x;
     o.mu = numer / denom;
     o.status = status;
+    return true;
+}
+
+// ---- pass 1 of the search only: a cheaper way to the same root -----------------------------------------------------
+// The fp64 iteration above is what decides the root (bracket, stopping test, accuracy); what it costs is the number of
+// evaluations, and from the warm start of the search (linear extrapolation of the previous two roots, error ~1e-3) it
+// needs two.  n2_refine32 runs the same Halley iteration in fp32 first -- FMA pipe and MUFU.RCP, which the search
+// kernel otherwise leaves idle next to the saturated FP64 pipe -- and hands the fp64 loop a start that is good to
+// ~1e-6, so that its first evaluation already passes the stopping test.  The fp32 numbers never reach a result: a
+// poor (or non-finite) refinement only costs fp64 evaluations.
+// w-form of the same sums:  w_v = e_v/den_v,  f = -sum R_v w_v,  f' = sum R_v w_v^2,  f''/2 = -sum R_v w_v^3;
+// nothing overflows for any input the plan accepts (R_v, A K < 2^57; w_v <= 1/x).
+__device__ __forceinline__ float rcp32(float a) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+template <int KV>
+__device__ __forceinline__ double n2_refine32(const double (&R)[KV], double S1, double A, double x0, int nit) {
+    float Rf[KV], ef[KV];
+    const float S1f = (float)S1, Af = (float)A;
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+        Rf[v] = (float)R[v];
+        ef[v] = fmaf(-(float)v, Af, S1f);
+    }
+    float x = (float)x0;
+    // Newton, until the step is below 3e-4 x (the next iterate is then at fp32 accuracy): one step from the usual warm
+    // start (error ~1e-3), two after an odometer carry, a handful from the cold start
+    for (int it = 0; it < nit; ++it) {
+        const float z = x * S1f;
+        const float y = (1.0f - x) * Af;
+        float s = 0.0f, sp = 0.0f;
+#pragma unroll
+        for (int v = 0; v < KV; ++v) {
+            const float w = ef[v] * rcp32(fmaf((float)v, y, z));
+            const float a = Rf[v] * w;
+            s += a;
+            sp = fmaf(a, w, sp);
+        }
+        const float d = s * rcp32(sp);               // -f/f'
+        float xn = x + d;
+        const bool last = fabsf(d) <= 3e-4f * x;
+        if (!(xn > 0.0f)) xn = 0.5f * x;             // (also catches NaN)
+        if (!(xn < 1.0f)) xn = 0.5f * (x + 1.0f);
+        x = xn;
+        if (last) break;
+    }
+    return (double)x;
+}
+
+// n2_root for pass 1 of the search (lB = 0, same classification, same fp64 iteration and stopping test; fp32-refined start).
+// The common case -- f(0) < 0 < f(1), bracket [0, 1] -- is handled inline; everything else (None candidates, roots at
+// the bracket ends, max_normal != 1) goes through n2_root itself.
+template <int KV>
+__device__ __forceinline__ bool n2_root_p1(const double (&R)[KV], double S1, bool zero_r_c0, const N2Const& k, double x0,
+                                           SolveOut& o) {
+    double ev[KV], nv[KV];
+    double s = 0.0;
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+        ev[v] = S1 - (double)v * k.A;  // exact
+        nv[v] = R[v] * ev[v];
+        s += nv[v];                    // f(1) = -s / S1 (same sum, same order as n2_root)
+    }
+    // f(0) < 0: -inf when the copy-number-0 group carries reads, else the finite sum of n2_root (the last column of every
+    // odometer row has no interval at copy number 0)
+    bool f0neg = nv[0] != 0.0;
+    if (!f0neg) {
+        double s0 = 0.0;
+#pragma unroll
+        for (int v = 1; v < KV; ++v) s0 = fma(nv[v], 1.0 / (double)v, s0);
+        f0neg = -s0 < 0.0;
+    }
+    const bool common = (S1 > 0.0) && !zero_r_c0 && f0neg && (s < 0.0) && (k.max_normal == 1.0) && !k.any_zero_rN;
+    if (!common) return n2_root<KV>(R, S1, zero_r_c0, k, x0, o);
+    const bool warm = (x0 > 0.0 && x0 < 1.0);
+    double x = n2_refine32<KV>(R, S1, k.A, warm ? x0 : 0.5, 8);
+    double lo = 0.0, hi = 1.0;
+    int it = 0;
+    for (; it < THETA_NEWTON_MAXIT; ++it)
+        if (n2_halley_step<KV, true>(nv, ev, S1, k.A, true, x, lo, hi)) break;
+    o.iters = it + 1;
+    if (it >= THETA_NEWTON_MAXIT) {
+        o.x = 0.0; o.mu = 0.0; o.nll = 0.0;
+        o.status = THETA_ST_NONE_NOCONV;
+        return false;
+    }
+    const double numer = -x * S1;
+    const double denom = (x - 1.0) * k.S0 + numer;
+    o.x = x;
+    o.mu = THETA_P1_FASTM2 ? numer * fast_rcp(denom) : numer / denom;  // (pass 1 feeds thresholds only; records are re-solved)
+    o.nll = 0.0;
+    o.status = THETA_ST_OK;
     return true;
 }
 
@@ -287,16 +408,21 @@ __device__ __forceinline__ double n2_l2(const double (&R)[KV], double S1, double
 // cannot matter (NLL far above the best seen); everything that can matter is evaluated by n2_l2.
 #define THETA_APPROX_C 4e-6
 #define THETA_APPROX_MIN_TM 0.0078125
+__device__ __forceinline__ float lg2_ftz(float a) {  // one MUFU.LG2 (no denormal scaling: the arguments are >= 2^-7)
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
 template <int KV>
 __device__ __forceinline__ double n2_l2_approx(const double (&R)[KV], double S1, double mu, const N2Const& k, double inv_A) {
     const double mu1 = 1.0 - mu;
     const double tm = k.tau * mu;
     const float mu1f = (float)mu1, tmf = (float)tm;
-    const float lgb = __log2f((float)((mu * k.S0 + mu1 * S1) * inv_A));
+    const float lgb = lg2_ftz((float)((mu * k.S0 + mu1 * S1) * inv_A));
     double acc = 0.0;
 #pragma unroll
     for (int v = 0; v < KV; ++v) {
-        const float lg = __log2f(fmaf((float)v, mu1f, tmf));
+        const float lg = lg2_ftz(fmaf((float)v, mu1f, tmf));
         acc = fma(R[v], (double)lg, acc);  // R[v] == 0 adds 0 (lg is finite: arguments >= 2^-7)
     }
     acc = fma(-k.Rtot, (double)lgb, acc);

@@ -17,6 +17,13 @@ namespace theta {
 
 static constexpr int kBlock = 128;
 static constexpr int kCounters = 8;
+// pass-1 tuning switches (development: -DTHETA_P1_REFINE=0 / -DTHETA_P1_INCREMENTAL=0 give the round-1 kernel back)
+#ifndef THETA_P1_REFINE
+#define THETA_P1_REFINE 1
+#endif
+#ifndef THETA_P1_INCREMENTAL
+#define THETA_P1_INCREMENTAL 0
+#endif
 // device status block (u64 words): [0..7] pass-1 counters, [8..15] pass-2 counters, [16] listed stripes,
 // [17] shard minimum (double bits), [18] global minimum used by pass 2 (double bits)
 static constexpr int kStatusWords = 32;
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
     T_.bind(smem, p.layout);
     const N2Const kc = p.kc;
     const int lane = threadIdx.x & 31;
-    unsigned long long solved = 0, iters = 0, nan_nll = 0, n_exact = 0, n_viol = 0;
+    unsigned int solved = 0, iters = 0, nan_nll = 0, n_exact = 0, n_viol = 0;  // per lane (a lane sees < 2^32 candidates)
     // Pass 1 proves most candidates irrelevant with the fp32-log NLL (n2_l2_approx): a candidate whose lower
     // bound exceeds T + margin -- T = the best exact NLL this warp has seen in this or an earlier (lower-rank)
     // stripe -- is neither the stripe minimum that matters (a strict prefix minimum of the stream is below
@@ -114,25 +121,58 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
             // pass 1 runs the same trip count in every lane so that the warp can pool its thresholds every 8
             // columns (candidates of the same stripe: the stripe is re-walked by pass 2 whenever it matters)
             const int trips = EMIT ? cnt : p.Lrun;
+            double R[KT + 1], S1 = 0.0, S1rest = 0.0, sr2 = 0.0;
+            bool z = false, fresh = true;
+            int rowpos = 0;  // position in the current odometer row (saturates at 2)
+            double xrow = -1.0, drow = 0.0, d1row = 0.0;
+            const double srm = T_.SR[T_.m];
+            const int qhi0 = T_.qhi[0];
             for (int t = 0; t < trips; ++t) {
                 if (!EMIT && (t & 7) == 0 && t) T = warp_min(T);
                 if (t >= cnt) continue;
-                double R[KT + 1], S1;
-                bool z;
-                n2_groups<KT>(T_, q, R, S1, z);
+                if (EMIT || THETA_P1_INCREMENTAL == 0 || fresh) {
+                    n2_groups<KT>(T_, q, R, S1, z);
+                    if (!EMIT && THETA_P1_INCREMENTAL) {
+                        S1rest = S1 - T_.SRN[q[0]];           // exact integers: any order of summation gives the same S1
+                        sr2 = KT >= 2 ? T_.SR[q[KT >= 2 ? 1 : 0]] : 0.0;
+                        fresh = false;
+                    }
+                }
                 SolveOut o;
                 // consecutive columns differ in one breakpoint, so the root moves smoothly: start Newton
                 // from the linear extrapolation of the last two roots (falls back to the last root)
                 double x0 = xprev;
-                if (xprev2 > 0.0) {
+                if (!EMIT && THETA_P1_REFINE && rowpos < 2) {
+                    // the first two columns after an odometer carry start from the same positions of the previous row:
+                    // first column = its first root extrapolated by the row-to-row trend, second = first + the previous
+                    // row's first difference
+                    if (rowpos == 0) {
+                        x0 = xrow;
+                        const double xe = xrow + drow;
+                        if (xe > 0.0 && xe < 1.0) x0 = xe;
+                    } else {
+                        const double xe = xprev + d1row;
+                        if (xe > 0.0 && xe < 1.0) x0 = xe;
+                    }
+                } else if (xprev2 > 0.0) {
                     const double xe = 2.0 * xprev - xprev2;
                     if (xe > 0.0 && xe < 1.0) x0 = xe;
                 }
-                if (n2_root<KT + 1>(R, S1, z, kc, x0, o)) {
+                if ((!EMIT && THETA_P1_REFINE) ? n2_root_p1<KT + 1>(R, S1, z, kc, x0, o) : n2_root<KT + 1>(R, S1, z, kc, x0, o)) {
                     ++solved;
                     iters += o.iters;
                     xprev2 = xprev;
                     xprev = o.x;
+                    if (!EMIT && THETA_P1_REFINE && rowpos < 2) {
+                        if (rowpos == 0) {
+                            drow = xrow > 0.0 ? o.x - xrow : 0.0;
+                            xrow = o.x;
+                            xprev2 = -1.0;  // the last column of the previous row says nothing about the trend of this one
+                        } else {
+                            d1row = o.x - xprev2;
+                        }
+                        ++rowpos;
+                    }
                     bool exact = true;
                     double na = 0.0;
                     if (!EMIT && kc.tau * o.mu >= THETA_APPROX_MIN_TM) {
@@ -175,7 +215,23 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
                         }
                     }
                 }
-                if (t + 1 < cnt) n2_next<KT>(T_, q);
+                if (t + 1 < cnt) {
+                    if (!EMIT && q[0] < qhi0) {
+                        // the common odometer step moves one interval from copy number 0 to 1: only R_0, R_1, S1 change
+                        const int q0 = ++q[0];
+                        if (THETA_P1_INCREMENTAL) {
+                            const double sr1 = T_.SR[q0];
+                            R[0] = srm - sr1;
+                            R[1] = sr1 - sr2;
+                            S1 = S1rest + T_.SRN[q0];
+                            z = T_.Z0[q0] > 0;
+                        }
+                    } else {
+                        n2_next<KT>(T_, q);
+                        fresh = true;
+                        rowpos = 0;
+                    }
+                }
             }
         }
         if (!EMIT) {
@@ -185,17 +241,15 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
         }
     }
     if (!EMIT) {
-        solved = warp_sum(solved);
-        iters = warp_sum(iters);
-        nan_nll = warp_sum(nan_nll);
-        n_exact = warp_sum(n_exact);
-        n_viol = warp_sum(n_viol);
+        const unsigned long long w_solved = warp_sum((unsigned long long)solved), w_iters = warp_sum((unsigned long long)iters);
+        const unsigned long long w_nan = warp_sum((unsigned long long)nan_nll), w_exact = warp_sum((unsigned long long)n_exact);
+        const unsigned long long w_viol = warp_sum((unsigned long long)n_viol);
         if (lane == 0) {
-            if (solved) atomicAdd(&p.counters[1], solved);
-            if (iters) atomicAdd(&p.counters[2], iters);
-            if (nan_nll) atomicAdd(&p.counters[4], nan_nll);
-            if (n_exact) atomicAdd(&p.counters[5], n_exact);
-            if (n_viol) atomicAdd(&p.counters[6], n_viol);
+            if (w_solved) atomicAdd(&p.counters[1], w_solved);
+            if (w_iters) atomicAdd(&p.counters[2], w_iters);
+            if (w_nan) atomicAdd(&p.counters[4], w_nan);
+            if (w_exact) atomicAdd(&p.counters[5], w_exact);
+            if (w_viol) atomicAdd(&p.counters[6], w_viol);
         }
     }
 }
