@@ -39,6 +39,9 @@ struct SolveOut {
     int iters;
 };
 
+#ifndef THETA_P1_F32HALLEY
+#define THETA_P1_F32HALLEY 0
+#endif
 #ifndef THETA_P1_FASTM2
 #define THETA_P1_FASTM2 1
 #endif
@@ -303,7 +306,7 @@ __device__ __forceinline__ float rcp32(float a) {
     return r;
 }
 template <int KV>
-__device__ __forceinline__ double n2_refine32(const double (&R)[KV], double S1, double A, double x0, int nit) {
+__device__ __forceinline__ float n2_refine32(const double (&R)[KV], double S1, double A, float x0, int nit) {
     float Rf[KV], ef[KV];
     const float S1f = (float)S1, Af = (float)A;
 #pragma unroll
@@ -311,37 +314,53 @@ __device__ __forceinline__ double n2_refine32(const double (&R)[KV], double S1, 
         Rf[v] = (float)R[v];
         ef[v] = fmaf(-(float)v, Af, S1f);
     }
-    float x = (float)x0;
-    // Newton, until the step is below 3e-4 x (the next iterate is then at fp32 accuracy): one step from the usual warm
-    // start (error ~1e-3), two after an odometer carry, a handful from the cold start
+    float x = x0;
+    // Iterate until the step d says the next iterate is good enough for the fp64 test of n2_halley_step<P1> to pass at
+    // its first evaluation (which needs an error below sqrt(1e-9 x mx), mx = min(x, 1-x)): Newton leaves
+    // |f''/(2f')| d^2 <= d^2/mx, so |d| <= 2e-3 mx is enough for any x (then d^2/mx <= 4e-6 mx <= sqrt(1e-9 x mx)/2 as long
+    // as mx >= 1e-6); Halley (THETA_P1_F32HALLEY) leaves 2 d^3/mx^2 and tolerates |d| <= 1e-2 mx.  One step from the usual
+    // warm start, a handful from the cold start.
     for (int it = 0; it < nit; ++it) {
         const float z = x * S1f;
         const float y = (1.0f - x) * Af;
-        float s = 0.0f, sp = 0.0f;
+        float s = 0.0f, sp = 0.0f, spp = 0.0f;
 #pragma unroll
         for (int v = 0; v < KV; ++v) {
             const float w = ef[v] * rcp32(fmaf((float)v, y, z));
             const float a = Rf[v] * w;
             s += a;
-            sp = fmaf(a, w, sp);
+            if (THETA_P1_F32HALLEY) {
+                const float b = a * w;
+                sp += b;
+                spp = fmaf(b, w, spp);
+            } else {
+                sp = fmaf(a, w, sp);
+            }
         }
-        const float d = s * rcp32(sp);               // -f/f'
+        const float rfp = rcp32(sp);
+        float d = s * rfp;                           // -f/f'
+        const float mx = fminf(x, 1.0f - x);
+        const bool last = fabsf(d) <= (THETA_P1_F32HALLEY ? 1e-2f : 2e-3f) * mx;
+        if (THETA_P1_F32HALLEY) {
+            const float den = fmaf(-d * spp, rfp, 1.0f);  // 1 + d f''/(2f'),  f''/2 = -spp
+            if (den > 0.5f && den < 2.0f) d *= rcp32(den);
+        }
         float xn = x + d;
-        const bool last = fabsf(d) <= 3e-4f * x;
         if (!(xn > 0.0f)) xn = 0.5f * x;             // (also catches NaN)
         if (!(xn < 1.0f)) xn = 0.5f * (x + 1.0f);
         x = xn;
         if (last) break;
     }
-    return (double)x;
+    return x;
 }
 
-// n2_root for pass 1 of the search (lB = 0, same classification, same fp64 iteration and stopping test; fp32-refined start).
+// n2_root for pass 1 of the search (lB = 0, same classification, same fp64 iteration; fp32 start x0f, refined in fp32).
 // The common case -- f(0) < 0 < f(1), bracket [0, 1] -- is handled inline; everything else (None candidates, roots at
-// the bracket ends, max_normal != 1) goes through n2_root itself.
+// the bracket ends, max_normal != 1) goes through n2_root itself.  xf returns the root as a float (warm-start state of the
+// caller, which keeps all of it in fp32).
 template <int KV>
-__device__ __forceinline__ bool n2_root_p1(const double (&R)[KV], double S1, bool zero_r_c0, const N2Const& k, double x0,
-                                           SolveOut& o) {
+__device__ __forceinline__ bool n2_root_p1(const double (&R)[KV], double S1, bool zero_r_c0, const N2Const& k, float x0f,
+                                           SolveOut& o, float& xf) {
     double ev[KV], nv[KV];
     double s = 0.0;
 #pragma unroll
@@ -360,19 +379,42 @@ __device__ __forceinline__ bool n2_root_p1(const double (&R)[KV], double S1, boo
         f0neg = -s0 < 0.0;
     }
     const bool common = (S1 > 0.0) && !zero_r_c0 && f0neg && (s < 0.0) && (k.max_normal == 1.0) && !k.any_zero_rN;
-    if (!common) return n2_root<KV>(R, S1, zero_r_c0, k, x0, o);
-    const bool warm = (x0 > 0.0 && x0 < 1.0);
-    double x = n2_refine32<KV>(R, S1, k.A, warm ? x0 : 0.5, 8);
-    double lo = 0.0, hi = 1.0;
-    int it = 0;
-    for (; it < THETA_NEWTON_MAXIT; ++it)
-        if (n2_halley_step<KV, true>(nv, ev, S1, k.A, true, x, lo, hi)) break;
-    o.iters = it + 1;
-    if (it >= THETA_NEWTON_MAXIT) {
-        o.x = 0.0; o.mu = 0.0; o.nll = 0.0;
-        o.status = THETA_ST_NONE_NOCONV;
-        return false;
+    if (!common) {
+        const bool ok = n2_root<KV>(R, S1, zero_r_c0, k, (double)x0f, o);
+        xf = (float)o.x;
+        return ok;
     }
+    const bool warm = (x0f > 0.0f && x0f < 1.0f);
+    xf = n2_refine32<KV>(R, S1, k.A, warm ? x0f : 0.5f, 8);
+    double x = (double)xf;
+    // first fp64 evaluation, nearly always the only one: the Halley step and the P1 test of n2_halley_step, with the
+    // bracket [0, 1] and f rising folded in (when the test passes, 1 + dN f''/(2f') lies within [0.99, 1.01])
+    int iters = 1;
+    {
+        double f, fp, fpp2;
+        n2_f_df_d2<KV>(nv, ev, S1, k.A, x, f, fp, fpp2);
+        const double rfp = fast_rcp1(fp);
+        const double dN = -f * rfp;
+        const double xn = fma(dN, fast_rcp1(fma(dN, fpp2 * rfp, 1.0)), x);
+        const double mx = fmin(x, 1.0 - x);
+        const bool conv = (dN * dN <= (50.0 * THETA_NEWTON_PRED) * x * mx) && (fabs(dN) <= 1e-2 * mx) && (xn > 0.0 && xn < 1.0);
+        if (conv) {
+            x = xn;
+        } else {
+            double lo = 0.0, hi = 1.0;
+            int it = 0;
+            for (; it < THETA_NEWTON_MAXIT; ++it)
+                if (n2_halley_step<KV, true>(nv, ev, S1, k.A, true, x, lo, hi)) break;
+            iters = it + 2;
+            if (it >= THETA_NEWTON_MAXIT) {
+                o.x = 0.0; o.mu = 0.0; o.nll = 0.0; o.iters = iters;
+                o.status = THETA_ST_NONE_NOCONV;
+                return false;
+            }
+            xf = (float)x;
+        }
+    }
+    o.iters = iters;
     const double numer = -x * S1;
     const double denom = (x - 1.0) * k.S0 + numer;
     o.x = x;

@@ -113,66 +113,33 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
         const uint64_t s_end = min(p.end, (uint64_t)(s_begin + (uint64_t)32 * (uint64_t)p.L));
         const uint64_t r0 = s_begin + ((uint64_t)sub * 32u + lane) * (uint64_t)p.Lrun;
         double tmin = INFINITY;
-        {
-            const int cnt = r0 < s_end ? (int)min((uint64_t)p.Lrun, s_end - r0) : 0;
-            int q[KT];
-            if (cnt) n2_unrank<KT>(T_, r0, q);
+        const int cnt = r0 < s_end ? (int)min((uint64_t)p.Lrun, s_end - r0) : 0;
+        int q[KT];
+        if (cnt) n2_unrank<KT>(T_, r0, q);
+        if constexpr (EMIT || !THETA_P1_REFINE) {
             double xprev = -1.0, xprev2 = -1.0;  // roots of the previous two columns (warm start)
             // pass 1 runs the same trip count in every lane so that the warp can pool its thresholds every 8
             // columns (candidates of the same stripe: the stripe is re-walked by pass 2 whenever it matters)
             const int trips = EMIT ? cnt : p.Lrun;
-            double R[KT + 1], S1 = 0.0, S1rest = 0.0, sr2 = 0.0;
-            bool z = false, fresh = true;
-            int rowpos = 0;  // position in the current odometer row (saturates at 2)
-            double xrow = -1.0, drow = 0.0, d1row = 0.0;
-            const double srm = T_.SR[T_.m];
-            const int qhi0 = T_.qhi[0];
             for (int t = 0; t < trips; ++t) {
                 if (!EMIT && (t & 7) == 0 && t) T = warp_min(T);
                 if (t >= cnt) continue;
-                if (EMIT || THETA_P1_INCREMENTAL == 0 || fresh) {
-                    n2_groups<KT>(T_, q, R, S1, z);
-                    if (!EMIT && THETA_P1_INCREMENTAL) {
-                        S1rest = S1 - T_.SRN[q[0]];           // exact integers: any order of summation gives the same S1
-                        sr2 = KT >= 2 ? T_.SR[q[KT >= 2 ? 1 : 0]] : 0.0;
-                        fresh = false;
-                    }
-                }
+                double R[KT + 1], S1;
+                bool z;
+                n2_groups<KT>(T_, q, R, S1, z);
                 SolveOut o;
                 // consecutive columns differ in one breakpoint, so the root moves smoothly: start Newton
                 // from the linear extrapolation of the last two roots (falls back to the last root)
                 double x0 = xprev;
-                if (!EMIT && THETA_P1_REFINE && rowpos < 2) {
-                    // the first two columns after an odometer carry start from the same positions of the previous row:
-                    // first column = its first root extrapolated by the row-to-row trend, second = first + the previous
-                    // row's first difference
-                    if (rowpos == 0) {
-                        x0 = xrow;
-                        const double xe = xrow + drow;
-                        if (xe > 0.0 && xe < 1.0) x0 = xe;
-                    } else {
-                        const double xe = xprev + d1row;
-                        if (xe > 0.0 && xe < 1.0) x0 = xe;
-                    }
-                } else if (xprev2 > 0.0) {
+                if (xprev2 > 0.0) {
                     const double xe = 2.0 * xprev - xprev2;
                     if (xe > 0.0 && xe < 1.0) x0 = xe;
                 }
-                if ((!EMIT && THETA_P1_REFINE) ? n2_root_p1<KT + 1>(R, S1, z, kc, x0, o) : n2_root<KT + 1>(R, S1, z, kc, x0, o)) {
+                if (n2_root<KT + 1>(R, S1, z, kc, x0, o)) {
                     ++solved;
                     iters += o.iters;
                     xprev2 = xprev;
                     xprev = o.x;
-                    if (!EMIT && THETA_P1_REFINE && rowpos < 2) {
-                        if (rowpos == 0) {
-                            drow = xrow > 0.0 ? o.x - xrow : 0.0;
-                            xrow = o.x;
-                            xprev2 = -1.0;  // the last column of the previous row says nothing about the trend of this one
-                        } else {
-                            d1row = o.x - xprev2;
-                        }
-                        ++rowpos;
-                    }
                     bool exact = true;
                     double na = 0.0;
                     if (!EMIT && kc.tau * o.mu >= THETA_APPROX_MIN_TM) {
@@ -215,8 +182,76 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
                         }
                     }
                 }
+                if (t + 1 < cnt) n2_next<KT>(T_, q);
+            }
+        } else {
+            // Pass 1.  Everything that only steers the root-finder lives in fp32: the predicted start of a column is the
+            // previous root plus the previous increment scaled by the ratio of the S1 increments (moving interval i from
+            // copy number 0 to 1 shifts the root by about gamma * rN_i with gamma varying slowly along the row), the first
+            // two columns after an odometer carry start from the same positions of the previous row, and n2_root_p1 refines
+            // the start in fp32 before its single fp64 evaluation.
+            double R[KT + 1], S1 = 0.0, S1prev = 0.0, S1rest = 0.0, sr2 = 0.0;
+            bool z = false, fresh = true;
+            int rowpos = 0;                                  // position in the current odometer row (saturates at 2)
+            float xpf = -1.0f, dxf = 0.0f, dsf_prev = 0.0f;  // previous root, its increment, the S1 increment that came with it
+            float xrowf = -1.0f, drowf = 0.0f, d1rowf = 0.0f;  // first root of the row, row-to-row trend, first increment
+            const double srm = T_.SR[T_.m];
+            const int qhi0 = T_.qhi[0];
+            for (int t = 0; t < p.Lrun; ++t) {  // same trip count in every lane: the warp pools its thresholds every 8 columns
+                if ((t & 7) == 0 && t) T = warp_min(T);
+                if (t >= cnt) continue;
+                if (THETA_P1_INCREMENTAL == 0 || fresh) {
+                    n2_groups<KT>(T_, q, R, S1, z);
+                    if (THETA_P1_INCREMENTAL) {
+                        S1rest = S1 - T_.SRN[q[0]];  // exact integers: any order of summation gives the same S1
+                        sr2 = T_.SR[q[KT >= 2 ? 1 : 0]];
+                        fresh = false;
+                    }
+                }
+                const float dsf = (float)(S1 - S1prev);
+                S1prev = S1;
+                float x0f;
+                if (rowpos >= 2) x0f = fmaf(dxf, dsf * rcp32(dsf_prev), xpf);
+                else if (rowpos == 0) x0f = xrowf + drowf;
+                else x0f = xpf + d1rowf;
+                if (!(x0f > 0.0f && x0f < 1.0f)) x0f = xpf;  // (xpf < 0: cold start)
+                SolveOut o;
+                float xf;
+                if (n2_root_p1<KT + 1>(R, S1, z, kc, x0f, o, xf)) {
+                    ++solved;
+                    iters += o.iters;
+                    const float dnew = xf - xpf;
+                    if (rowpos == 0) {
+                        drowf = xrowf > 0.0f ? xf - xrowf : 0.0f;
+                        xrowf = xf;
+                        rowpos = 1;
+                    } else if (rowpos == 1) {
+                        d1rowf = dnew;
+                        rowpos = 2;
+                    }
+                    dxf = dnew;
+                    dsf_prev = dsf;
+                    xpf = xf;
+                    bool exact = true;
+                    double na = 0.0;
+                    if (kc.tau * o.mu >= THETA_APPROX_MIN_TM) {
+                        na = n2_l2_approx<KT + 1>(R, S1, o.mu, kc, inv_A);
+                        if (na - approx_E > T + approx_margin && !p.verify) exact = false;  // (NaN compares false)
+                    }
+                    if (exact) {
+                        const double nll = n2_l2<KT + 1>(R, S1, o.mu, kc, s_logtab);
+                        ++n_exact;
+                        if (p.verify && kc.tau * o.mu >= THETA_APPROX_MIN_TM && !(fabs(na - nll) <= approx_E)) ++n_viol;
+                        if (nll != nll) {
+                            ++nan_nll;
+                        } else {
+                            tmin = fmin(tmin, nll);
+                            T = fmin(T, nll);
+                        }
+                    }
+                }
                 if (t + 1 < cnt) {
-                    if (!EMIT && q[0] < qhi0) {
+                    if (q[0] < qhi0) {
                         // the common odometer step moves one interval from copy number 0 to 1: only R_0, R_1, S1 change
                         const int q0 = ++q[0];
                         if (THETA_P1_INCREMENTAL) {
