@@ -40,7 +40,7 @@ struct SolveOut {
 };
 
 #ifndef THETA_P1_F32HALLEY
-#define THETA_P1_F32HALLEY 0
+#define THETA_P1_F32HALLEY 1
 #endif
 #ifndef THETA_P1_FASTM2
 #define THETA_P1_FASTM2 1
@@ -306,7 +306,7 @@ __device__ __forceinline__ float rcp32(float a) {
     return r;
 }
 template <int KV>
-__device__ __forceinline__ float n2_refine32(const double (&R)[KV], double S1, double A, float x0, int nit) {
+__device__ __forceinline__ float n2_refine32(const double (&R)[KV], double S1, double A, float x0, int nit, int* used = nullptr) {
     float Rf[KV], ef[KV];
     const float S1f = (float)S1, Af = (float)A;
 #pragma unroll
@@ -315,12 +315,14 @@ __device__ __forceinline__ float n2_refine32(const double (&R)[KV], double S1, d
         ef[v] = fmaf(-(float)v, Af, S1f);
     }
     float x = x0;
-    // Iterate until the step d says the next iterate is good enough for the fp64 test of n2_halley_step<P1> to pass at
-    // its first evaluation (which needs an error below sqrt(1e-9 x mx), mx = min(x, 1-x)): Newton leaves
-    // |f''/(2f')| d^2 <= d^2/mx, so |d| <= 2e-3 mx is enough for any x (then d^2/mx <= 4e-6 mx <= sqrt(1e-9 x mx)/2 as long
-    // as mx >= 1e-6); Halley (THETA_P1_F32HALLEY) leaves 2 d^3/mx^2 and tolerates |d| <= 1e-2 mx.  One step from the usual
-    // warm start, a handful from the cold start.
+    // Iterate until the step d says the next iterate is good enough for the fp64 test of n2_root_p1 to pass at its first
+    // evaluation (which needs an error below sqrt(1e-9 x mx), mx = min(x, 1-x)).  Halley leaves at most 2 d^3/mx^2 (see
+    // n2_halley_step), so |d| <= 2e-2 mx is enough for every x; plain Newton (THETA_P1_F32HALLEY=0) leaves d^2/mx and
+    // needs |d| <= 2e-3 mx.  What matters is the slowest lane of the warp: with Halley the predicted start of nearly
+    // every column passes after ONE step (level changes in the sorted read-depth ratios and the first columns after an
+    // odometer carry included), with Newton 11% of the columns -- i.e. nearly every warp step -- needed a second one.
     for (int it = 0; it < nit; ++it) {
+        if (used) *used = it + 1;
         const float z = x * S1f;
         const float y = (1.0f - x) * Af;
         float s = 0.0f, sp = 0.0f, spp = 0.0f;
@@ -340,7 +342,7 @@ __device__ __forceinline__ float n2_refine32(const double (&R)[KV], double S1, d
         const float rfp = rcp32(sp);
         float d = s * rfp;                           // -f/f'
         const float mx = fminf(x, 1.0f - x);
-        const bool last = fabsf(d) <= (THETA_P1_F32HALLEY ? 1e-2f : 2e-3f) * mx;
+        const bool last = fabsf(d) <= (THETA_P1_F32HALLEY ? 2e-2f : 2e-3f) * mx;
         if (THETA_P1_F32HALLEY) {
             const float den = fmaf(-d * spp, rfp, 1.0f);  // 1 + d f''/(2f'),  f''/2 = -spp
             if (den > 0.5f && den < 2.0f) d *= rcp32(den);
@@ -360,7 +362,7 @@ __device__ __forceinline__ float n2_refine32(const double (&R)[KV], double S1, d
 // caller, which keeps all of it in fp32).
 template <int KV>
 __device__ __forceinline__ bool n2_root_p1(const double (&R)[KV], double S1, bool zero_r_c0, const N2Const& k, float x0f,
-                                           SolveOut& o, float& xf) {
+                                           SolveOut& o, float& xf, int* used32 = nullptr) {
     double ev[KV], nv[KV];
     double s = 0.0;
 #pragma unroll
@@ -385,7 +387,7 @@ __device__ __forceinline__ bool n2_root_p1(const double (&R)[KV], double S1, boo
         return ok;
     }
     const bool warm = (x0f > 0.0f && x0f < 1.0f);
-    xf = n2_refine32<KV>(R, S1, k.A, warm ? x0f : 0.5f, 8);
+    xf = n2_refine32<KV>(R, S1, k.A, warm ? x0f : 0.5f, 8, used32);
     double x = (double)xf;
     // first fp64 evaluation, nearly always the only one: the Halley step and the P1 test of n2_halley_step, with the
     // bracket [0, 1] and f rising folded in (when the test passes, 1 + dN f''/(2f') lies within [0.99, 1.01])

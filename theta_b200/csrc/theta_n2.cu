@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -20,6 +21,9 @@ static constexpr int kCounters = 8;
 // pass-1 tuning switches (development: -DTHETA_P1_REFINE=0 / -DTHETA_P1_INCREMENTAL=0 give the round-1 kernel back)
 #ifndef THETA_P1_REFINE
 #define THETA_P1_REFINE 1
+#endif
+#ifndef THETA_P1_DEBUGSTATS
+#define THETA_P1_DEBUGSTATS 0
 #endif
 #ifndef THETA_P1_INCREMENTAL
 #define THETA_P1_INCREMENTAL 0
@@ -197,9 +201,15 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
             float xrowf = -1.0f, drowf = 0.0f, d1rowf = 0.0f;  // first root of the row, row-to-row trend, first increment
             const double srm = T_.SR[T_.m];
             const int qhi0 = T_.qhi[0];
-            for (int t = 0; t < p.Lrun; ++t) {  // same trip count in every lane: the warp pools its thresholds every 8 columns
+            // t = -1 is a probe: the root of the first column of the row the run starts in (q_1 at its lowest admissible
+            // value, higher levels as unranked), so that the first odometer carry of the run already has the previous
+            // row's first root to start from.  Root only -- the probe column is not a candidate of this run.
+            const int q0_first = q[0];
+            for (int t = -1; t < p.Lrun; ++t) {  // same trip count in every lane: the warp pools its thresholds every 8 columns
                 if ((t & 7) == 0 && t) T = warp_min(T);
-                if (t >= cnt) continue;
+                if (t >= cnt || cnt == 0) continue;
+                const bool probe = t < 0;
+                if (probe) q[0] = max(T_.qlo[0], q[1]);
                 if (THETA_P1_INCREMENTAL == 0 || fresh) {
                     n2_groups<KT>(T_, q, R, S1, z);
                     if (THETA_P1_INCREMENTAL) {
@@ -217,12 +227,27 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
                 if (!(x0f > 0.0f && x0f < 1.0f)) x0f = xpf;  // (xpf < 0: cold start)
                 SolveOut o;
                 float xf;
+#if THETA_P1_DEBUGSTATS
+                int used32 = 0;
+                const int dcat = t == 0 ? 0 : t == 1 ? 1 : rowpos == 0 ? 2 : rowpos == 1 ? 3 : 4;
+                const bool solved_now = n2_root_p1<KT + 1>(R, S1, z, kc, x0f, o, xf, &used32);
+                atomicAdd(&p.counters[20 + dcat], 1ULL);
+                atomicAdd(&p.counters[25 + dcat], (unsigned long long)used32);
+                if (dcat == 4 && used32 >= 2) atomicAdd(&p.counters[30], 1ULL);
+                if (dcat == 4 && used32 >= 3) atomicAdd(&p.counters[31], 1ULL);
+                if (solved_now) {
+#else
                 if (n2_root_p1<KT + 1>(R, S1, z, kc, x0f, o, xf)) {
+#endif
+                    if (probe) {
+                        xrowf = xf;
+                        xpf = xf;  // (a poor but valid start for the run's first column when it is not the row's first)
+                    } else {
                     ++solved;
                     iters += o.iters;
                     const float dnew = xf - xpf;
                     if (rowpos == 0) {
-                        drowf = xrowf > 0.0f ? xf - xrowf : 0.0f;
+                        drowf = (xrowf > 0.0f && t > 0) ? xf - xrowf : 0.0f;
                         xrowf = xf;
                         rowpos = 1;
                     } else if (rowpos == 1) {
@@ -249,6 +274,14 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
                             T = fmin(T, nll);
                         }
                     }
+                    }
+                }
+                if (probe) {
+                    // back to the run's first column: a row start itself (rowpos 0, exact start) or somewhere inside the row
+                    rowpos = (q0_first == q[0]) ? 0 : 2;
+                    q[0] = q0_first;
+                    fresh = true;
+                    continue;
                 }
                 if (t + 1 < cnt) {
                     if (q[0] < qhi0) {
@@ -856,6 +889,12 @@ static void read_pass1_stats(theta_plan* pl) {
     pl->stats.min_nll = g;
     pl->stats.n_exact = ctr[5];
     pl->stats.n_bound_violations = ctr[6];
+#if THETA_P1_DEBUGSTATS
+    fprintf(stderr, "[p1 fp32 iterations] t=0: %.2f (n=%llu)  t=1: %.2f (%llu)  row start: %.2f (%llu)  second: %.2f (%llu)  rest: %.3f (%llu; >=2: %llu, >=3: %llu)\n",
+            (double)ctr[25] / (double)std::max(1ULL, ctr[20]), ctr[20], (double)ctr[26] / (double)std::max(1ULL, ctr[21]), ctr[21],
+            (double)ctr[27] / (double)std::max(1ULL, ctr[22]), ctr[22], (double)ctr[28] / (double)std::max(1ULL, ctr[23]), ctr[23],
+            (double)ctr[29] / (double)std::max(1ULL, ctr[24]), ctr[24], ctr[30], ctr[31]);
+#endif
 }
 
 extern "C" int theta_search_n2_pass1_end(theta_plan* pl, double* local_min) {
