@@ -308,9 +308,12 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
     const size_t head = sizeof(unsigned long long) * kStatusWordsX;
     int rc = THETA_OK;
     // everything one step enqueues on the stream (also what the graph captures)
-    auto enqueue = [&](size_t bytes) -> int {
+    // (with_pass1 = false: the retry after a record block that outgrew the exchange slot -- the stripe minima of pass 1 and
+    // the all-reduced minimum are still in place, so only the exchange of the minimum (idempotent), pass 2 and the gather
+    // are repeated with the larger slot)
+    auto enqueue = [&](size_t bytes, bool with_pass1 = true) -> int {
         if (debug) cudaEventRecord(c->dbg[0], st);
-        int r = theta_search_n2_pass1_begin(pl, rank_begin, rank_end, c->d_min, stream);
+        int r = with_pass1 ? theta_search_n2_pass1_begin(pl, rank_begin, rank_end, c->d_min, stream) : THETA_OK;
         if (r) return r;
         if (debug) cudaEventRecord(c->dbg[1], st);
         const bool peer = c->world > 1 && c->peer_ok && c->xcap <= kPeerRecs;
@@ -340,7 +343,13 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
         if (rc) return rc;
         const uint64_t key[5] = {pl->uid, rank_begin, rank_end, c->xcap, (uint64_t)(uintptr_t)st};
         const bool same = std::memcmp(key, c->g_key, sizeof(key)) == 0;
-        if (use_graph && same && c->g_exec) {
+        if (attempt > 0) {
+            if (c->g_exec) { cudaGraphExecDestroy(c->g_exec); c->g_exec = nullptr; }
+            std::memcpy(c->g_key, key, sizeof(key));
+            c->g_seen = 0;
+            rc = enqueue(bytes, false);
+            if (rc) return rc;
+        } else if (use_graph && same && c->g_exec) {
             theta_search_n2_graph_replay(pl, rank_begin, rank_end, stream);  // host-side bookkeeping of pass1_begin
             THETA_CUDA(cudaGraphLaunch(c->g_exec, st));
         } else {
