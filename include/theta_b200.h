@@ -153,11 +153,12 @@ int theta_search_n2_pass2(theta_plan* plan, double global_min, double prior_min,
 int theta_search_n2_pass2_dev(theta_plan* plan, const double* global_min_dev, double prior_min, theta_cand* out_host,
                               uint64_t cap, uint64_t* n_out, double* global_min_host, void* stream);
 /* Fully asynchronous form for the multi-GPU exchange (replaces returnQueue / find_mins, RunTHetA.py:141,162-171):
- * pass 2 is enqueued and its status block + first `cap` raw records land in the caller's DEVICE buffer
- * [uint64 status[32] | theta_cand records[cap]] -- the operand of ncclAllGather -- with no host synchronisation.
- * status[11] (records emitted) > cap means the shard overflowed the buffer (fall back to theta_search_n2_pass2_dev).
- * After synchronising, the caller passes its own status words to _async_done (statistics) and the union of all
- * shards' raw records to theta_filter_records (sort by rank + the exact superset filter of the fold replay). */
+ * pass 2 is enqueued and its status block + this shard's records -- sorted by rank and filtered ON THE DEVICE to what the
+ * fold replay needs (strict prefix minima w.r.t. prior_min, everything within 2.5 margins of the global minimum, NaN) --
+ * land in the caller's DEVICE buffer [uint64 status[32] | theta_cand records[cap]], the operand of the all-gather, with no
+ * host synchronisation.  status[11] = records kept; > cap means they did not fit (retry with a larger block).
+ * After synchronising, the caller passes its own status words to _async_done (statistics) and the concatenation of all
+ * shards' blocks to theta_filter_records (the same filter over the union: a linear pass, the blocks arrive sorted). */
 int theta_search_n2_pass2_enqueue(theta_plan* plan, const double* global_min_dev, double prior_min, void* out_dev,
                                   uint64_t cap, void* stream);
 int theta_search_n2_async_done(theta_plan* plan, const unsigned long long* status_host);

@@ -418,3 +418,34 @@ def test_lower_bound_above_upper_bound_follows_the_reference(lib, golden, tmp_pa
         for b, g in zip(best, case["best"]):
             assert np.array_equal(b[0], np.array(g["C"]))
             assert abs(b[1][0] - g["mu"][0]) <= 1e-9 and abs(b[2] - g["nll"]) <= 1e-10 * g["nll"]
+
+
+def test_device_record_filter_equals_host_filter(lib):
+    """records_filter_kernel (the exchange block of theta_search_n2_pass2_enqueue: this shard's records sorted by rank and
+    filtered on the device) == the host path (theta_search_n2_pass2_dev: D2H of the raw records, std::sort, the filter of
+    the fold replay), byte for byte, on whole spaces and on rank windows that start mid-space (prior = +inf)."""
+    import torch
+    O = _oracle()
+    cases = [(O.synthetic_problem_n2(150, 5, seed=1), None), (O.synthetic_problem_n2(60, 4, seed=3), None),
+             (O.synthetic_problem_n2(150, 5, seed=1), (7_000_000, 19_000_000)), (O.synthetic_problem_n2(40, 3, seed=2), (5, 900))]
+    for P, win in cases:
+        plan = lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"])
+        b, e = win if win else (0, plan.count())
+        plan.pass1_begin(b, e, None, None)
+        ref, g = plan.pass2_dev(None, float("inf"), None)
+        cap = 4096
+        gmin = torch.zeros(1, dtype=torch.float64, device="cuda")
+        out = torch.zeros(32 * 8 + cap * lib.CAND_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        plan.pass1_begin(b, e, gmin.data_ptr(), None)
+        plan.pass2_enqueue(gmin.data_ptr(), out.data_ptr(), cap, float("inf"), None)
+        torch.cuda.synchronize()
+        raw = out.cpu().numpy()
+        status = raw[:256].view(np.uint64)
+        plan.async_done(status)
+        n = int(status[11])
+        assert n == len(ref), (n, len(ref))
+        got = raw[256:256 + n * lib.CAND_DTYPE.itemsize].view(lib.CAND_DTYPE)
+        assert float(gmin.item()) == g
+        assert got.tobytes() == ref.tobytes()
+        assert np.all(np.diff(got["rank"].astype(np.int64)) > 0)
+        plan.close()

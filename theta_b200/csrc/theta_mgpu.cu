@@ -182,6 +182,7 @@ struct theta_comm {
     bool peer_ok = false;
     unsigned long long* h_err = nullptr;  // pinned
     cudaStream_t st_own = nullptr;        // used when the caller passes the legacy default stream (which cannot be captured)
+    std::vector<theta_cand> all;          // the gathered records of a step (reused)
 };
 
 static int comm_buffers(theta_comm* c, size_t block_bytes) {
@@ -304,6 +305,10 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
     static const bool debug = getenv("THETA_DEBUG") != nullptr;
     static const bool graph_env = !debug && !(getenv("THETA_NO_GRAPH") && getenv("THETA_NO_GRAPH")[0] == '1');
     const bool use_graph = graph_env && !c->g_disabled;
+    static const bool hdbg = getenv("THETA_DEBUG_HOST") != nullptr;  // host-side timeline of the step, one line per call
+    const auto th0 = std::chrono::steady_clock::now();
+    auto th1 = th0, th2 = th0;
+    const char* how = "eager";
     if (debug && !c->dbg[0]) for (int i = 0; i < 5; ++i) cudaEventCreate(&c->dbg[i]);
     const size_t head = sizeof(unsigned long long) * kStatusWordsX;
     int rc = THETA_OK;
@@ -352,6 +357,7 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
         } else if (use_graph && same && c->g_exec) {
             theta_search_n2_graph_replay(pl, rank_begin, rank_end, stream);  // host-side bookkeeping of pass1_begin
             THETA_CUDA(cudaGraphLaunch(c->g_exec, st));
+            how = "graph";
         } else {
             if (!same) {
                 if (c->g_exec) { cudaGraphExecDestroy(c->g_exec); c->g_exec = nullptr; }
@@ -375,6 +381,7 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
                 }
                 if (graph) cudaGraphDestroy(graph);
                 if (ok) ok = cudaGraphLaunch(c->g_exec, st) == cudaSuccess;
+                how = ok ? "capture" : "capture-failed";
                 if (!ok) {
                     cudaGetLastError();
                     if (c->g_exec) { cudaGraphExecDestroy(c->g_exec); c->g_exec = nullptr; }
@@ -387,7 +394,9 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
                 if (rc) return rc;
             }
         }
+        if (hdbg) th1 = std::chrono::steady_clock::now();
         THETA_CUDA(cudaStreamSynchronize(st));
+        if (hdbg) th2 = std::chrono::steady_clock::now();
         if (c->h_err && c->peer_ok && *c->h_err) { set_error("peer exchange timed out (a rank did not reach the step)"); return THETA_ERR_CUDA; }
         if (debug) {
             float t[4];
@@ -405,9 +414,19 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
         c->xcap = worst + 64;  // every rank sees the same counts and takes the same branch
     }
     const size_t bytes = head + sizeof(theta_cand) * c->xcap;
+    auto tp = std::chrono::steady_clock::now();
+    double tpart[4] = {0, 0, 0, 0};
+    auto lap = [&](int i) {
+        if (!hdbg) return;
+        const auto now = std::chrono::steady_clock::now();
+        tpart[i] = std::chrono::duration<double, std::micro>(now - tp).count();
+        tp = now;
+    };
     rc = theta_search_n2_async_done(pl, reinterpret_cast<const unsigned long long*>(c->h_recv + (size_t)c->rank * bytes));
     if (rc) return rc;
-    std::vector<theta_cand> all;
+    lap(0);
+    std::vector<theta_cand>& all = c->all;
+    all.clear();
     double g = INFINITY;
     uint64_t solved = 0;
     for (int r = 0; r < c->world; ++r) {
@@ -420,14 +439,28 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
         const theta_cand* recs = reinterpret_cast<const theta_cand*>(blk + head);
         all.insert(all.end(), recs, recs + stw[kStEmitted]);
     }
+    lap(1);
     uint64_t n = 0;
     rc = theta_filter_records(all.data(), all.size(), INFINITY, g + 2.5 * THETA_TIE_MARGIN, &n);
     if (rc) return rc;
+    lap(2);
     if (global_min) *global_min = g;
     if (n_solved_total) *n_solved_total = solved;
     *n_out = n;
     if (n > cap) { set_error("%llu records, the caller's buffer holds %llu", (unsigned long long)n, (unsigned long long)cap); return THETA_ERR_OVERFLOW; }
     if (out_host && n) std::memcpy(out_host, all.data(), sizeof(theta_cand) * n);
+    lap(3);
+    if (hdbg) {
+        const auto th3 = std::chrono::steady_clock::now();
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::micro>(b - a).count();
+        };
+        theta_search_stats sst{};
+        theta_search_stats_get(pl, &sst);
+        fprintf(stderr, "[theta dist host %d/%d] %s%s: enqueue %.1f us, wait %.1f us, post %.1f us (stats %.1f, gather %.1f [%zu records], filter %.1f, copy %.1f); pass1 %.1f us, pass2 %.1f us (events)\n",
+                c->rank, c->world, how, (c->world > 1 && c->peer_ok) ? "+peer" : "", us(th0, th1), us(th1, th2), us(th2, th3),
+                tpart[0], tpart[1], all.size(), tpart[2], tpart[3], sst.ms_pass1 * 1e3, sst.ms_pass2 * 1e3);
+    }
     return THETA_OK;
 }
 

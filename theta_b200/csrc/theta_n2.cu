@@ -458,7 +458,8 @@ static int launch_search_v(const theta_plan* plan, const SearchParams& sp, cudaS
     return THETA_OK;
 }
 
-// THETA_SEARCH_MINB (tuning knob): resident CTAs per SM the pass-1 kernel is compiled for (6 -> 80 registers, 5 -> 96, 4 -> 128)
+// THETA_SEARCH_MINB (tuning knob): resident CTAs per SM the pass-1 kernel is compiled for (6 -> 80 registers, 5 -> 96, 4 -> 128);
+// unset: chosen by the level count
 static int g_search_minb = -1;
 
 template <int KT, bool EMIT>
@@ -466,9 +467,10 @@ static int launch_search(const theta_plan* plan, const SearchParams& sp, cudaStr
     if (EMIT) return launch_search_v<KT, EMIT, 6>(plan, sp, st);
     if (g_search_minb < 0) {
         const char* e = getenv("THETA_SEARCH_MINB");
-        g_search_minb = e ? atoi(e) : 5;
+        g_search_minb = e ? atoi(e) : 0;
     }
-    switch (g_search_minb) {
+    // measured on B200 (pass 1, m=150): K=5 0.555 ms at 5 CTAs/SM vs 0.562 at 6; K=7 14.0 ms at 5 vs 13.5 at 6
+    switch (g_search_minb ? g_search_minb : (KT <= 5 ? 5 : 6)) {
         case 4: return launch_search_v<KT, false, 4>(plan, sp, st);
         case 5: return launch_search_v<KT, false, 5>(plan, sp, st);
         default: return launch_search_v<KT, false, 6>(plan, sp, st);
@@ -793,6 +795,137 @@ __global__ void __launch_bounds__(1024) stripe_scan_kernel(const double* __restr
     }
     if (tid < kCounters) status[kCounters + tid] = 0ULL;  // pass-2 counters
 }
+
+// The records pass 2 emits are a superset of what the fold replay needs (every lane keeps its own running minimum, and
+// with prior = +inf the first stripes of a shard emit nearly all their candidates: ~1 400 records per shard on config #2
+// against ~100 that matter).  Sorting and filtering them on the host (theta_filter_records) was the largest fixed cost of
+// a multi-GPU step: every rank sorted the union of all shards' records, 0.4 ms at 8 GPUs.  This kernel does the filter
+// where the records are: one block sorts the shard's records by rank (bitonic, shared memory), takes the exclusive
+// prefix minimum of the NLL in rank order and keeps   NaN  |  NLL < min(prior, everything before)  |  NLL <= near_thr
+// -- exactly theta_filter_records on this shard.  A record dropped here is dropped by the filter over the union as well
+// (its running minimum only gets lower with more shards in front), so the host is left with a linear pass over the
+// concatenated blocks.  Output block: the status words (kStEmitted := records kept) followed by the kept records in rank
+// order.  More than kFilterMax records (or than fit `cap`): the block is passed through unfiltered / flagged as overflow
+// through kStEmitted > cap, and the caller falls back to the host filter / a larger exchange slot.
+static constexpr int kFilterMax = 4096;
+static constexpr size_t kFilterSmem = (2 * sizeof(unsigned long long) + sizeof(unsigned short)) * kFilterMax;
+static constexpr int kStEmittedWord = kCounters + 3;
+__global__ void __launch_bounds__(1024) records_filter_kernel(const theta_cand* __restrict__ emit, unsigned long long emit_cap,
+                                                              const unsigned long long* __restrict__ status,
+                                                              const double* __restrict__ gmin_dev, double prior_min, double margin,
+                                                              unsigned char* __restrict__ out, unsigned long long cap) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(fsm);            // [kFilterMax] rank
+    double* val = reinterpret_cast<double*>(fsm + sizeof(unsigned long long) * kFilterMax);  // [kFilterMax] NLL in rank order
+    unsigned short* idx = reinterpret_cast<unsigned short*>(fsm + 2 * sizeof(unsigned long long) * kFilterMax);  // [kFilterMax]
+    __shared__ double s_w[32];
+    __shared__ unsigned int s_c[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long* out_status = reinterpret_cast<unsigned long long*>(out);
+    theta_cand* out_recs = reinterpret_cast<theta_cand*>(out + sizeof(unsigned long long) * kStatusWords);
+    const unsigned long long n_raw = status[kStEmittedWord];
+    const unsigned long long n_have = n_raw < emit_cap ? n_raw : emit_cap;
+    if (n_raw > emit_cap || n_have > (unsigned long long)kFilterMax) {
+        // too many to sort here: hand over what fits, unfiltered, with the raw count (the caller's overflow / host-filter path)
+        for (int i = tid; i < kStatusWords; i += 1024) out_status[i] = status[i];
+        const unsigned long long ncopy = n_have < cap ? n_have : cap;
+        for (unsigned long long i = tid; i < ncopy; i += 1024) out_recs[i] = emit[i];
+        return;
+    }
+    const int n = (int)n_have;
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int i = tid; i < P; i += 1024) {
+        key[i] = i < n ? emit[i].rank : ~0ULL;
+        idx[i] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += 1024) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = key[i], b = key[l];
+                    if ((a > b) == up) {
+                        key[i] = b; key[l] = a;
+                        const unsigned short t = idx[i]; idx[i] = idx[l]; idx[l] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < P; i += 1024) val[i] = i < n ? emit[idx[i]].nll : INFINITY;
+    __syncthreads();
+    // thread t owns the contiguous chunk [t*per, (t+1)*per) of the sorted records
+    const int per = (P + 1023) / 1024;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    double cm = INFINITY;
+    for (int i = lo; i < hi; ++i) { const double v = val[i]; if (v == v) cm = fmin(cm, v); }
+    double incl = cm;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = fmin(incl, y);
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        double w = s_w[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w = fmin(w, y);
+        }
+        s_w[lane] = w;
+    }
+    __syncthreads();
+    double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) prev = INFINITY;
+    const double g = gmin_dev ? *gmin_dev : __longlong_as_double((long long)status[kStLocalMin]);
+    const double near_thr = g + margin;
+    const double run0 = fmin(prior_min, fmin(warp > 0 ? s_w[warp - 1] : INFINITY, prev));  // min of everything before the chunk
+    // (theta_filter_records: keep = NaN || v < run || v <= near_thr; run = min(run, v) -- a NaN never lowers it)
+    unsigned int kept = 0;
+    {
+        double run = run0;
+        for (int i = lo; i < hi; ++i) {
+            const double v = val[i];
+            if ((v != v) || v < run || v <= near_thr) ++kept;
+            if (v < run) run = v;
+        }
+    }
+    unsigned int pos = kept;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, pos, o);
+        if (lane >= o) pos += y;
+    }
+    if (lane == 31) s_c[warp] = pos;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = s_c[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        s_c[lane] = w;
+    }
+    __syncthreads();
+    const unsigned int total = s_c[31];
+    unsigned int at = (warp > 0 ? s_c[warp - 1] : 0u) + pos - kept;
+    if ((unsigned long long)total <= cap) {
+        double run = run0;
+        for (int i = lo; i < hi; ++i) {
+            const double v = val[i];
+            if ((v != v) || v < run || v <= near_thr) out_recs[at++] = emit[idx[i]];
+            if (v < run) run = v;
+        }
+    }
+    for (int i = tid; i < kStatusWords; i += 1024) out_status[i] = i == kStEmittedWord ? (unsigned long long)total : status[i];
+}
 }  // namespace theta
 
 // timing events of the plan: inside a stream capture they are recorded as external event nodes, so that they can
@@ -806,6 +939,8 @@ static cudaError_t record_event(cudaEvent_t ev, cudaStream_t st) {
 
 static int plan_events(theta_plan* pl) {
     if (!pl->ev0) {
+        // (per device, once per plan and outside any stream capture: the first step of a plan always runs eagerly)
+        THETA_CUDA(cudaFuncSetAttribute(records_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmem));
         THETA_CUDA(cudaEventCreate(&pl->ev0)); THETA_CUDA(cudaEventCreate(&pl->ev1));
         THETA_CUDA(cudaEventCreate(&pl->ev2)); THETA_CUDA(cudaEventCreate(&pl->ev3));
     }
@@ -1018,11 +1153,13 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
     return THETA_OK;
 }
 
-// Fully asynchronous pass 2 for the multi-GPU exchange: list scan + emit kernel are enqueued, then the status
-// block and the first `cap` raw (unsorted, unfiltered) records are copied device-to-device into the caller's
-// buffer  [ u64 status[32] | theta_cand records[cap] ]  -- the operand of the all-gather.  Nothing is waited for.
-// The caller fetches the gathered buffers, then hands its own status words to theta_search_n2_async_done and
-// all raw records to theta_filter_records.  status[8+3] > cap means this shard overflowed the exchange buffer.
+// Fully asynchronous pass 2 for the multi-GPU exchange: list scan, emit kernel and records_filter_kernel are enqueued;
+// the caller's device buffer receives  [ u64 status[32] | theta_cand records[cap] ]  -- the operand of the all-gather:
+// this shard's records sorted by rank and filtered exactly as theta_filter_records would (prior_min, global minimum + 2.5
+// margins), status[8+3] = their number.  Nothing is waited for.  The caller fetches the gathered buffers, hands its own
+// status words to theta_search_n2_async_done and the concatenated records to theta_filter_records (a linear pass when
+// every block arrives sorted).  status[8+3] > cap means this shard's records did not fit the exchange block (or were too
+// many to be filtered on the device and are handed over raw once the block is large enough).
 extern "C" int theta_search_n2_pass2_enqueue(theta_plan* pl, const double* global_min_dev, double prior_min,
                                              void* out_dev, uint64_t cap, void* stream) {
     if (!pl || !out_dev || cap == 0) { set_error("null argument"); return THETA_ERR_INVALID; }
@@ -1059,10 +1196,10 @@ extern "C" int theta_search_n2_pass2_enqueue(theta_plan* pl, const double* globa
         if (rc) return rc;
     }
     THETA_CUDA(record_event(pl->ev3, st));
-    unsigned char* out = static_cast<unsigned char*>(out_dev);
-    THETA_CUDA(cudaMemcpyAsync(out, pl->d_counters, sizeof(unsigned long long) * kStatusWords, cudaMemcpyDeviceToDevice, st));
-    THETA_CUDA(cudaMemcpyAsync(out + sizeof(unsigned long long) * kStatusWords, pl->d_emit, sizeof(theta_cand) * cap,
-                               cudaMemcpyDeviceToDevice, st));
+    // status block + this shard's records, sorted by rank and filtered to what the fold replay needs, into the exchange block
+    records_filter_kernel<<<1, 1024, kFilterSmem, st>>>(pl->d_emit, pl->emit_cap, pl->d_counters, global_min_dev, prior_min, margin,
+                                                         static_cast<unsigned char*>(out_dev), cap);
+    THETA_CUDA(cudaGetLastError());
     return THETA_OK;
 }
 
@@ -1082,7 +1219,9 @@ extern "C" int theta_search_n2_async_done(theta_plan* pl, const unsigned long lo
 // of the sequence (starting from prior_min) and everything within near_thr.  In place; returns the new count.
 extern "C" int theta_filter_records(theta_cand* recs, uint64_t n, double prior_min, double near_thr, uint64_t* n_out) {
     if ((!recs && n) || !n_out) { set_error("null argument"); return THETA_ERR_INVALID; }
-    std::sort(recs, recs + n, [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; });
+    // (blocks that went through records_filter_kernel arrive sorted: the concatenation of the shards' blocks then is, too)
+    const auto by_rank = [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; };
+    if (!std::is_sorted(recs, recs + n, by_rank)) std::sort(recs, recs + n, by_rank);
     size_t w = 0;
     double run = prior_min;
     for (size_t i = 0; i < n; ++i) {
