@@ -371,11 +371,11 @@ def main():
     if world > 1:
         dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
     # bytes that cross PCIe per call and rank: H2D = the plan arena (count tables, r, rN, their prefix sums, status
-    # block); D2H = the status block + the record window (N=1: 1024 x 48 B speculative; N>1: world x (256 B + 256 x 48 B))
+    # block); D2H = the status block + the device-filtered records (256 B + 256 x 48 B per shard; N>1: the gathered blocks of all shards)
     up256 = lambda v: (v + 255) & ~255
     h2d = (up256(plan.table_bytes()) + 2 * up256(8 * plan.m) + 2 * up256(8 * (plan.pitch + 1)) + up256(4 * (plan.pitch + 1))
            + up256(8 * 32))
-    d2h = 8 * 32 + 48 * 1024 if world == 1 else world * (8 * 32 + 48 * 256)
+    d2h = 8 * 32 + 48 * 256 if world == 1 else world * (8 * 32 + 48 * 256)
     e2e = {"value": total * args.steps / float(tdt.item()), "unit": "candidates/s",
            "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
            "ms_per_step": 1e3 * float(tdt.item()) / args.steps,

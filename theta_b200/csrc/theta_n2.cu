@@ -659,6 +659,7 @@ extern "C" void theta_plan_destroy(theta_plan* pl) {
     theta::dfree(pl->d_stripe_min); theta::dfree(pl->d_emit);
     theta::dfree(pl->d_list); theta::dfree(pl->d_prior);
     theta::hfree(pl->h_emit); theta::hfree(pl->h_ctr);
+    theta::dfree(pl->d_xblk); theta::hfree(pl->h_xblk);
     if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); cudaEventDestroy(pl->ev2); cudaEventDestroy(pl->ev3); }
     delete pl;
 }
@@ -1065,7 +1066,7 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
     const uint64_t stripes = pl->p1_stripes;
     const double margin = 2.5 * THETA_TIE_MARGIN;
     size_t want = std::max<size_t>(1 << 14, pl->emit_cap);
-    const size_t spec = 1024;  // records copied back speculatively together with the status block (one sync)
+    bool filtered = false;  // the records came back sorted and filtered by the device
     theta_cand* host = nullptr;
     size_t n_host = 0;
     double g = INFINITY;
@@ -1076,12 +1077,6 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
             cudaError_t e = theta::dmalloc(&pl->d_emit, sizeof(theta_cand) * want);
             if (e != cudaSuccess) { rc = cuda_fail(e, "emit buffer", __FILE__, __LINE__); break; }
             pl->emit_cap = want;
-        }
-        if (std::max(spec, want) > pl->h_emit_cap) {
-            theta::hfree(pl->h_emit); pl->h_emit = nullptr; pl->h_emit_cap = 0;
-            cudaError_t e = theta::hmalloc(&pl->h_emit, sizeof(theta_cand) * std::max(spec, want));
-            if (e != cudaSuccess) { rc = cuda_fail(e, "emit staging", __FILE__, __LINE__); break; }
-            pl->h_emit_cap = std::max(spec, want);
         }
         record_event(pl->ev2, st);
         // (re)builds the list and zeroes the pass-2 counters
@@ -1106,24 +1101,55 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
             if (rc) break;
         }
         record_event(pl->ev3, st);
-        cudaError_t e = cudaMemcpyAsync(pl->h_ctr, pl->d_counters, sizeof(unsigned long long) * kStatusWords, cudaMemcpyDeviceToHost, st);
-        const size_t n_spec = std::min(spec, pl->emit_cap);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(pl->h_emit, pl->d_emit, sizeof(theta_cand) * n_spec, cudaMemcpyDeviceToHost, st);
+        // The shard's records are sorted by rank and filtered on the device (records_filter_kernel) into one small block
+        // [status | records]; the status words and the first kSpecRecs records come back in ONE copy and one wait.
+        constexpr size_t kXCap = 1024, kSpecRecs = 256, kHead = sizeof(unsigned long long) * kStatusWords;
+        if (!pl->d_xblk) {
+            cudaError_t ea = theta::dmalloc(&pl->d_xblk, kHead + sizeof(theta_cand) * kXCap);
+            if (ea == cudaSuccess) ea = theta::hmalloc(&pl->h_xblk, kHead + sizeof(theta_cand) * kXCap);
+            if (ea != cudaSuccess) { rc = cuda_fail(ea, "record block", __FILE__, __LINE__); break; }
+        }
+        records_filter_kernel<<<1, 1024, kFilterSmem, st>>>(pl->d_emit, pl->emit_cap, pl->d_counters, global_min_dev, prior_min, margin,
+                                                             pl->d_xblk, kXCap);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pl->h_xblk, pl->d_xblk, kHead + sizeof(theta_cand) * kSpecRecs, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "pass2", __FILE__, __LINE__); break; }
+        std::memcpy(pl->h_ctr, pl->h_xblk, kHead);
         pl->p1_pending = false;
         read_pass1_stats(pl);
         cudaEventElapsedTime(&pl->stats.ms_pass2, pl->ev2, pl->ev3);
         const unsigned long long* ctr = pl->h_ctr;
         std::memcpy(&g, &ctr[kStGlobalMin], sizeof(double));
         pl->stats.n_rescanned = ctr[kStList];
+        const unsigned long long kept = ctr[kCounters + 3];
+        if (kept <= kXCap) {
+            if (kept > kSpecRecs) {
+                e = cudaMemcpyAsync(pl->h_xblk + kHead + sizeof(theta_cand) * kSpecRecs, pl->d_xblk + kHead + sizeof(theta_cand) * kSpecRecs,
+                                    sizeof(theta_cand) * (kept - kSpecRecs), cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) { rc = cuda_fail(e, "pass2 D2H", __FILE__, __LINE__); break; }
+            }
+            host = reinterpret_cast<theta_cand*>(pl->h_xblk + kHead);
+            n_host = (size_t)kept;
+            filtered = true;
+            break;
+        }
+        // more records than the block holds, or too many for the device-side sort: the raw records come back and the
+        // host sorts and filters them (below)
+        e = cudaMemcpy(pl->h_ctr, pl->d_counters, sizeof(unsigned long long) * kStatusWords, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "pass2 status", __FILE__, __LINE__); break; }
         const unsigned long long emitted = ctr[kCounters + 3];
         if (emitted > pl->emit_cap) { want = (size_t)emitted + 1024; continue; }
-        if (emitted > n_spec) {
-            e = cudaMemcpyAsync(pl->h_emit + n_spec, pl->d_emit + n_spec, sizeof(theta_cand) * (emitted - n_spec), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { rc = cuda_fail(e, "pass2 D2H", __FILE__, __LINE__); break; }
+        if ((size_t)emitted > pl->h_emit_cap) {
+            theta::hfree(pl->h_emit); pl->h_emit = nullptr; pl->h_emit_cap = 0;
+            e = theta::hmalloc(&pl->h_emit, sizeof(theta_cand) * (size_t)emitted);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "emit staging", __FILE__, __LINE__); break; }
+            pl->h_emit_cap = (size_t)emitted;
         }
+        e = cudaMemcpyAsync(pl->h_emit, pl->d_emit, sizeof(theta_cand) * emitted, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "pass2 D2H", __FILE__, __LINE__); break; }
         host = pl->h_emit;
         n_host = (size_t)emitted;
         break;
@@ -1131,8 +1157,9 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
     if (rc) return rc;
     if (global_min_host) *global_min_host = g;
     const double near_thr = g + margin;
-    std::sort(host, host + n_host, [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; });
-    {   // keep exactly: strict prefix minima of the whole stream (w.r.t. everything before this shard),
+    if (!filtered) {
+        std::sort(host, host + n_host, [](const theta_cand& a, const theta_cand& b) { return a.rank < b.rank; });
+        // keep exactly: strict prefix minima of the whole stream (w.r.t. everything before this shard),
         // the near-minimum set, and NaN values -- the per-lane filter on the device emits a superset
         size_t w = 0;
         double run = prior_min;

@@ -157,6 +157,8 @@ struct theta_plan {
     bool p1_pending = false;
     unsigned long long* d_counters = nullptr;  // [0] stripe ticket, [1] solved, [2] newton iters, [3] emitted, [4] nan-nll
     theta_cand* d_emit = nullptr;
+    unsigned char* d_xblk = nullptr;  // [status | filtered records] of the single-shard pass 2 (device) ...
+    unsigned char* h_xblk = nullptr;  // ... and its pinned copy
     size_t emit_cap = 0;
     double2* d_logtab = nullptr;  // fast_log table (theta_core.cuh)
     uint32_t* d_list = nullptr;   // pass-2 stripe list / per-stripe prior minima
