@@ -420,32 +420,44 @@ def test_lower_bound_above_upper_bound_follows_the_reference(lib, golden, tmp_pa
             assert abs(b[1][0] - g["mu"][0]) <= 1e-9 and abs(b[2] - g["nll"]) <= 1e-10 * g["nll"]
 
 
-def test_device_record_filter_equals_host_filter(lib):
-    """records_filter_kernel (the exchange block of theta_search_n2_pass2_enqueue: this shard's records sorted by rank and
-    filtered on the device) == the host path (theta_search_n2_pass2_dev: D2H of the raw records, std::sort, the filter of
-    the fold replay), byte for byte, on whole spaces and on rank windows that start mid-space (prior = +inf)."""
+def test_device_record_filter_equals_host_filter(lib, monkeypatch):
+    """records_filter_kernel (this shard's records sorted by rank and filtered on the device: the exchange block of
+    theta_search_n2_pass2_enqueue and the result of theta_search_n2_pass2_dev) == the host filter of the raw records
+    (THETA_FILTER_HOST=1: D2H of everything pass 2 emitted, std::sort, the filter of the fold replay), byte for byte, on
+    whole spaces and on rank windows that start mid-space (prior = +inf) -- with the sort in shared memory and, with
+    THETA_FILTER_FORCE_GLOBAL=1, in the plan's global scratch area (the path of record blocks above 4 096)."""
     import torch
     O = _oracle()
     cases = [(O.synthetic_problem_n2(150, 5, seed=1), None), (O.synthetic_problem_n2(60, 4, seed=3), None),
-             (O.synthetic_problem_n2(150, 5, seed=1), (7_000_000, 19_000_000)), (O.synthetic_problem_n2(40, 3, seed=2), (5, 900))]
+             (O.synthetic_problem_n2(150, 5, seed=1), (7_000_000, 19_000_000)), (O.synthetic_problem_n2(40, 3, seed=2), (5, 900)),
+             (O.synthetic_problem_n2(150, 7, seed=1), (100_000_000, 400_000_000))]
     for P, win in cases:
         plan = lib.Plan(2, P["r"], P["rN"], P["lower"], P["upper"])
         b, e = win if win else (0, plan.count())
+        monkeypatch.setenv("THETA_FILTER_HOST", "1")
         plan.pass1_begin(b, e, None, None)
         ref, g = plan.pass2_dev(None, float("inf"), None)
-        cap = 4096
-        gmin = torch.zeros(1, dtype=torch.float64, device="cuda")
-        out = torch.zeros(32 * 8 + cap * lib.CAND_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-        plan.pass1_begin(b, e, gmin.data_ptr(), None)
-        plan.pass2_enqueue(gmin.data_ptr(), out.data_ptr(), cap, float("inf"), None)
-        torch.cuda.synchronize()
-        raw = out.cpu().numpy()
-        status = raw[:256].view(np.uint64)
-        plan.async_done(status)
-        n = int(status[11])
-        assert n == len(ref), (n, len(ref))
-        got = raw[256:256 + n * lib.CAND_DTYPE.itemsize].view(lib.CAND_DTYPE)
-        assert float(gmin.item()) == g
-        assert got.tobytes() == ref.tobytes()
-        assert np.all(np.diff(got["rank"].astype(np.int64)) > 0)
+        monkeypatch.delenv("THETA_FILTER_HOST")
+        assert len(ref) > 0
+        for force_global in ("0", "1"):
+            monkeypatch.setenv("THETA_FILTER_FORCE_GLOBAL", force_global)
+            plan.pass1_begin(b, e, None, None)
+            dev, g2 = plan.pass2_dev(None, float("inf"), None)
+            assert g2 == g and dev.tobytes() == ref.tobytes(), (force_global, len(dev), len(ref))
+            cap = 4096
+            gmin = torch.zeros(1, dtype=torch.float64, device="cuda")
+            out = torch.zeros(32 * 8 + cap * lib.CAND_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+            plan.pass1_begin(b, e, gmin.data_ptr(), None)
+            plan.pass2_enqueue(gmin.data_ptr(), out.data_ptr(), cap, float("inf"), None)
+            torch.cuda.synchronize()
+            raw = out.cpu().numpy()
+            status = raw[:256].view(np.uint64)
+            plan.async_done(status)
+            n = int(status[11])
+            assert n == len(ref), (n, len(ref))
+            got = raw[256:256 + n * lib.CAND_DTYPE.itemsize].view(lib.CAND_DTYPE)
+            assert float(gmin.item()) == g
+            assert got.tobytes() == ref.tobytes()
+            assert np.all(np.diff(got["rank"].astype(np.int64)) > 0)
+        monkeypatch.delenv("THETA_FILTER_FORCE_GLOBAL")
         plan.close()

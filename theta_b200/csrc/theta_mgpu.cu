@@ -309,6 +309,7 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
     const auto th0 = std::chrono::steady_clock::now();
     auto th1 = th0, th2 = th0;
     const char* how = "eager";
+    int attempts = 0;
     if (debug && !c->dbg[0]) for (int i = 0; i < 5; ++i) cudaEventCreate(&c->dbg[i]);
     const size_t head = sizeof(unsigned long long) * kStatusWordsX;
     int rc = THETA_OK;
@@ -394,6 +395,7 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
                 if (rc) return rc;
             }
         }
+        ++attempts;
         if (hdbg) th1 = std::chrono::steady_clock::now();
         THETA_CUDA(cudaStreamSynchronize(st));
         if (hdbg) th2 = std::chrono::steady_clock::now();
@@ -457,8 +459,8 @@ extern "C" int theta_search_n2_dist(theta_plan* pl, theta_comm* c, uint64_t rank
         };
         theta_search_stats sst{};
         theta_search_stats_get(pl, &sst);
-        fprintf(stderr, "[theta dist host %d/%d] %s%s: enqueue %.1f us, wait %.1f us, post %.1f us (stats %.1f, gather %.1f [%zu records], filter %.1f, copy %.1f); pass1 %.1f us, pass2 %.1f us (events)\n",
-                c->rank, c->world, how, (c->world > 1 && c->peer_ok) ? "+peer" : "", us(th0, th1), us(th1, th2), us(th2, th3),
+        fprintf(stderr, "[theta dist host %d/%d] %s%s x%d: enqueue %.1f us, wait %.1f us, post %.1f us (stats %.1f, gather %.1f [%zu records], filter %.1f, copy %.1f); pass1 %.1f us, pass2 %.1f us (events)\n",
+                c->rank, c->world, how, (c->world > 1 && c->peer_ok) ? "+peer" : "", attempts, us(th0, th1), us(th1, th2), us(th2, th3),
                 tpart[0], tpart[1], all.size(), tpart[2], tpart[3], sst.ms_pass1 * 1e3, sst.ms_pass2 * 1e3);
     }
     return THETA_OK;

@@ -120,7 +120,80 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
         const int cnt = r0 < s_end ? (int)min((uint64_t)p.Lrun, s_end - r0) : 0;
         int q[KT];
         if (cnt) n2_unrank<KT>(T_, r0, q);
-        if constexpr (EMIT || !THETA_P1_REFINE) {
+        if constexpr (EMIT) {
+            // Pass 2: a unit is 32 lanes x Lrun (<= 4) consecutive ranks, lane-major.  Phase 1 evaluates every candidate of
+            // the unit (warm-started); phase 2 decides what to emit from the EXACT prefix minimum of the unit in rank order
+            // (an exclusive prefix-min over the lanes plus the lane's own earlier columns) on top of the stripe's prior --
+            // with only a per-lane running minimum every lane of a record stripe emitted a column or two, ~1 400 records
+            // per shard on config #2 against the ~100 that matter; phase 3 walks the run again and solves the few emitted
+            // columns from the cold start (the record must not depend on how the range was cut: SURVEY 8e).
+            constexpr int kRunMax = 4;  // >= Lrun of every pass-2 launch (theta_search_n2_pass2_*)
+            double nl[kRunMax];
+            float xpf = -1.0f;  // previous root (phase 1 only steers the decision: the fp32-refined solver of pass 1 will do)
+            double lanemin = INFINITY;
+#pragma unroll
+            for (int t = 0; t < kRunMax; ++t) {
+                nl[t] = INFINITY;  // a None candidate is never emitted
+                if (t < cnt) {
+                    double R[KT + 1], S1;
+                    bool z;
+                    n2_groups<KT>(T_, q, R, S1, z);
+                    SolveOut o;
+                    float xf;
+                    if (n2_root_p1<KT + 1>(R, S1, z, kc, xpf, o, xf)) {
+                        xpf = xf;
+                        nl[t] = n2_l2<KT + 1>(R, S1, o.mu, kc, s_logtab);
+                        lanemin = fmin(lanemin, nl[t]);  // (fmin ignores a NaN NLL)
+                    }
+                    if (t + 1 < cnt) n2_next<KT>(T_, q);
+                }
+            }
+            double run = lanemin;  // inclusive prefix-min over the lanes ...
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double y = __shfl_up_sync(0xffffffffu, run, o);
+                if (lane >= o) run = fmin(run, y);
+            }
+            run = __shfl_up_sync(0xffffffffu, run, 1);  // ... made exclusive
+            if (lane == 0) run = INFINITY;
+            run = fmin(run, prior);
+            unsigned emitmask = 0u;
+#pragma unroll
+            for (int t = 0; t < kRunMax; ++t) {
+                const double v = nl[t];
+                if (t < cnt) {
+                    if (v != v) emitmask |= 1u << t;  // isClose(nan, x) is True: a NaN NLL is always appended (Q6)
+                    else if (v <= near_thr || v < run) emitmask |= 1u << t;
+                    run = fmin(run, v);
+                }
+            }
+            if (emitmask) {
+                n2_unrank<KT>(T_, r0, q);
+                for (int t = 0; t < cnt; ++t) {
+                    if ((emitmask >> t) & 1u) {
+                        double R[KT + 1], S1;
+                        bool z;
+                        n2_groups<KT>(T_, q, R, S1, z);
+                        SolveOut oc;
+                        n2_solve<KT + 1>(R, S1, z, kc, -1.0, oc, s_logtab);
+                        if (oc.nll != oc.nll) ++nan_nll;
+                        const unsigned long long slot = atomicAdd(&p.counters[3], 1ULL);
+                        if (slot < p.emit_cap) {
+                            theta_cand c;
+                            c.rank = r0 + t;
+                            c.nll = oc.nll;
+                            c.mu[0] = oc.mu;
+                            c.mu[1] = 1.0 - oc.mu;
+                            c.mu[2] = 0.0;
+                            c.status = oc.status;
+                            c.flags = oc.iters;
+                            p.emit[slot] = c;
+                        }
+                    }
+                    if (t + 1 < cnt) n2_next<KT>(T_, q);
+                }
+            }
+        } else if constexpr (!THETA_P1_REFINE) {
             double xprev = -1.0, xprev2 = -1.0;  // roots of the previous two columns (warm start)
             // pass 1 runs the same trip count in every lane so that the warp can pool its thresholds every 8
             // columns (candidates of the same stripe: the stripe is re-walked by pass 2 whenever it matters)
@@ -464,7 +537,7 @@ static int g_search_minb = -1;
 
 template <int KT, bool EMIT>
 static int launch_search(const theta_plan* plan, const SearchParams& sp, cudaStream_t st) {
-    if (EMIT) return launch_search_v<KT, EMIT, 6>(plan, sp, st);
+    if (EMIT) return launch_search_v<KT, EMIT, 4>(plan, sp, st);  // pass 2 is a few hundred warps: registers before occupancy
     if (g_search_minb < 0) {
         const char* e = getenv("THETA_SEARCH_MINB");
         g_search_minb = e ? atoi(e) : 0;
@@ -659,7 +732,7 @@ extern "C" void theta_plan_destroy(theta_plan* pl) {
     theta::dfree(pl->d_stripe_min); theta::dfree(pl->d_emit);
     theta::dfree(pl->d_list); theta::dfree(pl->d_prior);
     theta::hfree(pl->h_emit); theta::hfree(pl->h_ctr);
-    theta::dfree(pl->d_xblk); theta::hfree(pl->h_xblk);
+    theta::dfree(pl->d_xblk); theta::hfree(pl->h_xblk); theta::dfree(pl->d_fscratch);
     if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); cudaEventDestroy(pl->ev2); cudaEventDestroy(pl->ev3); }
     delete pl;
 }
@@ -806,19 +879,23 @@ __global__ void __launch_bounds__(1024) stripe_scan_kernel(const double* __restr
 // -- exactly theta_filter_records on this shard.  A record dropped here is dropped by the filter over the union as well
 // (its running minimum only gets lower with more shards in front), so the host is left with a linear pass over the
 // concatenated blocks.  Output block: the status words (kStEmitted := records kept) followed by the kept records in rank
-// order.  More than kFilterMax records (or than fit `cap`): the block is passed through unfiltered / flagged as overflow
-// through kStEmitted > cap, and the caller falls back to the host filter / a larger exchange slot.
+// order.  Up to kFilterMax records are sorted in shared memory; up to kFilterMaxGlobal (the whole 1.7e11-candidate space of
+// config #3 emits 4.7e4 per shard) in a global scratch area of the plan, still by this one block -- a millisecond next
+// to a search of seconds, and it keeps the exchange blocks small whatever the space.  More than that (or than fit
+// `cap`): the block is passed through unfiltered / flagged as overflow through kStEmitted > cap, and the caller falls
+// back to the host filter / a larger exchange slot.
 static constexpr int kFilterMax = 4096;
-static constexpr size_t kFilterSmem = (2 * sizeof(unsigned long long) + sizeof(unsigned short)) * kFilterMax;
+static constexpr int kFilterMaxGlobal = 1 << 16;
+static constexpr size_t kFilterSmem = (2 * sizeof(unsigned long long) + sizeof(unsigned int)) * kFilterMax;
+static constexpr size_t kFilterScratch = (2 * sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)kFilterMaxGlobal;
 static constexpr int kStEmittedWord = kCounters + 3;
 __global__ void __launch_bounds__(1024) records_filter_kernel(const theta_cand* __restrict__ emit, unsigned long long emit_cap,
                                                               const unsigned long long* __restrict__ status,
                                                               const double* __restrict__ gmin_dev, double prior_min, double margin,
-                                                              unsigned char* __restrict__ out, unsigned long long cap) {
+                                                              unsigned char* __restrict__ out, unsigned long long cap,
+                                                              unsigned char* scratch /* kFilterScratch bytes or NULL */,
+                                                              int smem_max /* kFilterMax; 0 forces the global path (tests) */) {
     extern __shared__ __align__(16) unsigned char fsm[];
-    unsigned long long* key = reinterpret_cast<unsigned long long*>(fsm);            // [kFilterMax] rank
-    double* val = reinterpret_cast<double*>(fsm + sizeof(unsigned long long) * kFilterMax);  // [kFilterMax] NLL in rank order
-    unsigned short* idx = reinterpret_cast<unsigned short*>(fsm + 2 * sizeof(unsigned long long) * kFilterMax);  // [kFilterMax]
     __shared__ double s_w[32];
     __shared__ unsigned int s_c[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -826,19 +903,25 @@ __global__ void __launch_bounds__(1024) records_filter_kernel(const theta_cand* 
     theta_cand* out_recs = reinterpret_cast<theta_cand*>(out + sizeof(unsigned long long) * kStatusWords);
     const unsigned long long n_raw = status[kStEmittedWord];
     const unsigned long long n_have = n_raw < emit_cap ? n_raw : emit_cap;
-    if (n_raw > emit_cap || n_have > (unsigned long long)kFilterMax) {
+    const bool in_smem = n_have <= (unsigned long long)smem_max;
+    if (n_raw > emit_cap || (!in_smem && (!scratch || n_have > (unsigned long long)kFilterMaxGlobal))) {
         // too many to sort here: hand over what fits, unfiltered, with the raw count (the caller's overflow / host-filter path)
         for (int i = tid; i < kStatusWords; i += 1024) out_status[i] = status[i];
         const unsigned long long ncopy = n_have < cap ? n_have : cap;
         for (unsigned long long i = tid; i < ncopy; i += 1024) out_recs[i] = emit[i];
         return;
     }
+    unsigned char* area = in_smem ? fsm : scratch;
+    const size_t amax = in_smem ? (size_t)kFilterMax : (size_t)kFilterMaxGlobal;
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(area);                        // [amax] rank
+    double* val = reinterpret_cast<double*>(area + sizeof(unsigned long long) * amax);            // [amax] NLL in rank order
+    unsigned int* idx = reinterpret_cast<unsigned int*>(area + 2 * sizeof(unsigned long long) * amax);  // [amax]
     const int n = (int)n_have;
     int P = 1;
     while (P < n) P <<= 1;
     for (int i = tid; i < P; i += 1024) {
         key[i] = i < n ? emit[i].rank : ~0ULL;
-        idx[i] = (unsigned short)i;
+        idx[i] = (unsigned int)i;
     }
     __syncthreads();
     for (int k = 2; k <= P; k <<= 1) {
@@ -850,7 +933,7 @@ __global__ void __launch_bounds__(1024) records_filter_kernel(const theta_cand* 
                     const unsigned long long a = key[i], b = key[l];
                     if ((a > b) == up) {
                         key[i] = b; key[l] = a;
-                        const unsigned short t = idx[i]; idx[i] = idx[l]; idx[l] = t;
+                        const unsigned int t = idx[i]; idx[i] = idx[l]; idx[l] = t;
                     }
                 }
             }
@@ -938,10 +1021,20 @@ static cudaError_t record_event(cudaEvent_t ev, cudaStream_t st) {
     return cudaEventRecord(ev, st);
 }
 
+// Test knobs, read at every search: THETA_FILTER_FORCE_GLOBAL=1 sorts every record block in the global scratch area;
+// THETA_FILTER_HOST=1 makes theta_search_n2_pass2_dev fetch the raw records and filter them on the host (the independent
+// reference of tests/test_gpu_n2.py::test_device_record_filter_equals_host_filter).
+static bool env_flag(const char* name) {
+    const char* e = getenv(name);
+    return e && e[0] == '1';
+}
+static int filter_smem_max() { return env_flag("THETA_FILTER_FORCE_GLOBAL") ? 0 : kFilterMax; }
+
 static int plan_events(theta_plan* pl) {
     if (!pl->ev0) {
         // (per device, once per plan and outside any stream capture: the first step of a plan always runs eagerly)
         THETA_CUDA(cudaFuncSetAttribute(records_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmem));
+        if (!pl->d_fscratch) THETA_CUDA(theta::dmalloc(&pl->d_fscratch, kFilterScratch));
         THETA_CUDA(cudaEventCreate(&pl->ev0)); THETA_CUDA(cudaEventCreate(&pl->ev1));
         THETA_CUDA(cudaEventCreate(&pl->ev2)); THETA_CUDA(cudaEventCreate(&pl->ev3));
     }
@@ -1065,7 +1158,7 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t stripes = pl->p1_stripes;
     const double margin = 2.5 * THETA_TIE_MARGIN;
-    size_t want = std::max<size_t>(1 << 14, pl->emit_cap);
+    size_t want = std::max<size_t>(kFilterMaxGlobal, pl->emit_cap);
     bool filtered = false;  // the records came back sorted and filtered by the device
     theta_cand* host = nullptr;
     size_t n_host = 0;
@@ -1110,7 +1203,7 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
             if (ea != cudaSuccess) { rc = cuda_fail(ea, "record block", __FILE__, __LINE__); break; }
         }
         records_filter_kernel<<<1, 1024, kFilterSmem, st>>>(pl->d_emit, pl->emit_cap, pl->d_counters, global_min_dev, prior_min, margin,
-                                                             pl->d_xblk, kXCap);
+                                                             pl->d_xblk, kXCap, pl->d_fscratch, filter_smem_max());
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(pl->h_xblk, pl->d_xblk, kHead + sizeof(theta_cand) * kSpecRecs, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -1123,7 +1216,7 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
         std::memcpy(&g, &ctr[kStGlobalMin], sizeof(double));
         pl->stats.n_rescanned = ctr[kStList];
         const unsigned long long kept = ctr[kCounters + 3];
-        if (kept <= kXCap) {
+        if (kept <= kXCap && !env_flag("THETA_FILTER_HOST")) {
             if (kept > kSpecRecs) {
                 e = cudaMemcpyAsync(pl->h_xblk + kHead + sizeof(theta_cand) * kSpecRecs, pl->d_xblk + kHead + sizeof(theta_cand) * kSpecRecs,
                                     sizeof(theta_cand) * (kept - kSpecRecs), cudaMemcpyDeviceToHost, st);
@@ -1194,7 +1287,7 @@ extern "C" int theta_search_n2_pass2_enqueue(theta_plan* pl, const double* globa
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t stripes = pl->p1_stripes;
     const double margin = 2.5 * THETA_TIE_MARGIN;
-    const size_t want = std::max<size_t>(std::max<size_t>(1 << 14, pl->emit_cap), cap);
+    const size_t want = std::max<size_t>(std::max<size_t>(kFilterMaxGlobal, pl->emit_cap), cap);
     if (want > pl->emit_cap) {
         theta::dfree(pl->d_emit); pl->d_emit = nullptr; pl->emit_cap = 0;
         THETA_CUDA(theta::dmalloc(&pl->d_emit, sizeof(theta_cand) * want));
@@ -1225,7 +1318,7 @@ extern "C" int theta_search_n2_pass2_enqueue(theta_plan* pl, const double* globa
     THETA_CUDA(record_event(pl->ev3, st));
     // status block + this shard's records, sorted by rank and filtered to what the fold replay needs, into the exchange block
     records_filter_kernel<<<1, 1024, kFilterSmem, st>>>(pl->d_emit, pl->emit_cap, pl->d_counters, global_min_dev, prior_min, margin,
-                                                         static_cast<unsigned char*>(out_dev), cap);
+                                                         static_cast<unsigned char*>(out_dev), cap, pl->d_fscratch, filter_smem_max());
     THETA_CUDA(cudaGetLastError());
     return THETA_OK;
 }

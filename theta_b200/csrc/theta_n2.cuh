@@ -159,6 +159,7 @@ struct theta_plan {
     theta_cand* d_emit = nullptr;
     unsigned char* d_xblk = nullptr;  // [status | filtered records] of the single-shard pass 2 (device) ...
     unsigned char* h_xblk = nullptr;  // ... and its pinned copy
+    unsigned char* d_fscratch = nullptr;  // records_filter_kernel: sort area for more records than fit shared memory
     size_t emit_cap = 0;
     double2* d_logtab = nullptr;  // fast_log table (theta_core.cuh)
     uint32_t* d_list = nullptr;   // pass-2 stripe list / per-stripe prior minima
