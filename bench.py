@@ -10,7 +10,8 @@ The scaling series is WEAK and uses ONE workload family at every N (including N=
 upper bounds widened by two copies (same r, rN, m, K=5 -> same cost per candidate; 4.196e8 candidates), first
 N x 25,251,156 ranks, cut into contiguous rank ranges -- 25,251,156 candidates (configs[1]'s count) per GPU per
 step.  The exact configs[1] space, the >=100x target shape and configs[2..4] are measured at every N too (`extra`,
-strong scaling).  The only communication is one ncclAllReduce(min) + one ncclAllGather of the records per step.
+strong scaling).  The only communication is one all-reduce(min) of a double + one all-gather of the filtered record blocks per step
+(remote stores over NVLink peer memory in two kernels of ours; ncclAllReduce / ncclAllGather as the fallback).
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   roofline         the streaming NLL kernel (theta_nll_tiles_n2) on tiles larger than L2, HBM-bound
@@ -318,7 +319,7 @@ def main():
     launches = [0]
 
     def step():
-        # per rank: search kernel, min reduction [, ncclAllReduce(min)], stripe scan, emit kernel [, ncclAllGather],
+        # per rank: search kernel, min reduction [, peer all-reduce(min)], stripe scan, emit kernel, record filter [, peer all-gather],
         # one host synchronisation; at N > 1 all of it inside ONE C call (theta_search_n2_dist)
         recs, g, _ = search.search_sharded(plan, begin, end, D, world, stream)
         launches[0] += 4
@@ -570,7 +571,7 @@ def main():
 
     if rank == 0:
         cfg = config_of(P, total, world)
-        cfg["sharding"] = ("contiguous rank ranges, %d per GPU; one ncclAllReduce(min) + one ncclAllGather of the records per step"
+        cfg["sharding"] = ("contiguous rank ranges, %d per GPU; one all-reduce(min) of a double + one all-gather of the device-filtered record blocks per step (NVLink peer-memory kernels, NCCL fallback)"
                            % ((total + world - 1) // world))
         cfg["l2_policy"] = ("search kernel streams nothing from HBM (tables in shared memory); the roofline kernel uses "
                             "tiles of %d MiB > L2" % (roof["tile_bytes"] >> 20 if roof else 0))

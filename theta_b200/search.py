@@ -142,8 +142,9 @@ def search_sharded(plan, begin, end, dist, world, stream=None):
     """The whole sharded search of one step.  Returns (records, global_min, n_solved): the records of all shards
     sorted by rank (a superset of what the fold replay needs), identical on every rank.
 
-    On GPUs (NCCL) the step is ONE C call per rank (theta_search_n2_dist): pass 1 -> ncclAllReduce(min) on the device
-    double -> stripe scan + pass 2 -> ncclAllGather of the status blocks and raw records -> one host wait.  The host
+    On GPUs the step is ONE C call per rank (theta_search_n2_dist): pass 1 -> all-reduce(min) on the device double ->
+    stripe scan + pass 2 + device record filter -> all-gather of the [status | records] blocks -> one host wait (both
+    collectives as remote stores over NVLink peer memory, NCCL as the fallback; a CUDA graph from the second step).  The host
     models of the tests and the gloo backend take the two-pass Python path below."""
     if dist is not None and hasattr(plan, "handle") and dist.get_backend() == "nccl":
         return comm_for(dist).search_n2(plan, begin, end, stream)
