@@ -322,7 +322,7 @@ def main():
         # per rank: search kernel, min reduction [, peer all-reduce(min)], stripe scan, emit kernel, record filter [, peer all-gather],
         # one host synchronisation; at N > 1 all of it inside ONE C call (theta_search_n2_dist)
         recs, g, _ = search.search_sharded(plan, begin, end, D, world, stream)
-        launches[0] += 4
+        launches[0] += 5 if world == 1 else 7  # search, min reduction, stripe scan, pass 2, record filter [+ peer all-reduce, peer all-gather]
         return recs, g
 
     def barrier():

@@ -255,6 +255,10 @@ void theta_comm_destroy(theta_comm* comm);
  * (or with THETA_EXCHANGE=nccl, or when the GPUs cannot map each other) the step uses ncclAllReduce / ncclAllGather. */
 int theta_comm_ipc_handle(theta_comm* comm, uint8_t* handle128);
 int theta_comm_open_peers(theta_comm* comm, const uint8_t* handles /* [world][128] */);
+/* Every rank must use the same exchange: query (enable < 0) this rank's state after theta_comm_open_peers, reduce it
+ * over the ranks with MIN, and set the agreed value (enable = 0 switches this rank to the NCCL collectives).  Returns
+ * the state after the call (1 = peer memory). */
+int theta_comm_peer_exchange(theta_comm* comm, int32_t enable);
 /* One sharded search step on this rank; every rank receives the union of the records, in enumeration order.
  * n=2: records = what the fold replay needs (theta_filter_records).  n=3: every candidate within `window` of the
  * global minimum (extra_min: NLL of the all-[tau,0,0] pseudo candidate, folded into the minimum), flags index

@@ -99,6 +99,7 @@ SYMBOLS = {
     "theta_comm_destroy": (None, [_VP]),
     "theta_comm_ipc_handle": (C.c_int, [_VP, _VP]),
     "theta_comm_open_peers": (C.c_int, [_VP, _VP]),
+    "theta_comm_peer_exchange": (C.c_int, [_VP, C.c_int32]),
     "theta_search_n2_dist": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_double), C.POINTER(C.c_uint64), _VP]),
     "theta_search_n3_dist": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint64, C.c_double, C.c_double, _VP, _VP, C.c_uint64,
@@ -509,6 +510,10 @@ class Comm(object):
         dist.all_gather_into_tensor(hs, torch.from_numpy(mine).to(dev))
         allh = np.ascontiguousarray(hs.cpu().numpy())
         check(load().theta_comm_open_peers(c._h, ptr(allh)))
+        # all ranks or none: a rank that could not map a peer sends everybody back to the NCCL collectives
+        ok = torch.tensor([load().theta_comm_peer_exchange(c._h, -1)], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        load().theta_comm_peer_exchange(c._h, int(ok.item()))
         return c
 
     def close(self):

@@ -250,6 +250,16 @@ extern "C" int theta_comm_open_peers(theta_comm* c, const uint8_t* handles /* [w
     return THETA_OK;
 }
 
+// Query (enable < 0) or set the peer-memory exchange of a communicator.  Every rank of a communicator must use the same
+// exchange (a rank on NCCL would wait for collectives its peers never post): after theta_comm_open_peers the launcher
+// reduces the ranks' answers with MIN and sets the agreed value.  Returns the state after the call (1 = peer memory).
+extern "C" int theta_comm_peer_exchange(theta_comm* c, int32_t enable) {
+    if (!c) return 0;
+    if (enable == 0) c->peer_ok = false;
+    // (enabling is only possible when this rank has mapped every peer: open_peers decides that)
+    return c->peer_ok ? 1 : 0;
+}
+
 extern "C" int theta_nccl_unique_id(uint8_t* id128) {
     if (!id128) { set_error("null argument"); return THETA_ERR_INVALID; }
     if (!nccl().ok) { set_error("libnccl.so.2 not found: multi-GPU search needs NCCL"); return THETA_ERR_UNSUPPORTED; }
