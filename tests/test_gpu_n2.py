@@ -461,3 +461,67 @@ def test_device_record_filter_equals_host_filter(lib, monkeypatch):
             assert np.all(np.diff(got["rank"].astype(np.int64)) > 0)
         monkeypatch.delenv("THETA_FILTER_FORCE_GLOBAL")
         plan.close()
+
+
+def test_search_equals_bruteforce_on_random_shapes(lib):
+    """The two-pass search (fp32-refined root-finder, fp32 NLL bound, device record filter) against the fold over EVERY
+    candidate solved from the cold start (theta_eval_ranks_n2), on randomised problems: tau 2 and 3, copy numbers up to
+    10, max_normal < 1 (roots at a bracket end, the generic solver path), intervals without tumour reads (NaN / None
+    candidates), tiny spaces and windows that start and end inside a stripe."""
+    from theta_b200.search import fold_replay
+    rng = np.random.default_rng(20261017)
+    n_cases = 0
+    for trial in range(60):
+        m = int(rng.integers(3, 28))
+        K = int(rng.integers(2, 11))
+        tau = int(rng.choice([2, 3]))
+        rN = rng.integers(2_000, 900_000, m)
+        c_true = np.sort(rng.integers(0, K + 1, m))
+        mu_true = rng.uniform(0.05, 0.95)
+        p = rN * (tau * mu_true + c_true * (1 - mu_true))
+        r = rng.multinomial(int(1.1 * rN.sum()), p / p.sum())
+        if trial % 7 == 3:
+            r[rng.integers(0, m)] = 0
+        order = np.argsort(r / rN, kind="stable")
+        r, rN, c_true = r[order], rN[order], np.sort(c_true)
+        lower = np.maximum(c_true - rng.integers(0, 3, m), 0)
+        upper = np.minimum(c_true + rng.integers(0, 3, m), K)
+        lower, upper = np.minimum.accumulate(lower[::-1])[::-1], np.maximum.accumulate(upper)
+        lower = np.minimum(lower, upper)
+        max_normal = 1.0 if trial % 5 else float(rng.uniform(0.3, 0.9))
+        try:
+            plan = lib.Plan(2, r.tolist(), rN.tolist(), lower.tolist(), upper.tolist(), tau=tau, max_normal=max_normal)
+        except lib.ThetaError:
+            continue
+        N = plan.count()
+        if N == 0 or N > 3_000_000:
+            plan.close()
+            continue
+        b = int(rng.integers(0, max(1, N // 3))) if trial % 2 else 0
+        e = N if trial % 3 else int(rng.integers(b + 1, N + 1))
+        g = plan.pass1(b, e)
+        recs = plan.pass2(g)
+        cands, _ = plan.eval_ranks(np.arange(b, e, dtype=np.uint64), want_vals=False)
+        ok = cands["status"] < 8
+        if not ok.any():
+            assert len(recs) == 0 and not np.isfinite(g)
+            plan.close()
+            continue
+        full = fold_replay(cands["rank"][ok], cands["nll"][ok], dup_first=False)
+        sub = fold_replay(recs["rank"], recs["nll"], dup_first=False)
+        want = [(int(cands["rank"][ok][i]), float(cands["mu"][ok][i][0]), float(cands["nll"][ok][i])) for i in full]
+        got = [(int(recs["rank"][i]), float(recs["mu"][i][0]), float(recs["nll"][i])) for i in sub]
+        assert [w[0] for w in want] == [x[0] for x in got], (trial, m, K, tau, max_normal, b, e)
+        for w_, g_ in zip(want, got):
+            if np.isnan(w_[2]):
+                assert np.isnan(g_[2])
+            else:
+                # records are the cold solve: the same root bit for bit; the NLL goes through the table logarithm in the
+                # search kernel and through libm log in theta_eval_ranks_n2 (1 ulp apart)
+                assert w_[1] == g_[1] and abs(w_[2] - g_[2]) <= 1e-13 * abs(w_[2])
+        finite = cands["nll"][ok][np.isfinite(cands["nll"][ok])]
+        if len(finite):
+            assert abs(g - finite.min()) <= 1e-12 * abs(g), (trial, g, finite.min())
+        n_cases += 1
+        plan.close()
+    assert n_cases >= 30

@@ -131,9 +131,10 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
             double nl[kRunMax];
             float xpf = -1.0f;  // previous root (phase 1 only steers the decision: the fp32-refined solver of pass 1 will do)
             double lanemin = INFINITY;
+            unsigned solvedmask = 0u;  // a None candidate is never emitted (not even when nothing is solved and near_thr = +inf)
 #pragma unroll
             for (int t = 0; t < kRunMax; ++t) {
-                nl[t] = INFINITY;  // a None candidate is never emitted
+                nl[t] = INFINITY;
                 if (t < cnt) {
                     double R[KT + 1], S1;
                     bool z;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
                     float xf;
                     if (n2_root_p1<KT + 1>(R, S1, z, kc, xpf, o, xf)) {
                         xpf = xf;
+                        solvedmask |= 1u << t;
                         nl[t] = n2_l2<KT + 1>(R, S1, o.mu, kc, s_logtab);
                         lanemin = fmin(lanemin, nl[t]);  // (fmin ignores a NaN NLL)
                     }
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kBlock, MINB) n2_search_kernel(const SearchPar
 #pragma unroll
             for (int t = 0; t < kRunMax; ++t) {
                 const double v = nl[t];
-                if (t < cnt) {
+                if ((solvedmask >> t) & 1u) {
                     if (v != v) emitmask |= 1u << t;  // isClose(nan, x) is True: a NaN NLL is always appended (Q6)
                     else if (v <= near_thr || v < run) emitmask |= 1u << t;
                     run = fmin(run, v);
