@@ -1030,6 +1030,13 @@ static bool env_flag(const char* name) {
     const char* e = getenv(name);
     return e && e[0] == '1';
 }
+// columns per lane in one pass-2 unit (<= kRunMax of the kernel): fewer = shorter dependent chain per lane (pass 2 is a few
+// hundred warps, i.e. latency), more = a longer exact prefix per unit (fewer records to filter).  THETA_P2_LRUN overrides.
+static int pass2_run_length() {
+    const char* e = getenv("THETA_P2_LRUN");
+    const int v = e ? atoi(e) : 2;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+}
 static int filter_smem_max() { return env_flag("THETA_FILTER_FORCE_GLOBAL") ? 0 : kFilterMax; }
 
 static int plan_events(theta_plan* pl) {
@@ -1182,7 +1189,7 @@ extern "C" int theta_search_n2_pass2_dev(theta_plan* pl, const double* global_mi
             sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
             sp.begin = pl->p1_begin; sp.end = pl->p1_end; sp.L = pl->p1_L; sp.n_items = (uint32_t)stripes;
             sp.n_items_dev = pl->d_counters + kStList;
-            sp.Lrun = std::min(pl->p1_L, 4); sp.units_per_item = (pl->p1_L + sp.Lrun - 1) / sp.Lrun;
+            sp.Lrun = std::min(pl->p1_L, pass2_run_length()); sp.units_per_item = (pl->p1_L + sp.Lrun - 1) / sp.Lrun;
             sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters + kCounters;
             sp.stripe_list = pl->d_list; sp.stripe_prior = pl->d_prior;
             sp.near_thr = 0.0; sp.near_thr_base = pl->d_counters + kStGlobalMin; sp.near_margin = margin;
@@ -1304,7 +1311,7 @@ extern "C" int theta_search_n2_pass2_enqueue(theta_plan* pl, const double* globa
         sp.tables = pl->d_tables; sp.layout = pl->layout; sp.kc = pl->kc; sp.logtab = pl->d_logtab;
         sp.begin = pl->p1_begin; sp.end = pl->p1_end; sp.L = pl->p1_L; sp.n_items = (uint32_t)stripes;
         sp.n_items_dev = pl->d_counters + kStList;
-        sp.Lrun = std::min(pl->p1_L, 4); sp.units_per_item = (pl->p1_L + sp.Lrun - 1) / sp.Lrun;
+        sp.Lrun = std::min(pl->p1_L, pass2_run_length()); sp.units_per_item = (pl->p1_L + sp.Lrun - 1) / sp.Lrun;
         sp.stripe_min = pl->d_stripe_min; sp.counters = pl->d_counters + kCounters;
         sp.stripe_list = pl->d_list; sp.stripe_prior = pl->d_prior;
         sp.near_thr = 0.0; sp.near_thr_base = pl->d_counters + kStGlobalMin; sp.near_margin = margin;
