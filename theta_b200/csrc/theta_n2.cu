@@ -536,16 +536,20 @@ static int launch_search_v(const theta_plan* plan, const SearchParams& sp, cudaS
 // THETA_SEARCH_MINB (tuning knob): resident CTAs per SM the pass-1 kernel is compiled for (6 -> 80 registers, 5 -> 96, 4 -> 128);
 // unset: chosen by the level count
 static int g_search_minb = -1;
-
-template <int KT, bool EMIT>
-static int launch_search(const theta_plan* plan, const SearchParams& sp, cudaStream_t st) {
-    if (EMIT) return launch_search_v<KT, EMIT, 4>(plan, sp, st);  // pass 2 is a few hundred warps: registers before occupancy
+static int search_minb(int KT) {
     if (g_search_minb < 0) {
         const char* e = getenv("THETA_SEARCH_MINB");
         g_search_minb = e ? atoi(e) : 0;
     }
+    const int v = g_search_minb ? g_search_minb : (KT <= 5 ? 5 : 6);
+    return v <= 4 ? 4 : (v == 5 ? 5 : 6);
+}
+
+template <int KT, bool EMIT>
+static int launch_search(const theta_plan* plan, const SearchParams& sp, cudaStream_t st) {
+    if (EMIT) return launch_search_v<KT, EMIT, 4>(plan, sp, st);  // pass 2 is a few hundred warps: registers before occupancy
     // measured on B200 (pass 1, m=150): K=5 0.555 ms at 5 CTAs/SM vs 0.562 at 6; K=7 14.0 ms at 5 vs 13.5 at 6
-    switch (g_search_minb ? g_search_minb : (KT <= 5 ? 5 : 6)) {
+    switch (search_minb(KT)) {
         case 4: return launch_search_v<KT, false, 4>(plan, sp, st);
         case 5: return launch_search_v<KT, false, 5>(plan, sp, st);
         default: return launch_search_v<KT, false, 6>(plan, sp, st);
@@ -1072,6 +1076,18 @@ extern "C" int theta_search_n2_pass1_begin(theta_plan* pl, uint64_t rank_begin, 
     const uint64_t target_stripes = (uint64_t)sm_count(pl->device) * 24 * (kBlock / 32);
     uint64_t L = N / (target_stripes * 32);
     L = std::max<uint64_t>(8, std::min<uint64_t>(L, 256));
+    if (L < 256) {
+        // a small space is only a handful of stripes per resident warp: pick the run length near L that minimises the columns
+        // the busiest warp walks, ceil(stripes / warps) * (L + 4) (config #2: L = 55 -> 14 348 stripes, 4.85 per warp; 54 -> 4.94)
+        const uint64_t warps = (uint64_t)sm_count(pl->device) * (uint64_t)search_minb(pl->KT) * (kBlock / 32);
+        uint64_t best_L = L, best_cost = ~0ull;
+        for (uint64_t c = L + 4; c + 12 >= L && c >= 8; --c) {
+            const uint64_t st_c = (N + c * 32 - 1) / (c * 32);
+            const uint64_t cost = ((st_c + warps - 1) / warps) * (c + 4);  // (+4: the probe and the cold first columns of a run)
+            if (cost < best_cost) { best_cost = cost; best_L = c; }
+        }
+        L = std::min<uint64_t>(best_L, 256);
+    }
     while ((N + L * 32 - 1) / (L * 32) > (1ull << 22)) L *= 2;
     pl->p1_L = (int)L; pl->p1_block = kBlock;
     const uint64_t stripes = (N + L * 32 - 1) / (L * 32);
