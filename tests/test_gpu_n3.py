@@ -173,6 +173,17 @@ def test_optimizer_and_enumerator_mirrors(lib, golden):
         else:
             assert np.abs(np.array(s[0]) - np.array(gold[i][1])).max() <= 1e-9
             assert abs(s[1] - gold[i][2]) <= 1e-10 * gold[i][2]
+    # the n=3 Enumerator walks the space in windows of work items: the WHOLE stream, with windows of ~64 candidates
+    class SmallBlocks(Enumerator):
+        BLOCK = 64
+    en_w = SmallBlocks(3, m, 3, 2, list(case["lower"]), list(case["upper"]), True)
+    keys = []
+    while True:
+        C = en_w.generate_next_C()
+        if C is False:
+            break
+        keys.append("".join("%d%d" % (int(a), int(b)) for a, b in C[:, 1:]))
+    assert keys == [g_[0] for g_ in gold]
     # n = 2 mirrors
     g2 = golden("n2_small_full.json")[3]
     en2 = Enumerator(2, g2["m"], g2["k"], 2, list(g2["lower"]), list(g2["upper"]))

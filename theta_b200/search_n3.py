@@ -181,29 +181,58 @@ def do_optimization_n3(m, k, tau, lower_bounds, upper_bounds, r, rN, sorted_inde
         plan.close()
 
 
-def dump_values_n3(plan, rows, path):
+def _item_windows(plan, n_items, leaves_per_window):
+    """Consecutive item ranges [b, e) holding about `leaves_per_window` candidates each (by the DP weights of the items),
+    in enumeration order: callers walk the space in bounded pieces instead of materialising it."""
+    w = plan.item_weights()
+    b = 0
+    while b < n_items:
+        e, acc = b, 0.0
+        while e < n_items and (e == b or acc + float(w[e]) <= leaves_per_window):
+            acc += float(w[e])
+            e += 1
+        yield b, e
+        b = e
+
+
+def dump_values_n3(plan, rows, path, leaves_per_window=1 << 18):
     """--GET_VALUES for n=3 (RunTHetA.py:188-215): one line per solved candidate of the stream the driver folds -- the
-    all-[tau,0,0] first matrix (Q2), then the candidates in enumeration order -- with column 1 of C, mu[0], likelihood."""
-    paths = plan.enumerate_n3()
-    paths = np.concatenate([np.zeros((1, plan.m), dtype=np.uint8), paths]) if len(paths) else np.zeros((1, plan.m), dtype=np.uint8)
-    mu, _, nll, st, _ = plan.solve_rows(paths, mode=1)
-    with open(path, "w") as f:
+    all-[tau,0,0] first matrix (Q2), then the candidates in enumeration order -- with column 1 of C, mu[0], likelihood.
+    The space is walked in windows of items, so the dump of a large space needs memory for one window only."""
+    n_items = plan.n_items if getattr(plan, "n_items", 0) else plan.prepare(1 << 12)
+
+    def lines(paths):
+        mu, _, nll, st, _ = plan.solve_rows(paths, mode=1)
         for i in range(len(paths)):
             if st[i] >= _lib.ST_NONE_SIGN:
                 continue
-            f.write("".join(str(rows[int(g)][0]) for g in paths[i]) + "\t" + str(np.float64(mu[i, 0])) + "\t" +
-                    str(np.float64(nll[i])) + "\n")
+            yield ("".join(str(rows[int(g)][0]) for g in paths[i]) + "\t" + str(np.float64(mu[i, 0])) + "\t" +
+                   str(np.float64(nll[i])) + "\n")
+
+    with open(path, "w") as f:
+        f.writelines(lines(np.zeros((1, plan.m), dtype=np.uint8)))
+        for b, e in _item_windows(plan, n_items, leaves_per_window):
+            paths = plan.enumerate_n3(b, e)
+            if len(paths):
+                f.writelines(lines(paths))
 
 
 def enumerator_next_n3(enum):
-    """Enumerator.generate_next_C for n=3 (python/Enumerator.py:74-87,172-223)."""
-    if getattr(enum, "_paths3", None) is None:
-        enum._plan.prepare(1 << 12)
-        enum._paths3 = enum._plan.enumerate_n3()
+    """Enumerator.generate_next_C for n=3 (python/Enumerator.py:74-87,172-223): candidates are produced on the GPU one
+    window of work items at a time (Enumerator.BLOCK candidates or so), never the whole space."""
+    if getattr(enum, "_rows3", None) is None:
+        enum._n_items3 = enum._plan.prepare(1 << 12)
+        enum._windows3 = _item_windows(enum._plan, enum._n_items3, enum.BLOCK)
         enum._rows3 = enum._plan.rows()
+        enum._paths3 = np.zeros((0, enum.m), dtype=np.uint8)
         enum._next = 0
-    if enum._next >= len(enum._paths3):
-        return False
+    while enum._next >= len(enum._paths3):
+        try:
+            b, e = next(enum._windows3)
+        except StopIteration:
+            return False
+        enum._paths3 = enum._plan.enumerate_n3(b, e)
+        enum._next = 0
     C = _matrix(enum._paths3[enum._next], enum._rows3, enum.tau, enum.m)
     enum._next += 1
     return C
