@@ -455,9 +455,12 @@ def main():
                 "ms_per_launch": t_nll, "tile_bytes": cnt * pitch, "check_max_rel_err_vs_solve": maxrel,
                 "note": "the north-star's NLL kernel; the kernel that binds the timed step is in roofline_search"}
         del tiles, mu, nll, stt
-        # ---- the kernel that binds the timed step: n2_search_kernel, FP64 pipe.  flops per candidate = 2 DFMA + DMUL +
-        # DADD executed (ncu smsp__sass_thread_inst_executed_op_d*_pred_on of the committed capture, profiles/
-        # search_flops.json) ; peak = DFMA microbenchmark on this GPU (theta_fp64_peak)
+        # ---- the kernel that binds the timed step: n2_search_kernel.  It streams nothing from HBM and (since round 2)
+        # runs one fp64 and one fp32 evaluation of the root-finder per candidate, so what binds it is INSTRUCTION ISSUE:
+        # achieved = warp instructions per launch (ncu smsp__inst_executed.sum of the committed capture of this very
+        # window, profiles/search_flops.json) / the event time measured here; peak = SMs x 4 schedulers x 1 instruction
+        # per cycle at the SM clock sampled during the run.  The fp64 view (2 DFMA + DMUL + DADD executed per candidate
+        # against the DFMA peak measured by theta_fp64_peak in this process) is kept next to it.
         fp64 = _lib.fp64_peak_gflops(stream)
         extra["fp64_peak_gflops_measured"] = fp64
         try:
@@ -465,14 +468,27 @@ def main():
                 sf = json.load(f)
             fl = float(sf["flops_per_candidate"])
             t_k = sum(p1_ms) / len(p1_ms) * 1e-3
-            ach_f = fl * (end - begin) / t_k / 1e9
+            n_k = int(end - begin)
+            ach_f = fl * n_k / t_k / 1e9
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+            issue_peak = sms * 4 * float(mhz) * 1e6 / 1e9                      # G warp-instructions / s
+            winst = float(sf["warp_inst_total"]) * n_k / float(sf["candidates"])  # warp instructions of one launch
+            ach_i = winst / t_k / 1e9
             roof_search = {"kernel": "n2_search_kernel<KT,false> (pass 1 of the timed step: %.0f %% of the step)"
                                      % (100.0 * (sum(p1_ms) / len(p1_ms)) / (ms_total / args.steps)),
-                           "bound": "fp64", "achieved": ach_f, "peak": fp64, "unit": "GFLOP/s", "frac": ach_f / fp64,
-                           "flops_per_candidate": fl, "flops_source": sf.get("source"),
-                           "ncu_sm__pipe_fp64_cycles_active_pct": sf.get("pipe_fp64_cycles_active_pct"),
-                           "candidates_per_launch": int(end - begin), "ms_per_launch": t_k * 1e3,
-                           "peak_source": "theta_fp64_peak: dependent-free DFMA streams, measured in this process"}
+                           "bound": "issue", "achieved": ach_i, "peak": issue_peak, "unit": "G warp-inst/s",
+                           "frac": ach_i / issue_peak,
+                           "warp_inst_per_candidate": winst / n_k, "inst_source": "ncu smsp__inst_executed.sum of one launch on "
+                           "this window (profiles/r2_search_flops.csv); ncu smsp__issue_active = %s %% of active cycles"
+                           % sf.get("issue_active_pct"),
+                           "peak_source": "%d SMs x 4 schedulers x %.0f MHz (SM clock sampled during the run)" % (sms, float(mhz)),
+                           "fp64": {"achieved": ach_f, "peak": fp64, "unit": "GFLOP/s", "frac": ach_f / fp64,
+                                    "flops_per_candidate": fl, "fp32_flops_per_candidate": sf.get("fp32_flops_per_candidate"),
+                                    "flops_source": sf.get("source"),
+                                    "ncu_sm__pipe_fp64_cycles_active_pct": sf.get("pipe_fp64_cycles_active_pct"),
+                                    "peak_source": "theta_fp64_peak: dependent-free DFMA streams, measured in this process"},
+                           "hbm_bytes_per_launch": 63488, "candidates_per_launch": n_k, "ms_per_launch": t_k * 1e3}
         except Exception:
             roof_search = None
     # search kernel own numbers (all ranks ran it; report rank 0's)
