@@ -268,8 +268,19 @@ def run_reference(args):
 
 
 def config_of(P, total, world):
+    """The `config` object of the JSON line -- the SAME dict in both arms (ours and --impl reference), so that the driver's
+    same-config check compares like with like.  `sharding` and `l2_policy` describe how our arm runs this workload."""
+    pitch = 8
+    while pitch < P["m"] or (pitch // 8) % 2 == 0:  # theta_tile_pitch: smallest 8 * odd >= m
+        pitch += 8
+    tile_mib = (min(int(total), 4 * 1024 * 1024) * pitch) >> 20
     return {"workload": P["desc"], "n": 2, "m": P["m"], "k": P["k"], "candidates": int(total),
-            "candidates_per_gpu": PER_GPU}
+            "candidates_per_gpu": PER_GPU,
+            "sharding": "contiguous rank ranges, %d per GPU; one all-reduce(min) of a double + one all-gather of the "
+                        "device-filtered record blocks per step (NVLink peer-memory kernels, NCCL fallback)"
+                        % ((int(total) + world - 1) // world),
+            "l2_policy": "search kernel streams nothing from HBM (tables in shared memory); the roofline kernel uses "
+                         "tiles of %d MiB > L2" % tile_mib}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -587,10 +598,6 @@ def main():
 
     if rank == 0:
         cfg = config_of(P, total, world)
-        cfg["sharding"] = ("contiguous rank ranges, %d per GPU; one all-reduce(min) of a double + one all-gather of the device-filtered record blocks per step (NVLink peer-memory kernels, NCCL fallback)"
-                           % ((total + world - 1) // world))
-        cfg["l2_policy"] = ("search kernel streams nothing from HBM (tables in shared memory); the roofline kernel uses "
-                            "tiles of %d MiB > L2" % (roof["tile_bytes"] >> 20 if roof else 0))
         line = {"metric": "C-candidates/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
