@@ -186,3 +186,22 @@ def test_rank_free_window_fold_equals_sequential_fold():
         idx = fold_replay(np.array(keep, dtype=np.uint64) + 1, nll[keep], dup_first=False)
         assert [keep[i] for i in idx] == want, (trial, window)
     assert widened > 50  # the widening path is exercised
+
+
+def test_bench_config_is_one_dict_for_both_arms():
+    """bench.py: the `config` object of the JSON line comes from ONE function for our arm and for --impl reference, names the
+    workload, the sharding and the L2 policy, and matches the committed bench line of the final tree."""
+    import json
+    import bench
+    P = bench.headline(1)
+    cfg = bench.config_of(P, bench.PER_GPU, 1)
+    assert cfg["candidates"] == cfg["candidates_per_gpu"] == 25251156 and cfg["n"] == 2 and cfg["m"] == 150 and cfg["k"] == 5
+    assert "workload" in cfg and "sharding" in cfg and "L2" in cfg["l2_policy"]
+    with open(os.path.join(ROOT, "profiles", "r2_bench_n1_final_noextra.json")) as f:
+        line = json.load(f)
+    assert line["config"] == cfg
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert key in line, key
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
