@@ -205,3 +205,73 @@ def test_bench_config_is_one_dict_for_both_arms():
         assert key in line, key
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+
+
+def test_two_pass_pipeline_model_equals_sequential_fold():
+    """Python model of the whole n=2 device pipeline against the sequential fold of the reference:
+    pass 1 reports per-stripe minima that are exact only where it matters (min <= T + 3e-3, T = the best exact NLL a warp has
+    seen in some earlier stripes -- modelled adversarially as the minimum over a random subset of the earlier stripes) and
+    over-estimates (up to +inf) elsewhere; the stripe scan lists record / near stripes; pass 2 emits, per unit of U
+    consecutive ranks, NaN | near-minimum | strict prefix minima w.r.t. the stripe's prior and the exact prefix of the unit;
+    every shard filters its records (prior = +inf); the union goes through theta_filter_records (host code of the library)
+    and the fold replay."""
+    import theta_oracle as O
+    from theta_b200 import _lib
+    from theta_b200.search import fold_replay, shard_range
+    rng = np.random.default_rng(11)
+    margin = 1e-3
+    for trial in range(150):
+        n = int(rng.integers(40, 3000))
+        steps = rng.choice([0.0, 3e-4, 6e-4, 1.1e-3, 0.5, 3.0, 40.0], size=n, p=[.25, .2, .15, .1, .1, .1, .1])
+        nll = 5e9 + np.cumsum(rng.choice([-1, 1], size=n) * steps)
+        if trial % 6 == 0:
+            nll[rng.integers(0, n, 2)] = np.nan
+        seq = O.fold([(0, float(nll[0]))] + [(i, float(v)) for i, v in enumerate(nll)])
+        S = int(rng.choice([16, 64, 100, 256]))  # stripe length
+        U = int(rng.choice([4, 32, 64]))         # pass-2 unit
+        for world in (1, 3):
+            blocks, mins = [], []
+            shards = [shard_range(n, rk, world) for rk in range(world)]
+            reported = []
+            for (b, e) in shards:  # ---- pass 1
+                rep = []
+                for s0 in range(b, e, S):
+                    v = nll[s0:min(e, s0 + S)]
+                    true_min = np.nanmin(v) if np.isfinite(v).any() else np.inf
+                    earlier = [np.nanmin(nll[t0:min(e, t0 + S)]) for t0 in range(b, s0, S) if np.isfinite(nll[t0:min(e, t0 + S)]).any()]
+                    seen = [x for x in earlier if rng.random() < 0.6]
+                    T = min(seen) if seen else np.inf
+                    if true_min <= T + 3 * margin:
+                        rep.append(true_min)
+                    else:
+                        rep.append(np.inf if rng.random() < 0.5 else true_min + rng.uniform(0, 50))
+                reported.append(rep)
+                mins.append(min(rep) if rep else np.inf)
+            g = min(mins)  # the all-reduce(min)
+            assert g == np.nanmin(nll)
+            any_nan = bool(np.isnan(nll).any())
+            for (b, e), rep in zip(shards, reported):  # ---- stripe scan + pass 2 + device filter, per shard
+                raw, P = [], np.inf
+                for si, s0 in enumerate(range(b, e, S)):
+                    x = rep[si]
+                    rec, near = x < P, x <= g + 2.5 * margin
+                    if rec or near or any_nan:
+                        prior = P if rec else -np.inf
+                        s1 = min(e, s0 + S)
+                        for u0 in range(s0, s1, U):
+                            run = prior
+                            for i in range(u0, min(s1, u0 + U)):
+                                v = nll[i]
+                                if v != v or v <= g + 2.5 * margin or v < run:
+                                    raw.append((i, v))
+                                if v < run:
+                                    run = v
+                    P = min(P, x)
+                rng.shuffle(raw)  # (emission order is arbitrary)
+                recs = np.zeros(len(raw), dtype=_lib.CAND_DTYPE)
+                recs["rank"] = [r_[0] for r_ in raw]
+                recs["nll"] = [r_[1] for r_ in raw]
+                blocks.append(_lib.filter_records(recs, g + 2.5 * margin))  # == records_filter_kernel (tested on the GPU)
+            allrecs = _lib.filter_records(np.concatenate(blocks), g + 2.5 * margin) if blocks else np.zeros(0, dtype=_lib.CAND_DTYPE)
+            got = [int(allrecs["rank"][i]) for i in fold_replay(allrecs["rank"], allrecs["nll"], dup_first=True)]
+            assert got == seq, (trial, world, S, U)
